@@ -1,0 +1,385 @@
+// K3/K7/K8/K9/K10: bf16 GEMM  C[M,N] = A[M,K] · W[N,K]^T  on the 5th-gen tensor cores.
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1 lane 0 : MMA issuer     (tcgen05.mma cta_group::1, M=128 x N=BLOCK_N x K=16, fp32 accum in TMEM,
+//                                   double-buffered accumulators so tile i+1's MMAs overlap tile i's epilogue)
+//   warps 2..5    : epilogue       (tcgen05.ld -> fused bias / GELU / residual / SwiGLU -> swizzled smem -> TMA store)
+// M, N, K tails are handled by TMA (zero fill on load, clipping on store).
+#include <stdio.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tma_host.h"
+
+namespace hb {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kEpiBarrier = 1;
+constexpr int kStagingBytes = BLOCK_M * 128;  // one 128-row x 128-byte chunk
+constexpr int kSmemBudget = 227 * 1024;
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int FIXED = 2 * kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int STAGES_RAW = (kSmemBudget - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 10 ? 10 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + FIXED;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mi, int& ni) {
+  constexpr int GM = 16;  // m-tiles swept together so concurrently-resident CTAs share W tiles in L2
+  const int per_group = GM * num_n;
+  const int g = t / per_group, r = t % per_group;
+  const int m_first = g * GM;
+  const int gm = min(GM, num_m - m_first);
+  mi = m_first + r % gm;
+  ni = r / gm;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
+               const bf16* __restrict__ bias, int M, int N, int K) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr bool kF32 = (EPI == EPI_F32);
+  constexpr bool kSwiGLU = (EPI == EPI_SWIGLU);
+  constexpr bool kResid = (EPI == EPI_RESID || EPI == EPI_BIAS_RESID);
+  constexpr bool kBias = (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID);
+  constexpr int OUT_BN = kSwiGLU ? BN / 2 : BN;          // output columns per tile
+  constexpr int CHUNK_COLS = kF32 ? 32 : 64;             // output columns per 128-byte staging row
+  constexpr int NCHUNK = (OUT_BN + CHUNK_COLS - 1) / CHUNK_COLS;
+  static_assert(!kSwiGLU || BN == 256, "SwiGLU epilogue expects [128 gate | 128 up] tiles");
+  static_assert(OUT_BN % 64 == 0, "tile width");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * C::A_BYTES;
+  uint8_t* staging = smem + STAGES * C::STAGE_BYTES;  // 2 x 16 KB, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
+  uint64_t* resid_bar = bars + 2 * STAGES + 4;  // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_c);
+    if (kResid) tma_prefetch_desc(&map_r);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    mbar_init(resid_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int mi, ni;
+        tile_coords(t, num_m, num_n, mi, ni);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          tma_load_2d(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, mi * BLOCK_M, kEvictNormal);
+          tma_load_2d(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K, ni * BN, kEvictNormal);
+          if (++s == STAGES) { s = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+      int s = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + s * C::A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + s * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + k * UMMA_K * 2);
+            umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above retire
+          if (++s == STAGES) { s = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;               // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;        // row within the 128-row tile == TMEM lane
+    const int epi_tid = threadIdx.x - 64;
+    const bool leader = (epi_tid == 0);
+    uint32_t resid_phase = 0;
+    int it = 0;
+    int chunk_ctr = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      int mi, ni;
+      tile_coords(t, num_m, num_n, mi, ni);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = mi * BLOCK_M;
+      const int n_out0 = ni * OUT_BN;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t t_tile = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c, ++chunk_ctr) {
+        uint8_t* buf = staging + (chunk_ctr & 1) * kStagingBytes;
+        uint8_t* my_row = buf + row * 128;
+        if (leader) {
+          tma_store_wait_read<1>();  // the store that last read `buf` (2 chunks ago) is done with smem
+          if (kResid) {
+            mbar_arrive_expect_tx(resid_bar, kStagingBytes);
+            tma_load_2d(buf, &map_r, resid_bar, n_out0 + c * CHUNK_COLS, m0, kEvictFirst);
+          }
+        }
+        bar_sync(kEpiBarrier, kEpiThreads);
+
+        if constexpr (kF32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_tile + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 o = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<uint4*>(my_row + ((j ^ (row & 7)) << 4)) = o;
+          }
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {  // two 32-column halves of the 64-column chunk
+            uint32_t v[32];
+            float f[32];
+            const int col = c * 64 + h * 32;  // output column within tile
+            tmem_ld_32x32b_x32(t_tile + col, v);
+            if constexpr (kSwiGLU) {
+              uint32_t u[32];
+              tmem_ld_32x32b_x32(t_tile + 128 + col, u);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = silu(__uint_as_float(v[j])) * __uint_as_float(u[j]);
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            }
+            if constexpr (kBias) {
+              const int nb = n_out0 + col;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int n = nb + j;
+                f[j] += (n < N) ? __bfloat162float(bias[n]) : 0.0f;
+              }
+            }
+            if constexpr (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            }
+            if constexpr (kResid) {
+              if (h == 0) {
+                mbar_wait(resid_bar, resid_phase);
+                resid_phase ^= 1;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(my_row + (((h * 4 + j) ^ (row & 7)) << 4));
+                const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y), r2 = unpack_bf16x2(rv.z),
+                             r3 = unpack_bf16x2(rv.w);
+                f[8 * j + 0] += r0.x; f[8 * j + 1] += r0.y; f[8 * j + 2] += r1.x; f[8 * j + 3] += r1.y;
+                f[8 * j + 4] += r2.x; f[8 * j + 5] += r2.y; f[8 * j + 6] += r3.x; f[8 * j + 7] += r3.y;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              *reinterpret_cast<uint4*>(my_row + (((h * 4 + j) ^ (row & 7)) << 4)) = o;
+            }
+          }
+        }
+        if (c == NCHUNK - 1) {
+          // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        fence_proxy_async_smem();
+        bar_sync(kEpiBarrier, kEpiThreads);
+        if (leader) {
+          tma_store_2d(&map_c, buf, n_out0 + c * CHUNK_COLS, m0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, int EPI>
+cudaError_t launch_cfg(cudaStream_t stream, const GemmArgs& g, int num_sms) {
+  using C = Cfg<BN>;
+  constexpr bool kF32 = (EPI == EPI_F32);
+  constexpr bool kSwiGLU = (EPI == EPI_SWIGLU);
+  CUtensorMap ma, mb, mc, mr;
+  const int n_out = kSwiGLU ? g.N / 2 : g.N;
+  if (!make_tmap_2d(&ma, g.A, TM_BF16, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, BLOCK_K, BLOCK_M)) return cudaErrorInvalidValue;
+  if (!make_tmap_2d(&mb, g.W, TM_BF16, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldw * 2, BLOCK_K, BN)) return cudaErrorInvalidValue;
+  if (kF32) {
+    if (!make_tmap_2d(&mc, g.C, TM_F32, (uint64_t)n_out, (uint64_t)g.M, (uint64_t)g.ldc * 4, 32, BLOCK_M)) return cudaErrorInvalidValue;
+  } else {
+    if (!make_tmap_2d(&mc, g.C, TM_BF16, (uint64_t)n_out, (uint64_t)g.M, (uint64_t)g.ldc * 2, 64, BLOCK_M)) return cudaErrorInvalidValue;
+  }
+  if (EPI == EPI_RESID || EPI == EPI_BIAS_RESID) {
+    if (!make_tmap_2d(&mr, g.R, TM_BF16, (uint64_t)n_out, (uint64_t)g.M, (uint64_t)g.ldr * 2, 64, BLOCK_M)) return cudaErrorInvalidValue;
+  } else {
+    mr = mc;
+  }
+  auto kern = gemm_tn_kernel<BN, EPI>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int num_m = (g.M + BLOCK_M - 1) / BLOCK_M, num_n = (g.N + BN - 1) / BN;
+  const int tiles = num_m * num_n;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, kNumThreads, C::SMEM, stream>>>(ma, mb, mc, mr, g.bias, g.M, g.N, g.K);
+  return cudaGetLastError();
+}
+
+template <int EPI>
+cudaError_t launch_epi(cudaStream_t stream, const GemmArgs& g, int num_sms) {
+  int bn = g.block_n;
+  if (bn == 0) {
+    // Fill the machine: prefer 256-wide tiles when there are at least ~2 waves of them.
+    const int num_m = (g.M + BLOCK_M - 1) / BLOCK_M;
+    bn = 256;
+    while (bn > 64 && (long)num_m * ((g.N + bn - 1) / bn) < 2L * num_sms) bn >>= 1;
+  }
+  switch (bn) {
+    case 256: return launch_cfg<256, EPI>(stream, g, num_sms);
+    case 128: return launch_cfg<128, EPI>(stream, g, num_sms);
+    case 64: return launch_cfg<64, EPI>(stream, g, num_sms);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace
+
+cudaError_t gemm_bf16_tn(cudaStream_t stream, const GemmArgs& g) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaErrorInvalidValue;
+  if ((g.K % 8) || (g.lda % 8) || (g.ldw % 8)) return cudaErrorInvalidValue;  // 16-byte TMA strides
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  switch (g.epi) {
+    case EPI_NONE: return launch_epi<EPI_NONE>(stream, g, num_sms);
+    case EPI_BIAS: return launch_epi<EPI_BIAS>(stream, g, num_sms);
+    case EPI_BIAS_GELU: return launch_epi<EPI_BIAS_GELU>(stream, g, num_sms);
+    case EPI_RESID: return launch_epi<EPI_RESID>(stream, g, num_sms);
+    case EPI_BIAS_RESID: return launch_epi<EPI_BIAS_RESID>(stream, g, num_sms);
+    case EPI_SWIGLU: {
+      if (g.N % 256) return cudaErrorInvalidValue;
+      GemmArgs h = g;
+      h.block_n = 256;
+      return launch_cfg<256, EPI_SWIGLU>(stream, h, num_sms);
+    }
+    case EPI_F32: return launch_epi<EPI_F32>(stream, g, num_sms);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------ test-only checker
+namespace {
+__global__ void gemm_naive_kernel(const bf16* A, int lda, const bf16* W, int ldw, void* C, int ldc, int M, int N, int K,
+                                  int f32) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) acc += __bfloat162float(A[(size_t)m * lda + k]) * __bfloat162float(W[(size_t)n * ldw + k]);
+  if (f32)
+    reinterpret_cast<float*>(C)[(size_t)m * ldc + n] = acc;
+  else
+    reinterpret_cast<bf16*>(C)[(size_t)m * ldc + n] = __float2bfloat16(acc);
+}
+}  // namespace
+
+cudaError_t gemm_naive_check(cudaStream_t stream, const GemmArgs& g) {
+  dim3 grid((g.N + 127) / 128, g.M);
+  gemm_naive_kernel<<<grid, 128, 0, stream>>>(g.A, g.lda, g.W, g.ldw, g.C, g.ldc, g.M, g.N, g.K, g.epi == EPI_F32);
+  return cudaGetLastError();
+}
+
+}  // namespace hb
