@@ -1,0 +1,162 @@
+// C ABI (include/helix_b200.h, include/helix_b200_kernels.h) over hb::Engine and the kernel launchers.
+#include <string.h>
+
+#include <string>
+
+#include "../../include/helix_b200.h"
+#include "../../include/helix_b200_kernels.h"
+#include "engine.h"
+#include "tma_host.h"
+
+using hb::Engine;
+
+struct hb_engine {
+  Engine impl;
+  explicit hb_engine(const hb_engine_cfg& c) : impl(c) {}
+};
+
+namespace {
+thread_local std::string g_last_create_error;
+thread_local std::string g_kernel_error;
+int kret(cudaError_t e) {
+  if (e != cudaSuccess) g_kernel_error = std::string(cudaGetErrorString(e)) + " [" + hb::tmap_last_error() + "]";
+  return (int)e;
+}
+}  // namespace
+
+extern "C" {
+
+int hb_abi_version(void) { return HB_ABI_VERSION; }
+
+int hb_engine_create(const hb_engine_cfg* cfg, hb_engine** out) {
+  if (!cfg || !out) {
+    g_last_create_error = "null argument";
+    return HB_ERR_INVALID;
+  }
+  hb_engine* e = new hb_engine(*cfg);
+  int rc = e->impl.init();
+  if (rc != HB_OK) {
+    g_last_create_error = e->impl.last_error();
+    delete e;
+    *out = nullptr;
+    return rc;
+  }
+  *out = e;
+  return HB_OK;
+}
+void hb_engine_destroy(hb_engine* e) { delete e; }
+const char* hb_last_error(hb_engine* e) { return e ? e->impl.last_error() : g_last_create_error.c_str(); }
+
+int hb_model_load_begin(hb_engine* e, const hb_model_desc* d) { return (e && d) ? e->impl.load_begin(*d) : HB_ERR_INVALID; }
+int hb_model_tensor_set(hb_engine* e, const char* name, const void* host, size_t n) {
+  return (e && name && host) ? e->impl.tensor_set(name, host, n) : HB_ERR_INVALID;
+}
+int hb_model_load_finish(hb_engine* e) { return e ? e->impl.load_finish() : HB_ERR_INVALID; }
+int hb_model_load_random(hb_engine* e, const hb_model_desc* d, uint64_t seed) {
+  return (e && d) ? e->impl.load_random(*d, seed) : HB_ERR_INVALID;
+}
+int hb_model_weights_arena(hb_engine* e, void** p, size_t* b) { return e ? e->impl.weights_arena(p, b) : HB_ERR_INVALID; }
+int hb_memory_estimate(const hb_model_desc* d, const hb_engine_cfg* c, uint64_t* w, uint64_t* kv, uint64_t* ws) {
+  if (!d || !c) return HB_ERR_INVALID;
+  if (!hb::validate_desc(*d).empty()) return HB_ERR_INVALID;
+  Engine::estimate(*d, *c, w, kv, ws);
+  return HB_OK;
+}
+
+int hb_engine_start(hb_engine* e) { return e ? e->impl.start() : HB_ERR_INVALID; }
+int hb_engine_stop(hb_engine* e) { return e ? e->impl.stop() : HB_ERR_INVALID; }
+int hb_step(hb_engine* e, int* did) { return e ? e->impl.step(did) : HB_ERR_INVALID; }
+int hb_submit(hb_engine* e, const int32_t* t, int32_t n, const hb_sampling* sp, uint64_t* id) {
+  return e ? e->impl.submit(t, n, sp, id) : HB_ERR_INVALID;
+}
+int hb_poll(hb_engine* e, uint64_t id, int32_t* out, int32_t cap, int32_t* n, int32_t* fin) {
+  return e ? e->impl.poll(id, out, cap, n, fin) : HB_ERR_INVALID;
+}
+int hb_wait(hb_engine* e, uint64_t id, int32_t ms) { return e ? e->impl.wait(id, ms) : HB_ERR_INVALID; }
+int hb_cancel(hb_engine* e, uint64_t id) { return e ? e->impl.cancel(id) : HB_ERR_INVALID; }
+int hb_release(hb_engine* e, uint64_t id) { return e ? e->impl.release(id) : HB_ERR_INVALID; }
+int hb_captured_logits(hb_engine* e, uint64_t id, int32_t which, float* out, size_t cap, int32_t* rows) {
+  return e ? e->impl.captured(id, which, out, cap, rows) : HB_ERR_INVALID;
+}
+int hb_embed(hb_engine* e, const int32_t* t, const int32_t* off, int32_t n, float* out) {
+  return e ? e->impl.embed(t, off, n, out) : HB_ERR_INVALID;
+}
+int hb_get_stats(hb_engine* e, hb_stats* s) { return e ? e->impl.stats(s) : HB_ERR_INVALID; }
+
+// ------------------------------------------------------------------ kernel-level ABI
+int hbk_init(void) { return kret(hb::kernels_init()); }
+const char* hbk_last_error(void) { return g_kernel_error.c_str(); }
+
+int hbk_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, const void* R, int ldr, const void* bias,
+             int M, int N, int K, int epi, int block_n) {
+  hb::GemmArgs g{(const hb::bf16*)A, lda, (const hb::bf16*)W, ldw, C, ldc, (const hb::bf16*)R, ldr,
+                 (const hb::bf16*)bias, M, N, K, (hb::Epi)epi, block_n};
+  return kret(hb::gemm_bf16_tn(0, g));
+}
+int hbk_gemm_naive(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K) {
+  hb::GemmArgs g{(const hb::bf16*)A, lda, (const hb::bf16*)W, ldw, C, ldc, nullptr, 0, nullptr, M, N, K, hb::EPI_F32, 0};
+  return kret(hb::gemm_naive_check(0, g));
+}
+int hbk_embed_gather(const int32_t* tokens, const void* table, void* x, int T, int H) {
+  return kret(hb::embed_gather(0, tokens, (const hb::bf16*)table, (hb::bf16*)x, T, H));
+}
+int hbk_bert_embed_ln(const int32_t* tokens, const int32_t* positions, const void* word, const void* pos,
+                      const void* type0, const void* gamma, const void* beta, void* x, int T, int H, float eps) {
+  return kret(hb::bert_embed_ln(0, tokens, positions, (const hb::bf16*)word, (const hb::bf16*)pos,
+                                (const hb::bf16*)type0, (const hb::bf16*)gamma, (const hb::bf16*)beta, (hb::bf16*)x, T, H,
+                                eps));
+}
+int hbk_rmsnorm(const void* x, const void* w, void* out, const int32_t* row_index, int rows, int H, float eps) {
+  return kret(hb::rmsnorm(0, (const hb::bf16*)x, (const hb::bf16*)w, (hb::bf16*)out, row_index, rows, H, eps));
+}
+int hbk_layernorm(const void* x, const void* g, const void* b, void* out, int rows, int H, float eps) {
+  return kret(hb::layernorm(0, (const hb::bf16*)x, (const hb::bf16*)g, (const hb::bf16*)b, (hb::bf16*)out, rows, H, eps));
+}
+int hbk_rope_kv_write(void* qkv, const int32_t* positions, const int32_t* slot_mapping, const float* inv_freq,
+                      void* k_cache, void* v_cache, int T, int Hq, int Hkv, int D, int page_size) {
+  return kret(hb::rope_kv_write(0, (hb::bf16*)qkv, positions, slot_mapping, inv_freq, (hb::bf16*)k_cache,
+                                (hb::bf16*)v_cache, T, Hq, Hkv, D, page_size));
+}
+int hbk_sample(const float* logits, int ldl, const float* temperature, const uint64_t* seed, int32_t* out, int B, int V) {
+  return kret(hb::sample_tokens(0, logits, ldl, temperature, seed, out, B, V));
+}
+int hbk_cls_pool_l2(const void* x, const int32_t* first_row, float* out, int B, int H) {
+  return kret(hb::cls_pool_l2(0, (const hb::bf16*)x, first_row, out, B, H));
+}
+static hb::AttnPrefillArgs mk_prefill(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
+                                      int ldo, const int32_t* cu, int B, int T, int max_seqlen, int Hq, int Hkv, int D,
+                                      int causal, float scale) {
+  hb::AttnPrefillArgs a{};
+  a.q = (const hb::bf16*)q; a.ldq = ldq;
+  a.k = (const hb::bf16*)k; a.ldk = ldk;
+  a.v = (const hb::bf16*)v; a.ldv = ldv;
+  a.out = (hb::bf16*)out; a.ldo = ldo;
+  a.cu_seqlens = cu;
+  a.B = B; a.T = T; a.max_seqlen = max_seqlen;
+  a.Hq = Hq; a.Hkv = Hkv; a.D = D; a.causal = causal; a.scale = scale;
+  return a;
+}
+int hbk_attn_prefill(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                     const int32_t* cu, int B, int T, int max_seqlen, int Hq, int Hkv, int D, int causal, float scale) {
+  return kret(hb::attn_prefill(0, mk_prefill(q, ldq, k, ldk, v, ldv, out, ldo, cu, B, T, max_seqlen, Hq, Hkv, D, causal, scale)));
+}
+int hbk_attn_naive(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, float* out, int ldo,
+                   const int32_t* cu, int B, int T, int max_seqlen, int Hq, int Hkv, int D, int causal, float scale) {
+  return kret(hb::attn_naive_check(0, mk_prefill(q, ldq, k, ldk, v, ldv, nullptr, ldo, cu, B, T, max_seqlen, Hq, Hkv, D, causal, scale), out));
+}
+int hbk_attn_decode(const void* q, int ldq, const void* k_cache, const void* v_cache, const int32_t* page_table,
+                    int max_pages, const int32_t* ctx_lens, void* out, int ldo, float* workspace, int B, int Hq, int Hkv,
+                    int D, int page_size, int num_splits, float scale) {
+  hb::AttnDecodeArgs a{};
+  a.q = (const hb::bf16*)q; a.ldq = ldq;
+  a.k_cache = (const hb::bf16*)k_cache; a.v_cache = (const hb::bf16*)v_cache;
+  a.page_table = page_table; a.max_pages = max_pages; a.ctx_lens = ctx_lens;
+  a.out = (hb::bf16*)out; a.ldo = ldo; a.workspace = workspace;
+  a.B = B; a.Hq = Hq; a.Hkv = Hkv; a.D = D; a.page_size = page_size; a.num_splits = num_splits; a.scale = scale;
+  return kret(hb::attn_decode(0, a));
+}
+size_t hbk_attn_decode_workspace_floats(int B, int Hq, int D, int num_splits) {
+  return hb::attn_decode_workspace_floats(B, Hq, D, num_splits);
+}
+
+}  // extern "C"

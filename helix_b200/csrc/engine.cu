@@ -1,0 +1,889 @@
+#include "engine.h"
+
+#include "tma_host.h"
+
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+
+namespace hb {
+
+namespace {
+
+size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+size_t al16(size_t x) { return (x + 15) & ~size_t(15); }
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// uniform in [-a, a] with a = sqrt(3)*std  (std 0.02 like the HF initializer_range)
+__global__ void fill_random_kernel(bf16* p, size_t n, uint64_t seed, float amp) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t h = mix64(seed ^ (i * 0xD1B54A32D192ED03ull));
+    const float u = (float)(h >> 40) * (1.0f / 16777216.0f) * 2.0f - 1.0f;
+    p[i] = __float2bfloat16(u * amp);
+  }
+}
+__global__ void fill_const_kernel(bf16* p, size_t n, float v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = __float2bfloat16(v);
+}
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+#define CU(expr)                                         \
+  do {                                                   \
+    cudaError_t e_ = (expr);                             \
+    if (e_ != cudaSuccess) return fail_cuda(e_, #expr);  \
+  } while (0)
+#define LAUNCH(expr)                                     \
+  do {                                                   \
+    cudaError_t e_ = (expr);                             \
+    launches_.fetch_add(1, std::memory_order_relaxed);   \
+    if (e_ != cudaSuccess) return fail_cuda(e_, #expr);  \
+  } while (0)
+
+Engine::Engine(const hb_engine_cfg& cfg) : cfg_(cfg) {
+  if (cfg_.max_seqs <= 0) cfg_.max_seqs = 256;
+  if (cfg_.max_ctx <= 0) cfg_.max_ctx = 8192;
+  if (cfg_.max_batched_tokens <= 0) cfg_.max_batched_tokens = 16384;
+  if (cfg_.kv_page_size <= 0) cfg_.kv_page_size = 64;
+  page_ = cfg_.kv_page_size;
+}
+
+Engine::~Engine() {
+  stop();
+  free_all();
+  if (stream_) {
+    cudaSetDevice(cfg_.device);
+    cudaStreamDestroy(stream_);
+  }
+}
+
+int Engine::fail(int code, const std::string& msg) {
+  std::lock_guard<std::mutex> g(err_mu_);
+  last_error_ = msg;
+  return code;
+}
+int Engine::fail_cuda(cudaError_t e, const char* what) {
+  cuda_error_.store((int)e);
+  return fail(HB_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " [" +
+                               std::string(tmap_last_error()) + "]");
+}
+const char* Engine::last_error() {
+  std::lock_guard<std::mutex> g(err_mu_);
+  return last_error_.c_str();
+}
+
+int Engine::init() {
+  if (page_ != 64) return fail(HB_ERR_INVALID, "kv_page_size must be 64");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(HB_ERR_CUDA, "no CUDA device available (this runtime has no CPU fallback)");
+  if (cfg_.device < 0 || cfg_.device >= n) return fail(HB_ERR_INVALID, "device ordinal out of range");
+  CU(cudaSetDevice(cfg_.device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg_.device));
+  if (prop.major != 10) return fail(HB_ERR_CUDA, "device is not sm_100 (Blackwell B200); kernels are sm_100a-only");
+  CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  CU(kernels_init());  // max-dynamic-smem attributes for every instantiation (never inside a graph capture)
+  return HB_OK;
+}
+
+void Engine::free_all() {
+  if (cfg_.device >= 0) cudaSetDevice(cfg_.device);
+  for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+  graphs_.clear();
+  auto fr = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  fr(model_.arena);
+  fr(model_.inv_freq);
+  fr(kv_);
+  fr(ws_);
+  fr(d_step_);
+  fr(all_logits_);
+  fr(d_embed_out_);
+  auto frh = [](auto*& p) {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+  };
+  frh(h_step_);
+  frh(h_sampled_);
+  frh(h_logits_);
+  frh(h_embed_out_);
+  loaded_ = false;
+  load_open_ = false;
+}
+
+// ------------------------------------------------------------------ sizing
+size_t Engine::workspace_bytes() const {
+  const hb_model_desc& d = model_.d;
+  const size_t T = t_cap_, H = d.hidden;
+  size_t b = 0;
+  b += 2 * al256(T * H * 2);                                  // x, xn
+  b += al256(T * (size_t)model_.qkv_cols() * 2);              // qkv
+  b += al256(T * (size_t)d.heads * d.head_dim * 2);           // attn
+  b += al256(T * (size_t)d.ffn * 2);                          // h
+  if (d.arch == HB_ARCH_LLAMA) {
+    b += al256((size_t)cfg_.max_seqs * d.vocab * 4);          // logits
+    b += al256(attn_decode_workspace_floats(cfg_.max_seqs, d.heads, d.head_dim, 16) * 4);
+    b += al256((size_t)cfg_.max_seqs * 4);                    // sampled
+  }
+  return b;
+}
+
+void Engine::estimate(const hb_model_desc& d, const hb_engine_cfg& c_in, uint64_t* w, uint64_t* kv, uint64_t* ws) {
+  Engine tmp(c_in);
+  tmp.model_.d = d;
+  tmp.t_cap_ = tmp.cfg_.max_batched_tokens;
+  if (w) *w = arena_bytes_for(d);
+  if (ws) *ws = tmp.workspace_bytes();
+  if (kv) {
+    if (d.arch == HB_ARCH_LLAMA) {
+      const uint64_t pages_per_seq = (tmp.cfg_.max_ctx + 63) / 64;
+      const uint64_t page_bytes = (uint64_t)d.layers * 2 * d.kv_heads * 64 * d.head_dim * 2;
+      *kv = (uint64_t)tmp.cfg_.max_seqs * pages_per_seq * page_bytes;
+    } else {
+      *kv = 0;
+    }
+  }
+}
+
+StepLayout Engine::layout(int T, int B) const {
+  StepLayout L;
+  size_t o = 0;
+  L.tokens = o; o = al16(o + 4 * (size_t)T);
+  L.positions = o; o = al16(o + 4 * (size_t)T);
+  L.slots = o; o = al16(o + 4 * (size_t)T);
+  L.cu = o; o = al16(o + 4 * (size_t)(B + 1));
+  L.last = o; o = al16(o + 4 * (size_t)B);
+  L.ctx = o; o = al16(o + 4 * (size_t)B);
+  L.pt = o; o = al16(o + 4 * (size_t)B * max_pages_per_seq_);
+  L.temp = o; o = al16(o + 4 * (size_t)B);
+  L.seed = o; o = al16(o + 8 * (size_t)B);
+  L.total = o;
+  return L;
+}
+
+// ------------------------------------------------------------------ model load
+int Engine::load_begin(const hb_model_desc& d) {
+  std::lock_guard<std::mutex> g(gpu_mu_);
+  if (loaded_ || load_open_) return fail(HB_ERR_STATE, "model already loaded on this engine");
+  const std::string why = validate_desc(d);
+  if (!why.empty()) return fail(HB_ERR_INVALID, "unsupported model description: " + why);
+  CU(cudaSetDevice(cfg_.device));
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  budget_ = cfg_.memory_budget_bytes ? cfg_.memory_budget_bytes : (free_b > (1ull << 30) ? free_b - (1ull << 30) : free_b);
+  model_.d = d;
+  model_.arena_bytes = arena_bytes_for(d);
+  if (model_.arena_bytes > budget_) return fail(HB_ERR_OOM, "weights alone exceed the memory budget");
+  if (model_.arena_bytes > free_b) return fail(HB_ERR_OOM, "weights exceed free device memory");
+  CU(cudaMalloc(&model_.arena, model_.arena_bytes));
+  layout_model(model_);
+  load_open_ = true;
+  return HB_OK;
+}
+
+int Engine::tensor_set(const char* name, const void* host, size_t n) {
+  std::lock_guard<std::mutex> g(gpu_mu_);
+  if (!load_open_) return fail(HB_ERR_STATE, "hb_model_tensor_set outside load_begin/finish");
+  auto it = model_.placements.find(name);
+  if (it == model_.placements.end()) return fail(HB_ERR_NOT_FOUND, std::string("unknown tensor name: ") + name);
+  const Placement& p = it->second;
+  if (n != p.rows * p.cols) return fail(HB_ERR_INVALID, std::string("tensor size mismatch for ") + name);
+  CU(cudaSetDevice(cfg_.device));
+  if (p.mode == 0) {
+    CU(cudaMemcpy(p.dst, host, n * 2, cudaMemcpyHostToDevice));
+  } else {
+    // gate (mode 1) / up (mode 2) rows interleaved per 128-row block: block t -> rows [t*256 + (mode-1)*128, +128)
+    const size_t blocks = p.rows / 128;
+    const bf16* src = static_cast<const bf16*>(host);
+    for (size_t t = 0; t < blocks; ++t) {
+      bf16* dst = p.dst + (t * 256 + (p.mode - 1) * 128) * p.cols;
+      CU(cudaMemcpyAsync(dst, src + t * 128 * p.cols, 128 * p.cols * 2, cudaMemcpyHostToDevice, stream_));
+    }
+    CU(cudaStreamSynchronize(stream_));
+  }
+  model_.filled[name] = true;
+  return HB_OK;
+}
+
+int Engine::alloc_runtime() {
+  const hb_model_desc& d = model_.d;
+  t_cap_ = cfg_.max_batched_tokens;
+  if (d.arch == HB_ARCH_BERT && cfg_.max_ctx > d.max_pos) cfg_.max_ctx = d.max_pos;
+  if (t_cap_ < cfg_.max_ctx) t_cap_ = cfg_.max_ctx;  // a whole prompt must fit one prefill step
+  b_cap_ = std::max(cfg_.max_seqs, d.arch == HB_ARCH_BERT ? 4096 : cfg_.max_seqs);
+  max_pages_per_seq_ = (cfg_.max_ctx + page_ - 1) / page_;
+
+  ws_bytes_ = workspace_bytes();
+  CU(cudaMalloc(&ws_, ws_bytes_));
+  uint8_t* p = ws_;
+  auto take = [&](size_t bytes) {
+    uint8_t* r = p;
+    p += al256(bytes);
+    return r;
+  };
+  const size_t T = t_cap_, H = d.hidden;
+  x_ = (bf16*)take(T * H * 2);
+  xn_ = (bf16*)take(T * H * 2);
+  qkv_ = (bf16*)take(T * (size_t)model_.qkv_cols() * 2);
+  attn_ = (bf16*)take(T * (size_t)d.heads * d.head_dim * 2);
+  h_ = (bf16*)take(T * (size_t)d.ffn * 2);
+  if (d.arch == HB_ARCH_LLAMA) {
+    logits_ = (float*)take((size_t)cfg_.max_seqs * d.vocab * 4);
+    dec_ws_ = (float*)take(attn_decode_workspace_floats(cfg_.max_seqs, d.heads, d.head_dim, 16) * 4);
+    sampled_ = (int32_t*)take((size_t)cfg_.max_seqs * 4);
+  }
+  step_bytes_ = layout(t_cap_, b_cap_).total;
+  CU(cudaMalloc(&d_step_, step_bytes_));
+  CU(cudaMallocHost(&h_step_, step_bytes_));
+  CU(cudaMallocHost(&h_sampled_, (size_t)b_cap_ * 4));
+
+  if (d.arch == HB_ARCH_LLAMA) {
+    const std::vector<float> f = rope_inv_freq(d);
+    CU(cudaMalloc(&model_.inv_freq, f.size() * 4));
+    CU(cudaMemcpy(model_.inv_freq, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+    // KV pool: whatever the budget leaves, capped at max_seqs full-length sequences
+    const uint64_t page_bytes = (uint64_t)d.layers * 2 * d.kv_heads * page_ * d.head_dim * 2;
+    const uint64_t used = model_.arena_bytes + ws_bytes_ + step_bytes_;
+    if (used >= budget_) return fail(HB_ERR_OOM, "weights + workspace exceed the memory budget");
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t avail = std::min<uint64_t>(budget_ - used, free_b > (256ull << 20) ? free_b - (256ull << 20) : 0);
+    uint64_t pages = avail / page_bytes;
+    const uint64_t want = (uint64_t)cfg_.max_seqs * max_pages_per_seq_;
+    if (pages > want) pages = want;
+    if (pages < (uint64_t)max_pages_per_seq_)
+      return fail(HB_ERR_OOM, "memory budget leaves no room for one full-context sequence of KV cache");
+    num_pages_ = (int)pages;
+    kv_bytes_ = pages * page_bytes;
+    CU(cudaMalloc(&kv_, kv_bytes_));
+    free_pages_.resize(num_pages_);
+    for (int i = 0; i < num_pages_; ++i) free_pages_[i] = num_pages_ - 1 - i;  // pop_back hands out page 0 first
+  } else {
+    CU(cudaMalloc(&d_embed_out_, (size_t)b_cap_ * H * 4));
+    CU(cudaMallocHost(&h_embed_out_, (size_t)b_cap_ * H * 4));
+  }
+  return HB_OK;
+}
+
+int Engine::load_finish() {
+  std::lock_guard<std::mutex> g(gpu_mu_);
+  if (!load_open_) return fail(HB_ERR_STATE, "hb_model_load_finish without load_begin");
+  for (auto& kv : model_.placements)
+    if (!model_.filled.count(kv.first)) return fail(HB_ERR_STATE, "tensor never uploaded: " + kv.first);
+  CU(cudaSetDevice(cfg_.device));
+  int rc = alloc_runtime();
+  if (rc != HB_OK) return rc;
+  load_open_ = false;
+  loaded_ = true;
+  return HB_OK;
+}
+
+int Engine::load_random(const hb_model_desc& d, uint64_t seed) {
+  int rc = load_begin(d);
+  if (rc != HB_OK) return rc;
+  std::lock_guard<std::mutex> g(gpu_mu_);
+  CU(cudaSetDevice(cfg_.device));
+  const size_t n = model_.arena_bytes / 2;
+  fill_random_kernel<<<148 * 8, 256, 0, stream_>>>(model_.arena, n, seed, 0.02f * 1.7320508f);
+  CU(cudaGetLastError());
+  for (auto& kv : model_.placements) {
+    const Placement& p = kv.second;
+    if (p.is_norm_gain) {
+      fill_const_kernel<<<8, 256, 0, stream_>>>(p.dst, p.rows * p.cols, 1.0f);
+      CU(cudaGetLastError());
+    }
+    model_.filled[kv.first] = true;
+  }
+  CU(cudaStreamSynchronize(stream_));
+  int rc2 = alloc_runtime();
+  if (rc2 != HB_OK) return rc2;
+  load_open_ = false;
+  loaded_ = true;
+  return HB_OK;
+}
+
+int Engine::weights_arena(void** p, size_t* bytes) {
+  if (!model_.arena) return fail(HB_ERR_STATE, "no model arena");
+  if (p) *p = model_.arena;
+  if (bytes) *bytes = model_.arena_bytes;
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------ forward passes
+int Engine::decode_splits(int B) const {
+  const int ctas = B * model_.d.kv_heads;
+  int s = (148 * 4 + ctas - 1) / ctas;
+  return std::max(1, std::min(16, s));
+}
+
+int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits) {
+  const hb_model_desc& d = model_.d;
+  const int H = d.hidden, D = d.head_dim, QD = d.heads * D, KD = d.kv_heads * D, QKV = model_.qkv_cols(), F = d.ffn;
+  const int32_t* tokens = (const int32_t*)(d_step_ + L.tokens);
+  const int32_t* positions = (const int32_t*)(d_step_ + L.positions);
+  const int32_t* slots = (const int32_t*)(d_step_ + L.slots);
+  const int32_t* cu = (const int32_t*)(d_step_ + L.cu);
+  const int32_t* last = (const int32_t*)(d_step_ + L.last);
+  const int32_t* ctx = (const int32_t*)(d_step_ + L.ctx);
+  const int32_t* pt = (const int32_t*)(d_step_ + L.pt);
+  const float* temp = (const float*)(d_step_ + L.temp);
+  const uint64_t* seed = (const uint64_t*)(d_step_ + L.seed);
+  const size_t layer_kv = (size_t)num_pages_ * d.kv_heads * page_ * D;  // elements per K (or V) plane
+
+  LAUNCH(embed_gather(stream_, tokens, model_.embed, x_, T, H));
+  for (int l = 0; l < d.layers; ++l) {
+    const LlamaLayerW& w = model_.ll[l];
+    bf16* kc = kv_ + (size_t)l * 2 * layer_kv;
+    bf16* vc = kc + layer_kv;
+    LAUNCH(rmsnorm(stream_, x_, w.attn_norm, xn_, nullptr, T, H, d.norm_eps));
+    {
+      GemmArgs g{xn_, H, w.wqkv, H, qkv_, QKV, nullptr, 0, nullptr, T, QKV, H, EPI_NONE, 0};
+      LAUNCH(gemm_bf16_tn(stream_, g));
+    }
+    LAUNCH(rope_kv_write(stream_, qkv_, positions, slots, model_.inv_freq, kc, vc, T, d.heads, d.kv_heads, D, page_));
+    if (prefill) {
+      AttnPrefillArgs a{};
+      a.q = qkv_; a.ldq = QKV;
+      a.k = qkv_ + QD; a.ldk = QKV;
+      a.v = qkv_ + QD + KD; a.ldv = QKV;
+      a.out = attn_; a.ldo = QD;
+      a.cu_seqlens = cu;
+      a.B = B; a.T = T; a.max_seqlen = max_seqlen;
+      a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D;
+      a.causal = 1;
+      a.scale = 1.0f / sqrtf((float)D);
+      LAUNCH(attn_prefill(stream_, a));
+    } else {
+      AttnDecodeArgs a{};
+      a.q = qkv_; a.ldq = QKV;
+      a.k_cache = kc; a.v_cache = vc;
+      a.page_table = pt; a.max_pages = max_pages_per_seq_;
+      a.ctx_lens = ctx;
+      a.out = attn_; a.ldo = QD;
+      a.workspace = dec_ws_;
+      a.B = B; a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D; a.page_size = page_;
+      a.num_splits = decode_splits(B);
+      a.scale = 1.0f / sqrtf((float)D);
+      LAUNCH(attn_decode(stream_, a));
+      launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel
+    }
+    {
+      GemmArgs g{attn_, QD, w.wo, QD, x_, H, x_, H, nullptr, T, H, QD, EPI_RESID, 0};
+      LAUNCH(gemm_bf16_tn(stream_, g));
+    }
+    LAUNCH(rmsnorm(stream_, x_, w.mlp_norm, xn_, nullptr, T, H, d.norm_eps));
+    {
+      GemmArgs g{xn_, H, w.wgu, H, h_, F, nullptr, 0, nullptr, T, 2 * F, H, EPI_SWIGLU, 256};
+      LAUNCH(gemm_bf16_tn(stream_, g));
+    }
+    {
+      GemmArgs g{h_, F, w.wdown, F, x_, H, x_, H, nullptr, T, H, F, EPI_RESID, 0};
+      LAUNCH(gemm_bf16_tn(stream_, g));
+    }
+  }
+  if (all_logits) {
+    LAUNCH(rmsnorm(stream_, x_, model_.final_norm, xn_, nullptr, T, H, d.norm_eps));
+    GemmArgs g{xn_, H, model_.lm_head, H, all_logits_, d.vocab, nullptr, 0, nullptr, T, d.vocab, H, EPI_F32, 0};
+    LAUNCH(gemm_bf16_tn(stream_, g));
+  }
+  // last position of every sequence -> final norm -> LM head -> sample
+  LAUNCH(rmsnorm(stream_, x_, model_.final_norm, h_, last, B, H, d.norm_eps));
+  {
+    GemmArgs g{h_, H, model_.lm_head, H, logits_, d.vocab, nullptr, 0, nullptr, B, d.vocab, H, EPI_F32, 0};
+    LAUNCH(gemm_bf16_tn(stream_, g));
+  }
+  LAUNCH(sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab));
+  return HB_OK;
+}
+
+int Engine::forward_bert(int T, int B, int max_seqlen, const StepLayout& L, float* d_out) {
+  const hb_model_desc& d = model_.d;
+  const int H = d.hidden, D = d.head_dim, F = d.ffn;
+  const int32_t* tokens = (const int32_t*)(d_step_ + L.tokens);
+  const int32_t* positions = (const int32_t*)(d_step_ + L.positions);
+  const int32_t* cu = (const int32_t*)(d_step_ + L.cu);
+  LAUNCH(bert_embed_ln(stream_, tokens, positions, model_.word, model_.pos, model_.type, model_.emb_ln_g,
+                       model_.emb_ln_b, x_, T, H, d.norm_eps));
+  for (int l = 0; l < d.layers; ++l) {
+    const BertLayerW& w = model_.bl[l];
+    {
+      GemmArgs g{x_, H, w.wqkv, H, qkv_, 3 * H, nullptr, 0, w.bqkv, T, 3 * H, H, EPI_BIAS, 0};
+      LAUNCH(gemm_bf16_tn(stream_, g));
+    }
+    {
+      AttnPrefillArgs a{};
+      a.q = qkv_; a.ldq = 3 * H;
+      a.k = qkv_ + H; a.ldk = 3 * H;
+      a.v = qkv_ + 2 * H; a.ldv = 3 * H;
+      a.out = attn_; a.ldo = H;
+      a.cu_seqlens = cu;
+      a.B = B; a.T = T; a.max_seqlen = max_seqlen;
+      a.Hq = d.heads; a.Hkv = d.heads; a.D = D;
+      a.causal = 0;
+      a.scale = 1.0f / sqrtf((float)D);
+      LAUNCH(attn_prefill(stream_, a));
+    }
+    {
+      GemmArgs g{attn_, H, w.wo, H, xn_, H, x_, H, w.bo, T, H, H, EPI_BIAS_RESID, 0};
+      LAUNCH(gemm_bf16_tn(stream_, g));
+    }
+    LAUNCH(layernorm(stream_, xn_, w.ln1_g, w.ln1_b, x_, T, H, d.norm_eps));
+    {
+      GemmArgs g{x_, H, w.w1, H, h_, F, nullptr, 0, w.b1, T, F, H, EPI_BIAS_GELU, 0};
+      LAUNCH(gemm_bf16_tn(stream_, g));
+    }
+    {
+      GemmArgs g{h_, F, w.w2, F, xn_, H, x_, H, w.b2, T, H, F, EPI_BIAS_RESID, 0};
+      LAUNCH(gemm_bf16_tn(stream_, g));
+    }
+    LAUNCH(layernorm(stream_, xn_, w.ln2_g, w.ln2_b, x_, T, H, d.norm_eps));
+  }
+  LAUNCH(cls_pool_l2(stream_, x_, cu, d_out, B, H));
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------ scheduling
+void Engine::finish_request(Request* r, ReqState st) {
+  // mu_ held
+  for (int32_t pg : r->pages) free_pages_.push_back(pg);
+  r->pages.clear();
+  r->state = st;
+}
+
+int Engine::submit(const int32_t* toks, int n, const hb_sampling* sp, uint64_t* id) {
+  if (!loaded_) return fail(HB_ERR_STATE, "hb_submit before a model is loaded");
+  if (model_.d.arch != HB_ARCH_LLAMA) return fail(HB_ERR_INVALID, "hb_submit needs a decoder model");
+  if (!toks || n <= 0 || !sp || !id) return fail(HB_ERR_INVALID, "null/empty argument");
+  if (n >= cfg_.max_ctx) return fail(HB_ERR_INVALID, "prompt does not fit context_length");
+  if (n > t_cap_) return fail(HB_ERR_INVALID, "prompt longer than max_batched_tokens");
+  for (int i = 0; i < n; ++i)
+    if (toks[i] < 0 || toks[i] >= model_.d.vocab) return fail(HB_ERR_INVALID, "token id out of range");
+  auto r = std::make_unique<Request>();
+  r->prompt.assign(toks, toks + n);
+  r->sp = *sp;
+  if (r->sp.max_tokens < 1) r->sp.max_tokens = 1;
+  if (n + r->sp.max_tokens > cfg_.max_ctx) r->sp.max_tokens = cfg_.max_ctx - n;
+  std::lock_guard<std::mutex> g(mu_);
+  if ((int)waiting_.size() >= 65536) return fail(HB_ERR_BUSY, "queue full");
+  r->id = next_id_++;
+  *id = r->id;
+  waiting_.push_back(r.get());
+  reqs_[r->id] = std::move(r);
+  cv_work_.notify_one();
+  return HB_OK;
+}
+
+int Engine::poll(uint64_t id, int32_t* out, int cap, int* n_out, int* finished) {
+  std::lock_guard<std::mutex> g(mu_);
+  auto it = reqs_.find(id);
+  if (it == reqs_.end()) return fail(HB_ERR_NOT_FOUND, "unknown request id");
+  Request* r = it->second.get();
+  int n = 0;
+  while (r->polled < r->out.size() && n < cap) out[n++] = r->out[r->polled++];
+  if (n_out) *n_out = n;
+  const bool done = r->state == ReqState::FINISHED || r->state == ReqState::CANCELLED || r->state == ReqState::FAILED;
+  if (finished) *finished = (done && r->polled == r->out.size()) ? (r->state == ReqState::FINISHED ? 1 : 2) : 0;
+  return HB_OK;
+}
+
+int Engine::wait(uint64_t id, int timeout_ms) {
+  std::unique_lock<std::mutex> g(mu_);
+  auto it = reqs_.find(id);
+  if (it == reqs_.end()) return fail(HB_ERR_NOT_FOUND, "unknown request id");
+  Request* r = it->second.get();
+  auto ready = [&] {
+    return r->polled < r->out.size() || r->state == ReqState::FINISHED || r->state == ReqState::CANCELLED ||
+           r->state == ReqState::FAILED;
+  };
+  if (timeout_ms < 0)
+    cv_out_.wait(g, ready);
+  else
+    cv_out_.wait_for(g, std::chrono::milliseconds(timeout_ms), ready);
+  return ready() ? HB_OK : HB_ERR_BUSY;
+}
+
+int Engine::cancel(uint64_t id) {
+  std::lock_guard<std::mutex> g(mu_);
+  auto it = reqs_.find(id);
+  if (it == reqs_.end()) return fail(HB_ERR_NOT_FOUND, "unknown request id");
+  Request* r = it->second.get();
+  if (r->state == ReqState::WAITING) {
+    waiting_.erase(std::remove(waiting_.begin(), waiting_.end(), r), waiting_.end());
+    finish_request(r, ReqState::CANCELLED);
+    cv_out_.notify_all();
+  } else if (r->state == ReqState::RUNNING) {
+    r->cancel_flag = true;  // the step loop retires it at the next step boundary
+  }
+  return HB_OK;
+}
+
+int Engine::release(uint64_t id) {
+  std::lock_guard<std::mutex> g(mu_);
+  auto it = reqs_.find(id);
+  if (it == reqs_.end()) return fail(HB_ERR_NOT_FOUND, "unknown request id");
+  Request* r = it->second.get();
+  if (r->state == ReqState::WAITING || r->state == ReqState::RUNNING)
+    return fail(HB_ERR_STATE, "request still active; cancel it first");
+  reqs_.erase(it);
+  return HB_OK;
+}
+
+int Engine::captured(uint64_t id, int which, float* out, size_t cap, int* rows) {
+  std::lock_guard<std::mutex> g(mu_);
+  auto it = reqs_.find(id);
+  if (it == reqs_.end()) return fail(HB_ERR_NOT_FOUND, "unknown request id");
+  const std::vector<float>& v = (which == HB_CAPTURE_PROMPT_LOGITS) ? it->second->prompt_logits : it->second->step_logits;
+  if (rows) *rows = (int)(v.size() / model_.d.vocab);
+  if (out) {
+    if (cap < v.size()) return fail(HB_ERR_INVALID, "capture buffer too small");
+    memcpy(out, v.data(), v.size() * 4);
+  }
+  return HB_OK;
+}
+
+int Engine::run_prefill(std::vector<Request*>& batch) {
+  const hb_model_desc& d = model_.d;
+  const int B = (int)batch.size();
+  int T = 0, max_len = 0;
+  bool want_all = false;
+  for (Request* r : batch) {
+    T += (int)r->prompt.size();
+    max_len = std::max(max_len, (int)r->prompt.size());
+    want_all |= (r->sp.capture & HB_CAPTURE_PROMPT_LOGITS) != 0;
+  }
+  if (want_all) {
+    if (T > 4096) return fail(HB_ERR_INVALID, "HB_CAPTURE_PROMPT_LOGITS limited to 4096 prompt tokens per step");
+    if (all_logits_rows_ < T) {
+      if (all_logits_) cudaFree(all_logits_);
+      all_logits_ = nullptr;
+      CU(cudaMalloc(&all_logits_, (size_t)T * d.vocab * 4));
+      all_logits_rows_ = T;
+    }
+  }
+  const StepLayout L = layout(T, B);
+  int32_t* tok = (int32_t*)(h_step_ + L.tokens);
+  int32_t* pos = (int32_t*)(h_step_ + L.positions);
+  int32_t* slot = (int32_t*)(h_step_ + L.slots);
+  int32_t* cu = (int32_t*)(h_step_ + L.cu);
+  int32_t* last = (int32_t*)(h_step_ + L.last);
+  float* temp = (float*)(h_step_ + L.temp);
+  uint64_t* seed = (uint64_t*)(h_step_ + L.seed);
+  int t = 0;
+  for (int i = 0; i < B; ++i) {
+    Request* r = batch[i];
+    cu[i] = t;
+    const int n = (int)r->prompt.size();
+    for (int j = 0; j < n; ++j, ++t) {
+      tok[t] = r->prompt[j];
+      pos[t] = j;
+      slot[t] = r->pages[j / page_] * page_ + j % page_;
+    }
+    last[i] = t - 1;
+    temp[i] = r->sp.temperature;
+    seed[i] = r->sp.seed * 0x9E3779B97F4A7C15ull + 0;
+  }
+  cu[B] = t;
+  CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
+  int rc = forward_llama(T, B, true, max_len, L, want_all);
+  if (rc != HB_OK) return rc;
+  CU(cudaMemcpyAsync(h_sampled_, sampled_, (size_t)B * 4, cudaMemcpyDeviceToHost, stream_));
+  CU(cudaStreamSynchronize(stream_));
+  steps_prefill_++;
+  tok_prefill_ += T;
+  // captures (test tap; synchronous copies are fine here)
+  for (int i = 0; i < B; ++i) {
+    Request* r = batch[i];
+    if (r->sp.capture & HB_CAPTURE_PROMPT_LOGITS) {
+      const int n = (int)r->prompt.size();
+      r->prompt_logits.resize((size_t)n * d.vocab);
+      CU(cudaMemcpy(r->prompt_logits.data(), all_logits_ + (size_t)cu[i] * d.vocab, (size_t)n * d.vocab * 4,
+                    cudaMemcpyDeviceToHost));
+    }
+    if (r->sp.capture & HB_CAPTURE_STEP_LOGITS) {
+      const size_t o = r->step_logits.size();
+      r->step_logits.resize(o + d.vocab);
+      CU(cudaMemcpy(r->step_logits.data() + o, logits_ + (size_t)i * d.vocab, (size_t)d.vocab * 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  return HB_OK;
+}
+
+int Engine::run_decode(std::vector<Request*>& batch) {
+  const hb_model_desc& d = model_.d;
+  const int B = (int)batch.size();
+  const StepLayout L = layout(B, B);
+  int32_t* tok = (int32_t*)(h_step_ + L.tokens);
+  int32_t* pos = (int32_t*)(h_step_ + L.positions);
+  int32_t* slot = (int32_t*)(h_step_ + L.slots);
+  int32_t* cu = (int32_t*)(h_step_ + L.cu);
+  int32_t* last = (int32_t*)(h_step_ + L.last);
+  int32_t* ctx = (int32_t*)(h_step_ + L.ctx);
+  int32_t* pt = (int32_t*)(h_step_ + L.pt);
+  float* temp = (float*)(h_step_ + L.temp);
+  uint64_t* seed = (uint64_t*)(h_step_ + L.seed);
+  for (int i = 0; i < B; ++i) {
+    Request* r = batch[i];
+    const int p = r->kv_len;
+    tok[i] = r->out.back();
+    pos[i] = p;
+    slot[i] = r->pages[p / page_] * page_ + p % page_;
+    cu[i] = i;
+    last[i] = i;
+    ctx[i] = p + 1;
+    const int np = (p + 1 + page_ - 1) / page_;
+    for (int j = 0; j < np; ++j) pt[(size_t)i * max_pages_per_seq_ + j] = r->pages[j];
+    temp[i] = r->sp.temperature;
+    seed[i] = r->sp.seed * 0x9E3779B97F4A7C15ull + (uint64_t)r->out.size();
+  }
+  cu[B] = B;
+  CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
+  if (cfg_.use_cuda_graphs) {
+    auto it = graphs_.find(B);
+    if (it == graphs_.end()) {
+      cudaGraph_t graph = nullptr;
+      const uint64_t l0 = launches_.load();
+      CU(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+      int rc = forward_llama(B, B, false, 1, L, false);
+      cudaError_t ce = cudaStreamEndCapture(stream_, &graph);
+      graph_kernels_[B] = launches_.load() - l0;
+      launches_.store(l0);  // captured, not executed
+      if (rc != HB_OK) return rc;
+      if (ce != cudaSuccess) return fail_cuda(ce, "cudaStreamEndCapture");
+      cudaGraphExec_t exec = nullptr;
+      CU(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      it = graphs_.emplace(B, exec).first;
+    }
+    CU(cudaGraphLaunch(it->second, stream_));
+    graph_launches_++;
+    launches_.fetch_add(graph_kernels_[B]);
+  } else {
+    int rc = forward_llama(B, B, false, 1, L, false);
+    if (rc != HB_OK) return rc;
+  }
+  CU(cudaMemcpyAsync(h_sampled_, sampled_, (size_t)B * 4, cudaMemcpyDeviceToHost, stream_));
+  CU(cudaStreamSynchronize(stream_));
+  steps_decode_++;
+  tok_decode_ += B;
+  for (int i = 0; i < B; ++i) {
+    Request* r = batch[i];
+    if (r->sp.capture & HB_CAPTURE_STEP_LOGITS) {
+      const size_t o = r->step_logits.size();
+      r->step_logits.resize(o + d.vocab);
+      CU(cudaMemcpy(r->step_logits.data() + o, logits_ + (size_t)i * d.vocab, (size_t)d.vocab * 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  return HB_OK;
+}
+
+int Engine::step(int* did_work) {
+  if (did_work) *did_work = 0;
+  if (!loaded_) return fail(HB_ERR_STATE, "hb_step before a model is loaded");
+  if (model_.d.arch != HB_ARCH_LLAMA) return HB_OK;
+  if (cuda_error_.load()) return fail(HB_ERR_CUDA, "engine is in a sticky CUDA error state");
+  std::lock_guard<std::mutex> gg(gpu_mu_);
+  CU(cudaSetDevice(cfg_.device));
+  std::vector<Request*> batch;
+  bool prefill = false;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    // retire cancelled sequences
+    for (size_t i = 0; i < running_.size();) {
+      if (running_[i]->cancel_flag) {
+        finish_request(running_[i], ReqState::CANCELLED);
+        running_.erase(running_.begin() + i);
+        cv_out_.notify_all();
+      } else {
+        ++i;
+      }
+    }
+    // admission: FIFO, whole prompts, pages for prompt + max_tokens reserved up front (no preemption)
+    int T = 0;
+    while (!waiting_.empty()) {
+      Request* r = waiting_.front();
+      const int n = (int)r->prompt.size();
+      const int need = (n + r->sp.max_tokens + page_ - 1) / page_;
+      if ((int)(running_.size() + batch.size()) >= cfg_.max_seqs) break;
+      if ((int)free_pages_.size() < need) break;
+      if (T + n > t_cap_) break;
+      for (int i = 0; i < need; ++i) {
+        r->pages.push_back(free_pages_.back());
+        free_pages_.pop_back();
+      }
+      waiting_.pop_front();
+      batch.push_back(r);
+      T += n;
+    }
+    if (!batch.empty()) {
+      prefill = true;
+    } else {
+      batch = running_;
+    }
+  }
+  if (batch.empty()) return HB_OK;
+  int rc = prefill ? run_prefill(batch) : run_decode(batch);
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    if (rc != HB_OK) {
+      for (Request* r : batch) {
+        if (!prefill) running_.erase(std::remove(running_.begin(), running_.end(), r), running_.end());
+        finish_request(r, ReqState::FAILED);
+      }
+      cv_out_.notify_all();
+      return rc;
+    }
+    for (int i = 0; i < (int)batch.size(); ++i) {
+      Request* r = batch[i];
+      const int32_t t = h_sampled_[i];
+      if (prefill) {
+        r->kv_len = (int)r->prompt.size();
+        r->state = ReqState::RUNNING;
+        running_.push_back(r);
+      } else {
+        r->kv_len += 1;
+      }
+      r->out.push_back(t);
+      const bool done = (int)r->out.size() >= r->sp.max_tokens || (r->sp.eos_token >= 0 && t == r->sp.eos_token) ||
+                        r->kv_len + 1 >= cfg_.max_ctx;
+      if (done) {
+        running_.erase(std::remove(running_.begin(), running_.end(), r), running_.end());
+        finish_request(r, ReqState::FINISHED);
+      }
+    }
+    cv_out_.notify_all();
+  }
+  if (did_work) *did_work = 1;
+  return HB_OK;
+}
+
+void Engine::loop() {
+  while (!stop_.load()) {
+    {
+      std::unique_lock<std::mutex> g(mu_);
+      cv_work_.wait_for(g, std::chrono::milliseconds(50),
+                        [&] { return stop_.load() || !waiting_.empty() || !running_.empty(); });
+      if (stop_.load()) break;
+      if (waiting_.empty() && running_.empty()) continue;
+    }
+    int did = 0;
+    int rc = step(&did);
+    if (rc != HB_OK && rc != HB_ERR_STATE) {
+      // sticky CUDA failure: fail everything still queued so callers do not hang
+      std::lock_guard<std::mutex> g(mu_);
+      for (Request* r : waiting_) finish_request(r, ReqState::FAILED);
+      waiting_.clear();
+      for (Request* r : running_) finish_request(r, ReqState::FAILED);
+      running_.clear();
+      cv_out_.notify_all();
+      if (rc == HB_ERR_CUDA) break;
+    }
+    if (!did) std::this_thread::sleep_for(std::chrono::microseconds(200));  // admission blocked (no pages / slots)
+  }
+}
+
+int Engine::start() {
+  if (!loaded_) return fail(HB_ERR_STATE, "hb_engine_start before a model is loaded");
+  if (thread_running_) return HB_OK;
+  stop_.store(false);
+  thread_ = std::thread([this] { loop(); });
+  thread_running_ = true;
+  return HB_OK;
+}
+
+int Engine::stop() {
+  if (!thread_running_) return HB_OK;
+  stop_.store(true);
+  cv_work_.notify_all();
+  if (thread_.joinable()) thread_.join();
+  thread_running_ = false;
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------ embeddings (BERT-style encoders)
+int Engine::embed(const int32_t* toks, const int32_t* offsets, int nseq, float* out) {
+  if (!loaded_) return fail(HB_ERR_STATE, "hb_embed before a model is loaded");
+  if (model_.d.arch != HB_ARCH_BERT) return fail(HB_ERR_INVALID, "hb_embed needs an encoder model");
+  if (nseq < 0 || (nseq > 0 && (!toks || !offsets || !out))) return fail(HB_ERR_INVALID, "null argument");
+  if (cuda_error_.load()) return fail(HB_ERR_CUDA, "engine is in a sticky CUDA error state");
+  const hb_model_desc& d = model_.d;
+  for (int i = 0; i < nseq; ++i) {
+    const int n = offsets[i + 1] - offsets[i];
+    if (n <= 0) return fail(HB_ERR_INVALID, "empty sequence");
+    if (n > cfg_.max_ctx || n > d.max_pos) return fail(HB_ERR_INVALID, "sequence longer than the model's positions");
+  }
+  for (int i = (nseq ? offsets[0] : 0); i < (nseq ? offsets[nseq] : 0); ++i)
+    if (toks[i] < 0 || toks[i] >= d.vocab) return fail(HB_ERR_INVALID, "token id out of range");
+  std::lock_guard<std::mutex> gg(gpu_mu_);
+  CU(cudaSetDevice(cfg_.device));
+  int s0 = 0;
+  while (s0 < nseq) {
+    int s1 = s0, T = 0, max_len = 0;
+    while (s1 < nseq && s1 - s0 < b_cap_) {
+      const int n = offsets[s1 + 1] - offsets[s1];
+      if (T + n > t_cap_) break;
+      T += n;
+      max_len = std::max(max_len, n);
+      ++s1;
+    }
+    const int B = s1 - s0;
+    const StepLayout L = layout(T, B);
+    int32_t* tok = (int32_t*)(h_step_ + L.tokens);
+    int32_t* pos = (int32_t*)(h_step_ + L.positions);
+    int32_t* cu = (int32_t*)(h_step_ + L.cu);
+    const int base = offsets[s0];
+    memcpy(tok, toks + base, (size_t)T * 4);
+    for (int i = 0; i < B; ++i) {
+      const int o = offsets[s0 + i] - base, n = offsets[s0 + i + 1] - offsets[s0 + i];
+      cu[i] = o;
+      for (int j = 0; j < n; ++j) pos[o + j] = j;
+    }
+    cu[B] = T;
+    CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
+    int rc = forward_bert(T, B, max_len, L, d_embed_out_);
+    if (rc != HB_OK) return rc;
+    CU(cudaMemcpyAsync(h_embed_out_, d_embed_out_, (size_t)B * d.hidden * 4, cudaMemcpyDeviceToHost, stream_));
+    CU(cudaStreamSynchronize(stream_));
+    memcpy(out + (size_t)s0 * d.hidden, h_embed_out_, (size_t)B * d.hidden * 4);
+    steps_prefill_++;
+    tok_prefill_ += T;
+    s0 = s1;
+  }
+  return HB_OK;
+}
+
+int Engine::stats(hb_stats* s) {
+  if (!s) return fail(HB_ERR_INVALID, "null stats");
+  memset(s, 0, sizeof *s);
+  std::lock_guard<std::mutex> g(mu_);
+  s->weights_bytes = model_.arena_bytes;
+  s->kv_bytes = kv_bytes_;
+  s->workspace_bytes = ws_bytes_ + step_bytes_;
+  s->budget_bytes = budget_;
+  s->kv_pages_total = num_pages_;
+  s->kv_pages_free = (int)free_pages_.size();
+  s->running = (int)running_.size();
+  s->waiting = (int)waiting_.size();
+  s->steps_prefill = steps_prefill_;
+  s->steps_decode = steps_decode_;
+  s->tokens_prefill = tok_prefill_;
+  s->tokens_decode = tok_decode_;
+  s->kernel_launches = launches_;
+  s->graph_launches = graph_launches_;
+  s->cuda_error = cuda_error_.load();
+  return HB_OK;
+}
+
+}  // namespace hb

@@ -1,0 +1,138 @@
+// One ModelInstance on one GPU: weight arena, paged KV pool, workspaces, request queues and the
+// continuous-batching step loop.  This is the in-process replacement for the backend child process a
+// reference Runtime owns (api/pkg/runner/slot.go:46-57); request admission mirrors what the reference
+// delegates to vLLM's scheduler (--max-num-seqs / paged KV), page bookkeeping is exact integer work.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/helix_b200.h"
+#include "kernels.h"
+#include "model.h"
+
+namespace hb {
+
+enum class ReqState { WAITING, RUNNING, FINISHED, CANCELLED, FAILED };
+
+struct Request {
+  uint64_t id = 0;
+  std::vector<int32_t> prompt;
+  std::vector<int32_t> out;
+  hb_sampling sp{};
+  ReqState state = ReqState::WAITING;
+  bool cancel_flag = false;
+  std::vector<int32_t> pages;
+  int kv_len = 0;       // tokens whose K/V are in the cache
+  size_t polled = 0;    // tokens already handed to the caller
+  std::vector<float> step_logits;    // rows of [vocab] (HB_CAPTURE_STEP_LOGITS)
+  std::vector<float> prompt_logits;  // [n_prompt][vocab] (HB_CAPTURE_PROMPT_LOGITS)
+};
+
+struct StepLayout {
+  size_t tokens, positions, slots, cu, last, ctx, pt, temp, seed, total;
+};
+
+class Engine {
+ public:
+  explicit Engine(const hb_engine_cfg& cfg);
+  ~Engine();
+  int init();  // device, stream
+
+  int load_begin(const hb_model_desc& d);
+  int tensor_set(const char* name, const void* host_bf16, size_t n);
+  int load_finish();
+  int load_random(const hb_model_desc& d, uint64_t seed);
+  int weights_arena(void** p, size_t* bytes);
+
+  int start();
+  int stop();
+  int step(int* did_work);
+  int submit(const int32_t* toks, int n, const hb_sampling* sp, uint64_t* id);
+  int poll(uint64_t id, int32_t* out, int cap, int* n_out, int* finished);
+  int wait(uint64_t id, int timeout_ms);
+  int cancel(uint64_t id);
+  int release(uint64_t id);
+  int captured(uint64_t id, int which, float* out, size_t cap, int* rows);
+  int embed(const int32_t* toks, const int32_t* offsets, int nseq, float* out);
+  int stats(hb_stats* s);
+  const char* last_error();
+
+  static void estimate(const hb_model_desc& d, const hb_engine_cfg& c, uint64_t* w, uint64_t* kv, uint64_t* ws);
+
+ private:
+  int fail(int code, const std::string& msg);
+  int fail_cuda(cudaError_t e, const char* what);
+  size_t workspace_bytes() const;
+  int alloc_runtime();
+  void free_all();
+  void loop();
+  void finish_request(Request* r, ReqState st);
+  StepLayout layout(int T, int B) const;
+  int forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits);
+  int forward_bert(int T, int B, int max_seqlen, const StepLayout& L, float* d_out);
+  int run_prefill(std::vector<Request*>& batch);
+  int run_decode(std::vector<Request*>& batch);
+  int decode_splits(int B) const;
+
+  hb_engine_cfg cfg_;
+  Model model_;
+  bool load_open_ = false, loaded_ = false;
+  cudaStream_t stream_ = nullptr;
+  int page_ = 64, max_pages_per_seq_ = 0, b_cap_ = 0, t_cap_ = 0;
+  uint64_t budget_ = 0;
+
+  // device memory
+  bf16* kv_ = nullptr;  // [layers][2][num_pages][Hkv][page][D]
+  size_t kv_bytes_ = 0;
+  int num_pages_ = 0;
+  std::vector<int32_t> free_pages_;
+  uint8_t* ws_ = nullptr;
+  size_t ws_bytes_ = 0;
+  bf16 *x_ = nullptr, *xn_ = nullptr, *qkv_ = nullptr, *attn_ = nullptr, *h_ = nullptr;
+  float* logits_ = nullptr;
+  float* dec_ws_ = nullptr;
+  int32_t* sampled_ = nullptr;
+  uint8_t* d_step_ = nullptr;  // per-step int/float inputs (layout())
+  uint8_t* h_step_ = nullptr;  // pinned mirror
+  int32_t* h_sampled_ = nullptr;
+  size_t step_bytes_ = 0;
+  float* all_logits_ = nullptr;  // lazily allocated [cap_rows][vocab] for HB_CAPTURE_PROMPT_LOGITS
+  int all_logits_rows_ = 0;
+  float* h_logits_ = nullptr;  // pinned, lazily sized
+  size_t h_logits_floats_ = 0;
+  float* d_embed_out_ = nullptr;  // [b_cap][hidden] fp32
+  float* h_embed_out_ = nullptr;
+
+  // decode CUDA graphs keyed by batch size
+  std::unordered_map<int, cudaGraphExec_t> graphs_;
+  std::unordered_map<int, uint64_t> graph_kernels_;  // kernels inside each captured step
+
+  // queues
+  std::mutex mu_;        // request tables
+  std::mutex gpu_mu_;    // serialises GPU steps (step loop vs hb_embed)
+  std::condition_variable cv_work_, cv_out_;
+  std::deque<Request*> waiting_;
+  std::vector<Request*> running_;
+  std::unordered_map<uint64_t, std::unique_ptr<Request>> reqs_;
+  uint64_t next_id_ = 1;
+  std::thread thread_;
+  std::atomic<bool> stop_{false};
+  bool thread_running_ = false;
+
+  std::mutex err_mu_;
+  std::string last_error_;
+  std::atomic<int> cuda_error_{0};
+  std::atomic<uint64_t> launches_{0}, graph_launches_{0}, steps_prefill_{0}, steps_decode_{0}, tok_prefill_{0},
+      tok_decode_{0};
+};
+
+}  // namespace hb

@@ -334,6 +334,38 @@ cudaError_t launch_epi(cudaStream_t stream, const GemmArgs& g, int num_sms) {
 
 }  // namespace
 
+namespace {
+template <int BN, int EPI>
+cudaError_t set_attr() {
+  return cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
+}
+template <int EPI>
+cudaError_t set_attr_epi() {
+  cudaError_t e;
+  if ((e = set_attr<256, EPI>()) != cudaSuccess) return e;
+  if ((e = set_attr<128, EPI>()) != cudaSuccess) return e;
+  return set_attr<64, EPI>();
+}
+}  // namespace
+
+cudaError_t gemm_init() {
+  cudaError_t e;
+  if ((e = set_attr_epi<EPI_NONE>()) != cudaSuccess) return e;
+  if ((e = set_attr_epi<EPI_BIAS>()) != cudaSuccess) return e;
+  if ((e = set_attr_epi<EPI_BIAS_GELU>()) != cudaSuccess) return e;
+  if ((e = set_attr_epi<EPI_RESID>()) != cudaSuccess) return e;
+  if ((e = set_attr_epi<EPI_BIAS_RESID>()) != cudaSuccess) return e;
+  if ((e = set_attr_epi<EPI_F32>()) != cudaSuccess) return e;
+  return set_attr<256, EPI_SWIGLU>();
+}
+
+cudaError_t kernels_init() {
+  cudaError_t e;
+  if ((e = gemm_init()) != cudaSuccess) return e;
+  if ((e = attn_prefill_init()) != cudaSuccess) return e;
+  return attn_decode_init();
+}
+
 cudaError_t gemm_bf16_tn(cudaStream_t stream, const GemmArgs& g) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaErrorInvalidValue;
   if ((g.K % 8) || (g.lda % 8) || (g.ldw % 8)) return cudaErrorInvalidValue;  // 16-byte TMA strides

@@ -10,6 +10,12 @@ namespace hb {
 
 typedef __nv_bfloat16 bf16;
 
+// Sets the opt-in shared-memory attribute of every kernel instantiation; call once per process/device.
+cudaError_t kernels_init();
+cudaError_t gemm_init();
+cudaError_t attn_prefill_init();
+cudaError_t attn_decode_init();
+
 // ---- GEMM: C[M,N] = A[M,K] · W[N,K]^T (both K-major, bf16 in, fp32 accumulate in TMEM) ----
 enum Epi : int {
   EPI_NONE = 0,        // C = acc                              (bf16)
@@ -39,5 +45,66 @@ struct GemmArgs {
 cudaError_t gemm_bf16_tn(cudaStream_t stream, const GemmArgs& a);
 // Debug/test-only CUDA-core GEMM (same contract, EPI_NONE/EPI_F32 only); used by tests as an on-device checker.
 cudaError_t gemm_naive_check(cudaStream_t stream, const GemmArgs& a);
+
+
+// ---- HBM-bound row kernels (K1, K2, K4, K10 sampling, K11) ----
+// x[t,:] = table[tokens[t],:]
+cudaError_t embed_gather(cudaStream_t s, const int32_t* tokens, const bf16* table, bf16* x, int T, int H);
+// BERT: x[t,:] = LayerNorm(word[tok[t]] + pos[positions[t]] + type[0]) * g + b
+cudaError_t bert_embed_ln(cudaStream_t s, const int32_t* tokens, const int32_t* positions, const bf16* word,
+                          const bf16* pos, const bf16* type0, const bf16* gamma, const bf16* beta, bf16* x, int T, int H,
+                          float eps);
+// out[r,:] = x[row_index ? row_index[r] : r, :] * rsqrt(mean(x^2)+eps) * w    (fp32 math, one bf16 rounding)
+cudaError_t rmsnorm(cudaStream_t s, const bf16* x, const bf16* w, bf16* out, const int32_t* row_index, int rows, int H,
+                    float eps);
+// out[r,:] = (x[r,:]-mean)/sqrt(var+eps)*g + b   (in-place allowed)
+cudaError_t layernorm(cudaStream_t s, const bf16* x, const bf16* gamma, const bf16* beta, bf16* out, int rows, int H,
+                      float eps);
+// In-place rotary embedding (HF rotate_half convention) on the q and k column blocks of the fused
+// qkv[T, (Hq+2*Hkv)*D] buffer, then scatter of the rotated k and of v into the paged KV cache:
+//   slot = slot_mapping[t] = page*page_size + offset;  cache layout [page][Hkv][page_size][D].
+// slot < 0 skips the cache write (embedding-only models never call this).
+cudaError_t rope_kv_write(cudaStream_t s, bf16* qkv, const int32_t* positions, const int32_t* slot_mapping,
+                          const float* inv_freq, bf16* k_cache, bf16* v_cache, int T, int Hq, int Hkv, int D,
+                          int page_size);
+// Greedy / Gumbel-max sampling over fp32 logits[B,V]: out[b] = argmax_v(logits[b,v]/temp[b] + g(seed[b],v)),
+// temp[b] <= 0 -> pure argmax (lowest index wins ties).
+cudaError_t sample_tokens(cudaStream_t s, const float* logits, int ldl, const float* temperature, const uint64_t* seed,
+                          int32_t* out, int B, int V);
+// out[b,:] = l2normalize(x[first_row[b], :]) as fp32 (CLS pooling for bge-style encoders)
+cudaError_t cls_pool_l2(cudaStream_t s, const bf16* x, const int32_t* first_row, float* out, int B, int H);
+
+
+// ---- K5: varlen flash attention over contiguous q/k/v rows (whole-prompt prefill, BERT encoder) ----
+struct AttnPrefillArgs {
+  const bf16* q; int ldq;   // [T, >=Hq*D], head h at column h*D
+  const bf16* k; int ldk;   // [T, >=Hkv*D]
+  const bf16* v; int ldv;
+  bf16* out; int ldo;       // [T, Hq*D]
+  const int32_t* cu_seqlens;  // [B+1] token offsets
+  int B, T, max_seqlen;
+  int Hq, Hkv, D;
+  int causal;
+  float scale;              // 1/sqrt(D)
+};
+cudaError_t attn_prefill(cudaStream_t stream, const AttnPrefillArgs& a);
+// test-only CUDA-core checker, fp32 output [T, ldo]
+cudaError_t attn_naive_check(cudaStream_t stream, const AttnPrefillArgs& a, float* out_f32);
+
+// ---- K6: paged-KV decode attention (one query token per sequence), split-KV + combine ----
+struct AttnDecodeArgs {
+  const bf16* q; int ldq;          // [B, >=Hq*D] (post-RoPE)
+  const bf16* k_cache;             // [num_pages][Hkv][page_size][D]
+  const bf16* v_cache;
+  const int32_t* page_table;       // [B, max_pages]
+  int max_pages;
+  const int32_t* ctx_lens;         // [B] kv length including the current token
+  bf16* out; int ldo;              // [B, Hq*D]
+  float* workspace;                // >= B*Hq*num_splits*(D+2) floats
+  int B, Hq, Hkv, D, page_size, num_splits;
+  float scale;
+};
+cudaError_t attn_decode(cudaStream_t stream, const AttnDecodeArgs& a);
+size_t attn_decode_workspace_floats(int B, int Hq, int D, int num_splits);
 
 }  // namespace hb

@@ -1,0 +1,326 @@
+// K1/K2/K4/K10(sampling)/K11 of SURVEY.md §2.3: HBM-bound row kernels.
+// 16-byte vectorised coalesced loads, warp-shuffle + one smem hop for block reductions, fp32 math.
+#include <math.h>
+
+#include "kernels.h"
+
+namespace hb {
+namespace {
+
+constexpr int kRowThreads = 128;
+constexpr int kMaxVec = 4;  // row cached in registers up to 128*4*8 = 4096 elements
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // protect `red` reuse
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < NT / 32) ? red[l] : 0.f;
+  return warp_sum(t);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+__global__ void embed_gather_kernel(const int32_t* __restrict__ tokens, const bf16* __restrict__ table,
+                                    bf16* __restrict__ x, int H) {
+  const int t = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)tokens[t] * H);
+  uint4* dst = reinterpret_cast<uint4*>(x + (size_t)t * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ out,
+               const int32_t* __restrict__ row_index, int H, float eps) {
+  __shared__ float red[kRowThreads / 32];
+  const int r = blockIdx.x;
+  const size_t src_row = row_index ? (size_t)row_index[r] : (size_t)r;
+  const uint4* src = reinterpret_cast<const uint4*>(x + src_row * H);
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)r * H);
+  const int nvec = H / 8;
+  uint4 cache[kMaxVec];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    const int i = threadIdx.x + j * kRowThreads;
+    if (i < nvec) {
+      cache[j] = src[i];
+      float f[8];
+      unpack8(cache[j], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ss += f[k] * f[k];
+    }
+  }
+  for (int i = threadIdx.x + kMaxVec * kRowThreads; i < nvec; i += kRowThreads) {
+    float f[8];
+    unpack8(src[i], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ss += f[k] * f[k];
+  }
+  ss = block_sum<kRowThreads>(ss, red);
+  const float inv = rsqrtf(ss / (float)H + eps);
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    const int i = threadIdx.x + j * kRowThreads;
+    if (i < nvec) {
+      float f[8], g[8];
+      unpack8(cache[j], f);
+      unpack8(__ldg(wv + i), g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = f[k] * inv * g[k];
+      dst[i] = pack8(f);
+    }
+  }
+  for (int i = threadIdx.x + kMaxVec * kRowThreads; i < nvec; i += kRowThreads) {
+    float f[8], g[8];
+    unpack8(src[i], f);
+    unpack8(__ldg(wv + i), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = f[k] * inv * g[k];
+    dst[i] = pack8(f);
+  }
+}
+
+// LayerNorm over rows of up to kMaxVec*128*8 elements held in registers (two-pass mean / variance).
+template <bool kEmbed>
+__global__ void __launch_bounds__(kRowThreads)
+layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                 bf16* __restrict__ out, int H, float eps, const int32_t* __restrict__ tokens,
+                 const int32_t* __restrict__ positions, const bf16* __restrict__ word, const bf16* __restrict__ pos,
+                 const bf16* __restrict__ type0) {
+  __shared__ float red[kRowThreads / 32];
+  const int r = blockIdx.x;
+  const int nvec = H / 8;
+  float vals[kMaxVec][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    const int i = threadIdx.x + j * kRowThreads;
+    if (i < nvec) {
+      if (kEmbed) {
+        float a[8], b[8], c[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(word + (size_t)tokens[r] * H) + i), a);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(pos + (size_t)positions[r] * H) + i), b);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(type0) + i), c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) vals[j][k] = a[k] + b[k] + c[k];
+      } else {
+        unpack8(reinterpret_cast<const uint4*>(x + (size_t)r * H)[i], vals[j]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += vals[j][k];
+    }
+  }
+  const float mean = block_sum<kRowThreads>(sum, red) / (float)H;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    const int i = threadIdx.x + j * kRowThreads;
+    if (i < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = vals[j][k] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float inv = rsqrtf(block_sum<kRowThreads>(sq, red) / (float)H + eps);
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    const int i = threadIdx.x + j * kRowThreads;
+    if (i < nvec) {
+      float g[8], b[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + i), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + i), b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (vals[j][k] - mean) * inv * g[k] + b[k];
+      reinterpret_cast<uint4*>(out + (size_t)r * H)[i] = pack8(o);
+    }
+  }
+}
+
+// One block per token. Pairs (i, i+D/2) of each q/k head are rotated; k,v rows go to the paged cache.
+__global__ void __launch_bounds__(256)
+rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positions,
+                     const int32_t* __restrict__ slot_mapping, const float* __restrict__ inv_freq,
+                     bf16* __restrict__ k_cache, bf16* __restrict__ v_cache, int Hq, int Hkv, int D, int page_size) {
+  extern __shared__ float cs[];  // cos[D/2], sin[D/2]
+  const int t = blockIdx.x;
+  const int half = D / 2;
+  const float p = (float)positions[t];
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    float s, c;
+    sincosf(p * inv_freq[i], &s, &c);
+    cs[i] = c;
+    cs[half + i] = s;
+  }
+  __syncthreads();
+  const int row_elems = (Hq + 2 * Hkv) * D;
+  bf16* row = qkv + (size_t)t * row_elems;
+  // rotate q and k heads: work items = (Hq+Hkv) * half/2 bf16x2 pairs
+  const int pairs_per_head = half / 2;
+  const int items = (Hq + Hkv) * pairs_per_head;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int h = it / pairs_per_head, j = (it % pairs_per_head) * 2;
+    __nv_bfloat162* lo = reinterpret_cast<__nv_bfloat162*>(row + h * D + j);
+    __nv_bfloat162* hi = reinterpret_cast<__nv_bfloat162*>(row + h * D + half + j);
+    const float2 a = __bfloat1622float2(*lo), b = __bfloat1622float2(*hi);
+    const float c0 = cs[j], c1 = cs[j + 1], s0 = cs[half + j], s1 = cs[half + j + 1];
+    *lo = __floats2bfloat162_rn(a.x * c0 - b.x * s0, a.y * c1 - b.y * s1);
+    *hi = __floats2bfloat162_rn(b.x * c0 + a.x * s0, b.y * c1 + a.y * s1);
+  }
+  const int slot = slot_mapping ? slot_mapping[t] : -1;
+  if (slot < 0) return;
+  __syncthreads();  // rotated k visible to the copy below
+  const int page = slot / page_size, off = slot % page_size;
+  const int vec_per_head = D / 8;
+  const uint4* ksrc = reinterpret_cast<const uint4*>(row + Hq * D);
+  const uint4* vsrc = reinterpret_cast<const uint4*>(row + (Hq + Hkv) * D);
+  for (int it = threadIdx.x; it < Hkv * vec_per_head; it += blockDim.x) {
+    const int h = it / vec_per_head, j = it % vec_per_head;
+    const size_t dst = (((size_t)page * Hkv + h) * page_size + off) * vec_per_head + j;
+    reinterpret_cast<uint4*>(k_cache)[dst] = ksrc[it];
+    reinterpret_cast<uint4*>(v_cache)[dst] = vsrc[it];
+  }
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(1024)
+sample_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ temperature,
+              const uint64_t* __restrict__ seed, int32_t* __restrict__ out, int V) {
+  __shared__ float sval[32];
+  __shared__ int sidx[32];
+  const int b = blockIdx.x;
+  const float* row = logits + (size_t)b * ldl;
+  const float temp = temperature ? temperature[b] : 0.f;
+  const bool greedy = !(temp > 0.f);
+  const float inv_t = greedy ? 1.f : 1.f / temp;
+  const uint64_t sd = seed ? seed[b] : 0;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    float x = row[v] * inv_t;
+    if (!greedy) {
+      const uint64_t h = mix64(sd ^ (0xD1B54A32D192ED03ull * (uint64_t)(v + 1)));
+      const float u = ((h >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+      x += -__logf(-__logf(u));
+    }
+    if (x > best || (x == best && v < bi)) { best = x; bi = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sval[w] = best; sidx[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    best = (l < (int)(blockDim.x >> 5)) ? sval[l] : -INFINITY;
+    bi = (l < (int)(blockDim.x >> 5)) ? sidx[l] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (l == 0) out[b] = bi;
+  }
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+cls_pool_l2_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ first_row, float* __restrict__ out, int H) {
+  __shared__ float red[kRowThreads / 32];
+  const int b = blockIdx.x;
+  const bf16* row = x + (size_t)first_row[b] * H;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < H; i += kRowThreads) {
+    const float v = __bfloat162float(row[i]);
+    ss += v * v;
+  }
+  ss = block_sum<kRowThreads>(ss, red);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int i = threadIdx.x; i < H; i += kRowThreads) out[(size_t)b * H + i] = __bfloat162float(row[i]) * inv;
+}
+
+}  // namespace
+
+cudaError_t embed_gather(cudaStream_t s, const int32_t* tokens, const bf16* table, bf16* x, int T, int H) {
+  if (T <= 0) return cudaSuccess;
+  if (H % 8) return cudaErrorInvalidValue;
+  embed_gather_kernel<<<T, 128, 0, s>>>(tokens, table, x, H);
+  return cudaGetLastError();
+}
+cudaError_t rmsnorm(cudaStream_t s, const bf16* x, const bf16* w, bf16* out, const int32_t* row_index, int rows, int H,
+                    float eps) {
+  if (rows <= 0) return cudaSuccess;
+  if (H % 8) return cudaErrorInvalidValue;
+  rmsnorm_kernel<<<rows, kRowThreads, 0, s>>>(x, w, out, row_index, H, eps);
+  return cudaGetLastError();
+}
+cudaError_t layernorm(cudaStream_t s, const bf16* x, const bf16* gamma, const bf16* beta, bf16* out, int rows, int H,
+                      float eps) {
+  if (rows <= 0) return cudaSuccess;
+  if (H % 8 || H > kMaxVec * kRowThreads * 8) return cudaErrorInvalidValue;
+  layernorm_kernel<false><<<rows, kRowThreads, 0, s>>>(x, gamma, beta, out, H, eps, nullptr, nullptr, nullptr, nullptr, nullptr);
+  return cudaGetLastError();
+}
+cudaError_t bert_embed_ln(cudaStream_t s, const int32_t* tokens, const int32_t* positions, const bf16* word,
+                          const bf16* pos, const bf16* type0, const bf16* gamma, const bf16* beta, bf16* x, int T, int H,
+                          float eps) {
+  if (T <= 0) return cudaSuccess;
+  if (H % 8 || H > kMaxVec * kRowThreads * 8) return cudaErrorInvalidValue;
+  layernorm_kernel<true><<<T, kRowThreads, 0, s>>>(nullptr, gamma, beta, x, H, eps, tokens, positions, word, pos, type0);
+  return cudaGetLastError();
+}
+cudaError_t rope_kv_write(cudaStream_t s, bf16* qkv, const int32_t* positions, const int32_t* slot_mapping,
+                          const float* inv_freq, bf16* k_cache, bf16* v_cache, int T, int Hq, int Hkv, int D,
+                          int page_size) {
+  if (T <= 0) return cudaSuccess;
+  if (D % 8) return cudaErrorInvalidValue;
+  rope_kv_write_kernel<<<T, 256, D * sizeof(float), s>>>(qkv, positions, slot_mapping, inv_freq, k_cache, v_cache, Hq,
+                                                         Hkv, D, page_size);
+  return cudaGetLastError();
+}
+cudaError_t sample_tokens(cudaStream_t s, const float* logits, int ldl, const float* temperature, const uint64_t* seed,
+                          int32_t* out, int B, int V) {
+  if (B <= 0) return cudaSuccess;
+  sample_kernel<<<B, 1024, 0, s>>>(logits, ldl, temperature, seed, out, V);
+  return cudaGetLastError();
+}
+cudaError_t cls_pool_l2(cudaStream_t s, const bf16* x, const int32_t* first_row, float* out, int B, int H) {
+  if (B <= 0) return cudaSuccess;
+  cls_pool_l2_kernel<<<B, kRowThreads, 0, s>>>(x, first_row, out, H);
+  return cudaGetLastError();
+}
+
+}  // namespace hb

@@ -1,0 +1,143 @@
+/* helix_b200.h — C ABI of the B200-native runtime that replaces the child-process backends
+ * (ollama serve / vllm api_server) behind Helix's runner.Runtime interface.
+ *
+ * What each entry point replaces in the reference (helixml/helix @ 2a205c7):
+ *   hb_engine_create / hb_model_load_* / hb_engine_start
+ *        <- Runtime.Start: OllamaRuntime.Start (api/pkg/runner/ollama_runtime.go:179-276) and
+ *           VLLMRuntime.Start (api/pkg/runner/vllm_runtime.go:163-252): spawn backend on gpu_index,
+ *           load weights, size the KV pool from --gpu-memory-utilization / ModelMemoryRequirement,
+ *           --max-num-seqs, --max-model-len (api/pkg/scheduler/runner.go:1187-1259,1344-1397).
+ *   hb_engine_destroy
+ *        <- Runtime.Stop (api/pkg/runner/slot.go:113-140): must release ALL device memory synchronously.
+ *   hb_submit / hb_poll / hb_cancel
+ *        <- the HTTP hop createChatCompletion makes to slot.URL()+"/v1/chat/completions"
+ *           (api/pkg/runner/openai_chat_handlers.go:100-175): token ids in, sampled token ids out,
+ *           one poll per SSE chunk; finish reason closes the stream.
+ *   hb_embed
+ *        <- createEmbedding's proxy to "/v1/embeddings" (api/pkg/runner/openai_embedding_handlers.go:569).
+ *   hb_stats / hb_last_error
+ *        <- Runtime.Status (slot.go:46-57): non-empty status == running (scheduler/scheduler.go:940).
+ *   hb_memory_estimate
+ *        <- POST /api/v1/memory-estimate (api/pkg/runner/memory_estimation_handlers.go:36-327).
+ *
+ * Conventions: 0 = ok, negative = hb_status error; caller owns every host buffer; the engine owns all
+ * device memory and (after hb_engine_start) one step-loop thread; all entry points are thread-safe; no
+ * callbacks into the caller (cgo-friendly). There is NO CPU fallback: without a CUDA device every
+ * entry point that needs one fails with HB_ERR_CUDA.
+ */
+#ifndef HELIX_B200_H_
+#define HELIX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_ABI_VERSION 1
+
+typedef enum hb_status {
+  HB_OK = 0,
+  HB_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  HB_ERR_CUDA = -2,      /* CUDA runtime error (sticky: engine must be destroyed) */
+  HB_ERR_OOM = -3,       /* does not fit the memory budget */
+  HB_ERR_STATE = -4,     /* call order violated (e.g. submit before model load) */
+  HB_ERR_NOT_FOUND = -5, /* unknown request id / tensor name */
+  HB_ERR_BUSY = -6,      /* queue full / no KV pages: retry later */
+} hb_status;
+
+typedef enum hb_arch { HB_ARCH_LLAMA = 0, HB_ARCH_BERT = 1 } hb_arch;
+
+typedef struct hb_engine hb_engine;
+
+typedef struct hb_engine_cfg {
+  int32_t device;               /* CUDA ordinal == CreateRunnerSlotAttributes.gpu_index (types/runner.go:92-104) */
+  uint64_t memory_budget_bytes; /* == model_memory_requirement: weights + KV pool + workspace must fit; 0 = all free */
+  int32_t max_seqs;             /* --max-num-seqs (default 256, types/memory.go:11) */
+  int32_t max_ctx;              /* context_length / --max-model-len */
+  int32_t max_batched_tokens;   /* prompt tokens processed per prefill step (default 16384) */
+  int32_t kv_page_size;         /* tokens per KV page; must be 64 */
+  int32_t use_cuda_graphs;      /* capture the decode step per batch size */
+  int32_t reserved[7];
+} hb_engine_cfg;
+
+typedef struct hb_model_desc {
+  int32_t arch;        /* hb_arch */
+  int32_t hidden, layers, heads, kv_heads, head_dim, ffn, vocab;
+  int32_t max_pos;     /* BERT position rows / Llama max positions */
+  int32_t type_vocab;  /* BERT token-type rows (row 0 is used) */
+  int32_t tie_embeddings;
+  float norm_eps;
+  float rope_theta;
+  float rope_factor;   /* llama3 rope scaling; <= 0 disables */
+  float rope_low_freq_factor, rope_high_freq_factor;
+  int32_t rope_orig_max_pos;
+  int32_t reserved[8];
+} hb_model_desc;
+
+typedef struct hb_sampling {
+  float temperature;   /* <= 0: greedy argmax. (The runner forces 0.1 when a request carries 0:
+                          api/pkg/runner/openai_chat_handlers.go:52-58 — that policy stays in the host shim.) */
+  uint64_t seed;
+  int32_t max_tokens;  /* generated tokens, >= 1 */
+  int32_t eos_token;   /* < 0: none */
+  int32_t capture;     /* HB_CAPTURE_* bit mask (parity tap) */
+  int32_t reserved[3];
+} hb_sampling;
+
+#define HB_CAPTURE_NONE 0
+#define HB_CAPTURE_STEP_LOGITS 1   /* fp32 logits row of every generated token */
+#define HB_CAPTURE_PROMPT_LOGITS 2 /* fp32 logits of every prompt position */
+
+typedef struct hb_stats {
+  uint64_t weights_bytes, kv_bytes, workspace_bytes, budget_bytes;
+  int32_t kv_pages_total, kv_pages_free;
+  int32_t running, waiting;
+  uint64_t steps_prefill, steps_decode;
+  uint64_t tokens_prefill, tokens_decode;
+  uint64_t kernel_launches;   /* launches of this library's kernels since creation */
+  uint64_t graph_launches;
+  int32_t cuda_error;         /* sticky cudaError_t, 0 = healthy */
+  int32_t reserved[7];
+} hb_stats;
+
+/* ---- lifecycle ---- */
+int hb_abi_version(void);
+int hb_engine_create(const hb_engine_cfg* cfg, hb_engine** out);
+void hb_engine_destroy(hb_engine* e);
+const char* hb_last_error(hb_engine* e); /* e may be NULL: last create error of this thread */
+
+/* ---- model load: describe, upload tensors by their HF checkpoint names (bf16, host memory), finish.
+ *      hb_model_load_random fills the same arena on the device from `seed` (benchmarks, NCCL-root). ---- */
+int hb_model_load_begin(hb_engine* e, const hb_model_desc* desc);
+int hb_model_tensor_set(hb_engine* e, const char* name, const void* host_bf16, size_t n_elems);
+int hb_model_load_finish(hb_engine* e);
+int hb_model_load_random(hb_engine* e, const hb_model_desc* desc, uint64_t seed);
+/* device address/size of the contiguous weight arena: replicas receive it by one NCCL broadcast */
+int hb_model_weights_arena(hb_engine* e, void** dev_ptr, size_t* bytes);
+/* closed-form footprint for the scheduler's packing (weights + max_seqs*max_ctx KV + workspace) */
+int hb_memory_estimate(const hb_model_desc* desc, const hb_engine_cfg* cfg, uint64_t* weights, uint64_t* kv,
+                       uint64_t* workspace);
+
+/* ---- generation ---- */
+int hb_engine_start(hb_engine* e); /* spawn the step-loop thread (continuous batching) */
+int hb_engine_stop(hb_engine* e);
+int hb_step(hb_engine* e, int* did_work); /* run ONE scheduler step on the caller's thread (no step-loop thread) */
+int hb_submit(hb_engine* e, const int32_t* tokens, int32_t n_tokens, const hb_sampling* sp, uint64_t* req_id);
+int hb_poll(hb_engine* e, uint64_t req_id, int32_t* out_tokens, int32_t cap, int32_t* n_out, int32_t* finished);
+int hb_wait(hb_engine* e, uint64_t req_id, int32_t timeout_ms); /* block until new tokens / finished */
+int hb_cancel(hb_engine* e, uint64_t req_id);
+int hb_release(hb_engine* e, uint64_t req_id); /* drop a finished request's record */
+/* parity tap: rows captured for req (see HB_CAPTURE_*), fp32 [rows][vocab] */
+int hb_captured_logits(hb_engine* e, uint64_t req_id, int32_t which, float* out, size_t cap_floats, int32_t* rows);
+
+/* ---- embeddings: nseq sequences, tokens[offsets[i]..offsets[i+1]) -> out[nseq][hidden] fp32 (CLS + L2) ---- */
+int hb_embed(hb_engine* e, const int32_t* tokens, const int32_t* offsets, int32_t nseq, float* out);
+
+int hb_get_stats(hb_engine* e, hb_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HELIX_B200_H_ */
