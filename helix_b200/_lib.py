@@ -36,7 +36,8 @@ class StatsC(C.Structure):
                 ("running", C.c_int32), ("waiting", C.c_int32), ("steps_prefill", C.c_uint64),
                 ("steps_decode", C.c_uint64), ("tokens_prefill", C.c_uint64), ("tokens_decode", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("graph_launches", C.c_uint64), ("cuda_error", C.c_int32),
-                ("reserved", C.c_int32 * 7)]
+                ("reserved", C.c_int32 * 7), ("gpu_ms_prefill", C.c_double), ("gpu_ms_decode", C.c_double),
+                ("prof_ms", C.c_double * 8), ("prof_work", C.c_double * 8), ("prof_launches", C.c_uint64 * 8)]
 
 
 P = C.c_void_p
@@ -65,6 +66,7 @@ SIGNATURES = {
     "hb_captured_logits": (I, [P, C.c_uint64, C.c_int32, P, C.c_size_t, C.POINTER(C.c_int32)]),
     "hb_embed": (I, [P, P, P, C.c_int32, P]),
     "hb_get_stats": (I, [P, C.POINTER(StatsC)]),
+    "hb_set_profile": (I, [P, C.c_int32]),
     # kernel-level ABI
     "hbk_init": (I, []),
     "hbk_last_error": (C.c_char_p, []),

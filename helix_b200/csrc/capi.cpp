@@ -82,6 +82,7 @@ int hb_embed(hb_engine* e, const int32_t* t, const int32_t* off, int32_t n, floa
   return e ? e->impl.embed(t, off, n, out) : HB_ERR_INVALID;
 }
 int hb_get_stats(hb_engine* e, hb_stats* s) { return e ? e->impl.stats(s) : HB_ERR_INVALID; }
+int hb_set_profile(hb_engine* e, int32_t on) { return e ? e->impl.set_profile(on != 0) : HB_ERR_INVALID; }
 
 // ------------------------------------------------------------------ kernel-level ABI
 int hbk_init(void) { return kret(hb::kernels_init()); }

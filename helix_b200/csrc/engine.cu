@@ -63,6 +63,9 @@ Engine::~Engine() {
   free_all();
   if (stream_) {
     cudaSetDevice(cfg_.device);
+    for (cudaEvent_t e : ev_pool_) cudaEventDestroy(e);
+    if (fwd_a_) cudaEventDestroy(fwd_a_);
+    if (fwd_b_) cudaEventDestroy(fwd_b_);
     cudaStreamDestroy(stream_);
   }
 }
@@ -93,6 +96,8 @@ int Engine::init() {
   CU(cudaGetDeviceProperties(&prop, cfg_.device));
   if (prop.major != 10) return fail(HB_ERR_CUDA, "device is not sm_100 (Blackwell B200); kernels are sm_100a-only");
   CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&fwd_a_));
+  CU(cudaEventCreate(&fwd_b_));
   CU(kernels_init());  // max-dynamic-smem attributes for every instantiation (never inside a graph capture)
   return HB_OK;
 }
@@ -322,6 +327,50 @@ int Engine::weights_arena(void** p, size_t* bytes) {
   return HB_OK;
 }
 
+// ------------------------------------------------------------------ measurement aids
+cudaEvent_t Engine::take_event() {
+  if (ev_next_ == ev_pool_.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ev_pool_.push_back(e);
+  }
+  return ev_pool_[ev_next_++];
+}
+void Engine::span_begin(int cat, double work) {
+  if (!profile_) return;
+  Span s{cat, take_event(), take_event(), work};
+  cudaEventRecord(s.a, stream_);
+  spans_.push_back(s);
+}
+void Engine::span_end() {
+  if (!profile_) return;
+  cudaEventRecord(spans_.back().b, stream_);
+}
+int Engine::drain_spans() {  // stream must be synchronised
+  for (const Span& s : spans_) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+      prof_ms_[s.cat] += ms;
+      prof_work_[s.cat] += s.work;
+      prof_launches_[s.cat] += 1;
+    }
+  }
+  spans_.clear();
+  ev_next_ = 0;
+  return HB_OK;
+}
+int Engine::set_profile(bool on) {
+  std::lock_guard<std::mutex> g(gpu_mu_);
+  profile_ = on;
+  return HB_OK;
+}
+#define SPAN(cat, work, expr) \
+  do {                        \
+    span_begin(cat, work);    \
+    LAUNCH(expr);             \
+    span_end();               \
+  } while (0)
+
 // ------------------------------------------------------------------ forward passes
 int Engine::decode_splits(int B) const {
   const int ctas = B * model_.d.kv_heads;
@@ -343,17 +392,20 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
   const uint64_t* seed = (const uint64_t*)(d_step_ + L.seed);
   const size_t layer_kv = (size_t)num_pages_ * d.kv_heads * page_ * D;  // elements per K (or V) plane
 
-  LAUNCH(embed_gather(stream_, tokens, model_.embed, x_, T, H));
+  const int gcat = prefill ? 0 : 4;  // GEMM family: FLOPs in prefill steps, weight bytes in decode steps
+  auto gwork = [&](double M, double N, double K) { return prefill ? 2.0 * M * N * K : 2.0 * (N * K + M * K + M * N); };
+  const double row_bytes = 2.0 * T * H * 2;
+  SPAN(3, 2.0 * T * H, embed_gather(stream_, tokens, model_.embed, x_, T, H));
   for (int l = 0; l < d.layers; ++l) {
     const LlamaLayerW& w = model_.ll[l];
     bf16* kc = kv_ + (size_t)l * 2 * layer_kv;
     bf16* vc = kc + layer_kv;
-    LAUNCH(rmsnorm(stream_, x_, w.attn_norm, xn_, nullptr, T, H, d.norm_eps));
+    SPAN(3, row_bytes, rmsnorm(stream_, x_, w.attn_norm, xn_, nullptr, T, H, d.norm_eps));
     {
       GemmArgs g{xn_, H, w.wqkv, H, qkv_, QKV, nullptr, 0, nullptr, T, QKV, H, EPI_NONE, 0};
-      LAUNCH(gemm_bf16_tn(stream_, g));
+      SPAN(gcat, gwork(T, QKV, H), gemm_bf16_tn(stream_, g));
     }
-    LAUNCH(rope_kv_write(stream_, qkv_, positions, slots, model_.inv_freq, kc, vc, T, d.heads, d.kv_heads, D, page_));
+    SPAN(3, 2.0 * T * (QD + 2.0 * KD) * 2, rope_kv_write(stream_, qkv_, positions, slots, model_.inv_freq, kc, vc, T, d.heads, d.kv_heads, D, page_));
     if (prefill) {
       AttnPrefillArgs a{};
       a.q = qkv_; a.ldq = QKV;
@@ -365,7 +417,7 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
       a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D;
       a.causal = 1;
       a.scale = 1.0f / sqrtf((float)D);
-      LAUNCH(attn_prefill(stream_, a));
+      SPAN(1, attn_flops_, attn_prefill(stream_, a));
     } else {
       AttnDecodeArgs a{};
       a.q = qkv_; a.ldq = QKV;
@@ -377,21 +429,21 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
       a.B = B; a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D; a.page_size = page_;
       a.num_splits = decode_splits(B);
       a.scale = 1.0f / sqrtf((float)D);
-      LAUNCH(attn_decode(stream_, a));
+      SPAN(2, attn_bytes_, attn_decode(stream_, a));
       launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel
     }
     {
       GemmArgs g{attn_, QD, w.wo, QD, x_, H, x_, H, nullptr, T, H, QD, EPI_RESID, 0};
-      LAUNCH(gemm_bf16_tn(stream_, g));
+      SPAN(gcat, gwork(T, H, QD), gemm_bf16_tn(stream_, g));
     }
-    LAUNCH(rmsnorm(stream_, x_, w.mlp_norm, xn_, nullptr, T, H, d.norm_eps));
+    SPAN(3, row_bytes, rmsnorm(stream_, x_, w.mlp_norm, xn_, nullptr, T, H, d.norm_eps));
     {
       GemmArgs g{xn_, H, w.wgu, H, h_, F, nullptr, 0, nullptr, T, 2 * F, H, EPI_SWIGLU, 256};
-      LAUNCH(gemm_bf16_tn(stream_, g));
+      SPAN(gcat, gwork(T, 2.0 * F, H), gemm_bf16_tn(stream_, g));
     }
     {
       GemmArgs g{h_, F, w.wdown, F, x_, H, x_, H, nullptr, T, H, F, EPI_RESID, 0};
-      LAUNCH(gemm_bf16_tn(stream_, g));
+      SPAN(gcat, gwork(T, H, F), gemm_bf16_tn(stream_, g));
     }
   }
   if (all_logits) {
@@ -403,7 +455,7 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
   LAUNCH(rmsnorm(stream_, x_, model_.final_norm, h_, last, B, H, d.norm_eps));
   {
     GemmArgs g{h_, H, model_.lm_head, H, logits_, d.vocab, nullptr, 0, nullptr, B, d.vocab, H, EPI_F32, 0};
-    LAUNCH(gemm_bf16_tn(stream_, g));
+    SPAN(gcat, gwork(B, d.vocab, H), gemm_bf16_tn(stream_, g));
   }
   LAUNCH(sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab));
   return HB_OK;
@@ -421,7 +473,7 @@ int Engine::forward_bert(int T, int B, int max_seqlen, const StepLayout& L, floa
     const BertLayerW& w = model_.bl[l];
     {
       GemmArgs g{x_, H, w.wqkv, H, qkv_, 3 * H, nullptr, 0, w.bqkv, T, 3 * H, H, EPI_BIAS, 0};
-      LAUNCH(gemm_bf16_tn(stream_, g));
+      SPAN(0, 2.0 * T * 3 * H * H, gemm_bf16_tn(stream_, g));
     }
     {
       AttnPrefillArgs a{};
@@ -434,22 +486,22 @@ int Engine::forward_bert(int T, int B, int max_seqlen, const StepLayout& L, floa
       a.Hq = d.heads; a.Hkv = d.heads; a.D = D;
       a.causal = 0;
       a.scale = 1.0f / sqrtf((float)D);
-      LAUNCH(attn_prefill(stream_, a));
+      SPAN(1, attn_flops_, attn_prefill(stream_, a));
     }
     {
       GemmArgs g{attn_, H, w.wo, H, xn_, H, x_, H, w.bo, T, H, H, EPI_BIAS_RESID, 0};
-      LAUNCH(gemm_bf16_tn(stream_, g));
+      SPAN(0, 2.0 * T * H * H, gemm_bf16_tn(stream_, g));
     }
-    LAUNCH(layernorm(stream_, xn_, w.ln1_g, w.ln1_b, x_, T, H, d.norm_eps));
+    SPAN(3, 4.0 * T * H, layernorm(stream_, xn_, w.ln1_g, w.ln1_b, x_, T, H, d.norm_eps));
     {
       GemmArgs g{x_, H, w.w1, H, h_, F, nullptr, 0, w.b1, T, F, H, EPI_BIAS_GELU, 0};
-      LAUNCH(gemm_bf16_tn(stream_, g));
+      SPAN(0, 2.0 * T * F * H, gemm_bf16_tn(stream_, g));
     }
     {
       GemmArgs g{h_, F, w.w2, F, xn_, H, x_, H, w.b2, T, H, F, EPI_BIAS_RESID, 0};
-      LAUNCH(gemm_bf16_tn(stream_, g));
+      SPAN(0, 2.0 * T * H * F, gemm_bf16_tn(stream_, g));
     }
-    LAUNCH(layernorm(stream_, xn_, w.ln2_g, w.ln2_b, x_, T, H, d.norm_eps));
+    SPAN(3, 4.0 * T * H, layernorm(stream_, xn_, w.ln2_g, w.ln2_b, x_, T, H, d.norm_eps));
   }
   LAUNCH(cls_pool_l2(stream_, x_, cu, d_out, B, H));
   return HB_OK;
@@ -597,10 +649,22 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   }
   cu[B] = t;
   CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
+  attn_flops_ = 0;
+  for (Request* r : batch) {
+    const double n = (double)r->prompt.size();
+    attn_flops_ += 4.0 * n * n * d.head_dim * d.heads * 0.5;  // causal half of QK^T + PV
+  }
+  CU(cudaEventRecord(fwd_a_, stream_));
   int rc = forward_llama(T, B, true, max_len, L, want_all);
   if (rc != HB_OK) return rc;
+  CU(cudaEventRecord(fwd_b_, stream_));
   CU(cudaMemcpyAsync(h_sampled_, sampled_, (size_t)B * 4, cudaMemcpyDeviceToHost, stream_));
   CU(cudaStreamSynchronize(stream_));
+  {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, fwd_a_, fwd_b_) == cudaSuccess) gpu_ms_prefill_ += ms;
+    drain_spans();
+  }
   steps_prefill_++;
   tok_prefill_ += T;
   // captures (test tap; synchronous copies are fine here)
@@ -650,7 +714,10 @@ int Engine::run_decode(std::vector<Request*>& batch) {
   }
   cu[B] = B;
   CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
-  if (cfg_.use_cuda_graphs) {
+  attn_bytes_ = 0;
+  for (Request* r : batch) attn_bytes_ += (double)(r->kv_len + 1) * 2.0 * d.kv_heads * d.head_dim * 2.0;
+  CU(cudaEventRecord(fwd_a_, stream_));
+  if (cfg_.use_cuda_graphs && !profile_) {
     auto it = graphs_.find(B);
     if (it == graphs_.end()) {
       cudaGraph_t graph = nullptr;
@@ -674,8 +741,14 @@ int Engine::run_decode(std::vector<Request*>& batch) {
     int rc = forward_llama(B, B, false, 1, L, false);
     if (rc != HB_OK) return rc;
   }
+  CU(cudaEventRecord(fwd_b_, stream_));
   CU(cudaMemcpyAsync(h_sampled_, sampled_, (size_t)B * 4, cudaMemcpyDeviceToHost, stream_));
   CU(cudaStreamSynchronize(stream_));
+  {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, fwd_a_, fwd_b_) == cudaSuccess) gpu_ms_decode_ += ms;
+    drain_spans();
+  }
   steps_decode_++;
   tok_decode_ += B;
   for (int i = 0; i < B; ++i) {
@@ -852,10 +925,22 @@ int Engine::embed(const int32_t* toks, const int32_t* offsets, int nseq, float* 
     }
     cu[B] = T;
     CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
+    attn_flops_ = 0;
+    for (int i = 0; i < B; ++i) {
+      const double n = offsets[s0 + i + 1] - offsets[s0 + i];
+      attn_flops_ += 4.0 * n * n * d.head_dim * d.heads;
+    }
+    CU(cudaEventRecord(fwd_a_, stream_));
     int rc = forward_bert(T, B, max_len, L, d_embed_out_);
     if (rc != HB_OK) return rc;
+    CU(cudaEventRecord(fwd_b_, stream_));
     CU(cudaMemcpyAsync(h_embed_out_, d_embed_out_, (size_t)B * d.hidden * 4, cudaMemcpyDeviceToHost, stream_));
     CU(cudaStreamSynchronize(stream_));
+    {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, fwd_a_, fwd_b_) == cudaSuccess) gpu_ms_prefill_ += ms;
+      drain_spans();
+    }
     memcpy(out + (size_t)s0 * d.hidden, h_embed_out_, (size_t)B * d.hidden * 4);
     steps_prefill_++;
     tok_prefill_ += T;
@@ -883,6 +968,13 @@ int Engine::stats(hb_stats* s) {
   s->kernel_launches = launches_;
   s->graph_launches = graph_launches_;
   s->cuda_error = cuda_error_.load();
+  s->gpu_ms_prefill = gpu_ms_prefill_;
+  s->gpu_ms_decode = gpu_ms_decode_;
+  for (int i = 0; i < 8; ++i) {
+    s->prof_ms[i] = prof_ms_[i];
+    s->prof_work[i] = prof_work_[i];
+    s->prof_launches[i] = prof_launches_[i];
+  }
   return HB_OK;
 }
 

@@ -64,6 +64,7 @@ class Engine {
   int captured(uint64_t id, int which, float* out, size_t cap, int* rows);
   int embed(const int32_t* toks, const int32_t* offsets, int nseq, float* out);
   int stats(hb_stats* s);
+  int set_profile(bool on);
   const char* last_error();
 
   static void estimate(const hb_model_desc& d, const hb_engine_cfg& c, uint64_t* w, uint64_t* kv, uint64_t* ws);
@@ -82,6 +83,22 @@ class Engine {
   int run_prefill(std::vector<Request*>& batch);
   int run_decode(std::vector<Request*>& batch);
   int decode_splits(int B) const;
+  // profiling spans
+  struct Span { int cat; cudaEvent_t a, b; double work; };
+  cudaEvent_t take_event();
+  void span_begin(int cat, double work);
+  void span_end();
+  int drain_spans();
+  bool profile_ = false;
+  bool step_is_prefill_ = true;
+  double attn_flops_ = 0, attn_bytes_ = 0;  // per-layer attention work of the current step
+  std::vector<cudaEvent_t> ev_pool_;
+  size_t ev_next_ = 0;
+  std::vector<Span> spans_;
+  cudaEvent_t fwd_a_ = nullptr, fwd_b_ = nullptr;
+  double gpu_ms_prefill_ = 0, gpu_ms_decode_ = 0;
+  double prof_ms_[8] = {0}, prof_work_[8] = {0};
+  uint64_t prof_launches_[8] = {0};
 
   hb_engine_cfg cfg_;
   Model model_;

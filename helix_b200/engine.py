@@ -213,4 +213,13 @@ class Engine:
     def stats(self):
         s = StatsC()
         self._ck(self._l.hb_get_stats(self._h, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in StatsC._fields_ if k != "reserved"}
+        out = {}
+        for k, _ in StatsC._fields_:
+            if k == "reserved":
+                continue
+            v = getattr(s, k)
+            out[k] = list(v) if hasattr(v, "__len__") else v
+        return out
+
+    def set_profile(self, on):
+        self._ck(self._l.hb_set_profile(self._h, int(bool(on))))

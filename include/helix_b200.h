@@ -100,6 +100,15 @@ typedef struct hb_stats {
   uint64_t graph_launches;
   int32_t cuda_error;         /* sticky cudaError_t, 0 = healthy */
   int32_t reserved[7];
+  /* device time of the forward passes (CUDA events on the engine stream: after the step's inputs are
+     resident, before the sampled ids are copied back) */
+  double gpu_ms_prefill, gpu_ms_decode;
+  /* hb_set_profile(e,1): per-launch CUDA-event spans by kernel family
+     [0]=tcgen05 GEMM in prefill steps, [1]=prefill attention, [2]=decode attention, [3]=row kernels,
+     [4]=tcgen05 GEMM in decode steps */
+  double prof_ms[8];
+  double prof_work[8];        /* algorithmic FLOPs ([0],[1]) or bytes ([2],[3],[4]) of the timed launches */
+  uint64_t prof_launches[8];
 } hb_stats;
 
 /* ---- lifecycle ---- */
@@ -136,6 +145,8 @@ int hb_captured_logits(hb_engine* e, uint64_t req_id, int32_t which, float* out,
 int hb_embed(hb_engine* e, const int32_t* tokens, const int32_t* offsets, int32_t nseq, float* out);
 
 int hb_get_stats(hb_engine* e, hb_stats* out);
+/* event-timed spans around every launch (measurement aid; disables CUDA-graph replay while on) */
+int hb_set_profile(hb_engine* e, int32_t on);
 
 #ifdef __cplusplus
 }
