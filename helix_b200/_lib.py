@@ -72,6 +72,7 @@ SIGNATURES = {
     "hbk_last_error": (C.c_char_p, []),
     "hbk_gemm": (I, [P, I, P, I, P, I, P, I, P, I, I, I, I, I]),
     "hbk_gemm_naive": (I, [P, I, P, I, P, I, I, I, I]),
+    "hbk_gemm_skinny": (I, [P, I, P, I, P, I, I, I, I]),
     "hbk_embed_gather": (I, [P, P, P, I, I]),
     "hbk_bert_embed_ln": (I, [P, P, P, P, P, P, P, P, I, I, C.c_float]),
     "hbk_rmsnorm": (I, [P, P, P, P, I, I, C.c_float]),
@@ -81,7 +82,7 @@ SIGNATURES = {
     "hbk_cls_pool_l2": (I, [P, P, P, I, I]),
     "hbk_attn_prefill": (I, [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, I, C.c_float]),
     "hbk_attn_naive": (I, [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, I, C.c_float]),
-    "hbk_attn_decode": (I, [P, I, P, P, P, I, P, P, I, P, I, I, I, I, I, I, C.c_float]),
+    "hbk_attn_decode": (I, [P, I, P, P, P, I, P, P, I, P, I, I, I, I, I, I, C.c_float, I]),
     "hbk_attn_decode_workspace_floats": (C.c_size_t, [I, I, I, I]),
 }
 

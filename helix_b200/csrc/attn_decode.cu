@@ -1,208 +1,314 @@
-// K6: paged-KV decode attention — one query token per sequence, HBM-bound.
-// Split-KV: grid (num_splits, Hkv, B); each CTA streams its share of the sequence's KV pages for ONE
-// kv head (16-byte cp.async, double buffered, page = contiguous [page_size][D] block per kv head) and
-// serves all `G = Hq/Hkv` query heads of the group from the same bytes, so every KV byte is read
-// from HBM exactly once per step.  A second tiny kernel merges the per-split (m, l, o) partials.
+// K6: paged-KV decode attention — one query token per sequence, HBM-bound —
+// on the tcgen05 tensor cores with TRANSPOSED score / output tiles so that all 128 TMEM lanes work:
+//
+//   S^T[kv=128 lanes, 16 cols] = K_tile[128 kv x D] (A, K-major smem)  ·  Q^T   (B: the G<=16 query heads of
+//                                                                               the GQA group, K-major)
+//   O^T[d =128 lanes, 16 cols] += V_tile^T (A, read MN-major straight from the [kv][d] page layout) · P^T (B)
+//
+// Split-KV grid (num_splits, Hkv, B): each CTA streams its share of the sequence's pages for ONE kv head with
+// TMA (3-D tensor map over [page*Hkv][64 tok][D], 8 KB boxes, 3-stage ring -> ~190 KB in flight per SM) and
+// serves all G query heads from the same bytes: every KV byte is read from HBM exactly once per step.
+//   warp 0 lane 0 : TMA producer      warp 1 lane 0 : MMA issuer
+//   warps 2..5    : softmax — thread <-> kv position (4 fp32 scores each): tile max / sum by warp shuffles +
+//                   one smem hop, lazy rescale of O^T (only when the running max moved by > 2^8), P^T -> smem.
+// A second tiny kernel merges the per-split (m, l, o) partials.
 #include <math.h>
+#include <stdio.h>
 
 #include "kernels.h"
+#include "ptx.cuh"
+#include "tma_host.h"
 
 namespace hb {
 namespace {
 
-constexpr int kThreads = 128;
-constexpr int kTile = 64;  // kv positions per smem tile (== page_size)
-constexpr int kMaxG = 8;
+constexpr int kThreads = 192;
+constexpr int BKV = 128;   // kv positions per tile (2 pages)
+constexpr int PAGE = 64;
+constexpr int NQ = 16;     // UMMA N: query heads of the group, zero padded
+constexpr int kMaxG = 16;
+constexpr float kRescaleThreshold = 8.0f;
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
-                   static_cast<uint32_t>(__cvta_generic_to_shared(smem))),
-               "l"(gmem)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
+template <int D>
+struct DCfg {
+  static constexpr int STAGES = 3;
+  static constexpr int KV_BYTES = BKV * D * 2;       // one K (or V) tile
+  static constexpr int Q_BYTES = NQ * D * 2;
+  static constexpr int P_BYTES = NQ * BKV * 2;
+  static constexpr int TAIL = (D == 64) ? BKV * 128 : 0;  // the M=128 PV MMA of a D=64 head reads one tile-chunk past V
+  static constexpr int SMEM = 2 * STAGES * KV_BYTES + TAIL + Q_BYTES + P_BYTES + 1024 + 1024;
+  static constexpr int SUB = D / 64;
+};
+
+// MN-major A/B operand descriptor and instruction descriptor with A MN-major are shared with attn_prefill (ptx.cuh).
+
 template <int D, int G>
-__global__ void __launch_bounds__(kThreads)
-attn_decode_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k_cache,
-                   const bf16* __restrict__ v_cache, const int32_t* __restrict__ page_table, int max_pages,
-                   const int32_t* __restrict__ ctx_lens, float* __restrict__ ws, int Hq, int Hkv, int num_splits,
+__global__ void __launch_bounds__(kThreads, 1)
+attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                   const bf16* __restrict__ q, int ldq, const int32_t* __restrict__ page_table, int max_pages,
+                   const int32_t* __restrict__ ctx_lens, float* __restrict__ ws, int Hkv, int num_splits,
                    float scale_log2) {
-  constexpr int KP = D + 8;  // padded K row (bf16 elements): 16-byte skew kills bank conflicts on row-per-thread reads
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* sK = reinterpret_cast<bf16*>(smem_raw);           // [2][kTile][KP]
-  bf16* sV = sK + 2 * kTile * KP;                          // [2][kTile][D]
-  float* sQ = reinterpret_cast<float*>(sV + 2 * kTile * D);  // [G][D], pre-scaled
-  float* sS = sQ + G * D;                                  // [G][kTile]
-  float* sF = sS + G * kTile;                              // [G] rescale factors
+  using C = DCfg<D>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                                   // [STAGES][KV_BYTES]
+  uint8_t* sV = sK + STAGES * C::KV_BYTES;              // [STAGES][KV_BYTES] (+TAIL)
+  uint8_t* sQ = sV + STAGES * C::KV_BYTES + C::TAIL;    // [SUB][16 rows][128 B]
+  uint8_t* sP = sQ + C::Q_BYTES;                        // [2][16 rows][128 B]
+  float* sRed = reinterpret_cast<float*>(sP + C::P_BYTES);  // [2][4 warps][G]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 2 * 4 * kMaxG);
+  uint64_t* k_full = bars;                  // [STAGES]
+  uint64_t* k_empty = bars + STAGES;        // [STAGES]
+  uint64_t* v_full = bars + 2 * STAGES;     // [STAGES]
+  uint64_t* v_empty = bars + 3 * STAGES;    // [STAGES]
+  uint64_t* s_full = bars + 4 * STAGES;     // [2]
+  uint64_t* s_empty = bars + 4 * STAGES + 2;  // [2]
+  uint64_t* q_ready = bars + 4 * STAGES + 4;
+  uint64_t* p_full = bars + 4 * STAGES + 5;
+  uint64_t* pv_done = bars + 4 * STAGES + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4 * STAGES + 7);
 
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ctx = ctx_lens[b];
-  const int n_pages = (ctx + kTile - 1) / kTile;
-  const int pps = (n_pages + num_splits - 1) / num_splits;
-  const int p_begin = split * pps;
-  const int p_end = min(n_pages, p_begin + pps);
+  const int n_pages = (ctx + PAGE - 1) / PAGE;
+  const int n_tiles_total = (ctx + BKV - 1) / BKV;
+  const int tps = (n_tiles_total + num_splits - 1) / num_splits;
+  const int t_begin = split * tps;
+  const int t_end = min(n_tiles_total, t_begin + tps);
   float* ws_base = ws + ((size_t)(b * Hkv + kvh) * num_splits + split) * G * (D + 2);
-
-  if (p_begin >= p_end) {
-    for (int i = tid; i < G * (D + 2); i += kThreads) {
-      const int within = i % (D + 2);
-      ws_base[i] = (within == D) ? -INFINITY : 0.f;  // m = -inf, l = 0, o = 0
-    }
+  if (t_begin >= t_end) {
+    for (int i = threadIdx.x; i < G * (D + 2); i += kThreads) ws_base[i] = (i % (D + 2) == D) ? -INFINITY : 0.f;
     return;
   }
-
-  for (int i = tid; i < G * D; i += kThreads) {
-    const int g = i / D, d = i % D;
-    sQ[i] = __bfloat162float(q[(size_t)b * ldq + (kvh * G + g) * D + d]) * scale_log2;
-  }
-
+  const int n_tiles = t_end - t_begin;
   const int32_t* pt = page_table + (size_t)b * max_pages;
-  constexpr int VEC_PER_ROW = D / 8;
-  auto load_page = [&](int page_idx, int buf) {
-    const size_t base = ((size_t)pt[page_idx] * Hkv + kvh) * kTile * D;
-    const uint4* ksrc = reinterpret_cast<const uint4*>(k_cache + base);
-    const uint4* vsrc = reinterpret_cast<const uint4*>(v_cache + base);
-    bf16* kd = sK + buf * kTile * KP;
-    bf16* vd = sV + buf * kTile * D;
-    for (int i = tid; i < kTile * VEC_PER_ROW; i += kThreads) {
-      const int row = i / VEC_PER_ROW, c = i % VEC_PER_ROW;
-      cp_async16(kd + row * KP + c * 8, ksrc + i);
-      cp_async16(vd + row * D + c * 8, vsrc + i);
-    }
-  };
 
-  // per-thread state
-  constexpr int NDP = D / 2;                 // d pairs
-  constexpr int HSTRIDE = kThreads / NDP;    // head stride in PV phase (2 for D=128, 4 for D=64)
-  constexpr int HPT = (G + HSTRIDE - 1) / HSTRIDE;
-  float acc[HPT][2];
-#pragma unroll
-  for (int i = 0; i < HPT; ++i) acc[i][0] = acc[i][1] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;  // meaningful in warp g (lanes replicate)
-  const int warp = tid >> 5, lane = tid & 31;
-
-  load_page(p_begin, 0);
-  cp_async_commit();
-  for (int p = p_begin; p < p_end; ++p) {
-    const int buf = (p - p_begin) & 1;
-    if (p + 1 < p_end) load_page(p + 1, buf ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    const bf16* kb = sK + buf * kTile * KP;
-    const bf16* vb = sV + buf * kTile * D;
-    const int valid = min(kTile, ctx - p * kTile);
-
-    // ---- scores: thread -> (pos = tid % 64, heads tid/64, tid/64+2, ...)
-    {
-      const int pos = tid % kTile;
-      float s[(G + 1) / 2];
-#pragma unroll
-      for (int i = 0; i < (G + 1) / 2; ++i) s[i] = 0.f;
-      const uint4* krow = reinterpret_cast<const uint4*>(kb + pos * KP);
-#pragma unroll 4
-      for (int c = 0; c < VEC_PER_ROW; ++c) {
-        const uint4 kv = krow[c];
-        const __nv_bfloat162* kp = reinterpret_cast<const __nv_bfloat162*>(&kv);
-        float kf[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 t = __bfloat1622float2(kp[i]);
-          kf[2 * i] = t.x;
-          kf[2 * i + 1] = t.y;
-        }
-#pragma unroll
-        for (int i = 0; i < (G + 1) / 2; ++i) {
-          const int g = tid / kTile + 2 * i;
-          if (g < G) {
-            const float4 q0 = *reinterpret_cast<const float4*>(sQ + g * D + c * 8);
-            const float4 q1 = *reinterpret_cast<const float4*>(sQ + g * D + c * 8 + 4);
-            s[i] += kf[0] * q0.x + kf[1] * q0.y + kf[2] * q0.z + kf[3] * q0.w + kf[4] * q1.x + kf[5] * q1.y +
-                    kf[6] * q1.z + kf[7] * q1.w;
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < (G + 1) / 2; ++i) {
-        const int g = tid / kTile + 2 * i;
-        if (g < G) sS[g * kTile + pos] = (pos < valid) ? s[i] : -INFINITY;
-      }
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
-    __syncthreads();
-    // ---- online softmax: warp g owns head g (extra heads loop)
-    for (int g = warp; g < G; g += kThreads / 32) {
-      const float s0 = sS[g * kTile + lane], s1 = sS[g * kTile + lane + 32];
-      float mx = fmaxf(s0, s1);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      // state for head g lives in registers of warp (g % 4) under index g / 4 — with G <= 4 a single slot
-      const float m_new = fmaxf(m_run, mx);
-      const float f = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_new);
-      const float p0 = fast_exp2(s0 - m_new), p1 = fast_exp2(s1 - m_new);
-      float sum = p0 + p1;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      l_run = l_run * f + sum;
-      m_run = m_new;
-      sS[g * kTile + lane] = p0;
-      sS[g * kTile + lane + 32] = p1;
-      if (lane == 0) sF[g] = f;
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
     }
-    __syncthreads();
-    // ---- PV: thread -> (d pair = tid % NDP, heads tid/NDP, +HSTRIDE, ...)
-    {
-      const int dp = tid % NDP;
-#pragma unroll
-      for (int i = 0; i < HPT; ++i) {
-        const int g = tid / NDP + i * HSTRIDE;
-        if (g < G) {
-          const float f = sF[g];
-          float a0 = acc[i][0] * f, a1 = acc[i][1] * f;
-          const float* pr = sS + g * kTile;
-#pragma unroll 8
-          for (int pos = 0; pos < kTile; ++pos) {
-            const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + pos * D + dp * 2));
-            const float pw = pr[pos];
-            a0 += pw * vv.x;
-            a1 += pw * vv.y;
-          }
-          acc[i][0] = a0;
-          acc[i][1] = a1;
-        }
-      }
-    }
-    __syncthreads();
+    mbar_init(q_ready, 4);
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
   }
-  cp_async_wait<0>();
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base;       // 2 x 16 columns
+  const uint32_t tmem_O = tmem_base + 32;  // 16 columns
 
-  // ---- write partials: layout per (b,kvh,split): [G][D+2] = o[D], m, l
-  {
-    const int dp = tid % NDP;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % STAGES;
+        const uint32_t ph = (j / STAGES) & 1;
+        const int pg0 = (t_begin + j) * 2;
+        // a tile's second page may not exist yet: re-load the first one (finite data, masked by the softmax)
+        const int page_a = pt[pg0], page_b = pt[min(pg0 + 1, n_pages - 1)];
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], C::KV_BYTES);
 #pragma unroll
-    for (int i = 0; i < HPT; ++i) {
-      const int g = tid / NDP + i * HSTRIDE;
-      if (g < G) {
-        ws_base[g * (D + 2) + dp * 2] = acc[i][0];
-        ws_base[g * (D + 2) + dp * 2 + 1] = acc[i][1];
+        for (int c = 0; c < C::SUB; ++c) {
+          tma_load_3d(sK + s * C::KV_BYTES + c * (BKV * 128), &map_k, &k_full[s], c * 64, 0, page_a * Hkv + kvh, kEvictFirst);
+          tma_load_3d(sK + s * C::KV_BYTES + c * (BKV * 128) + PAGE * 128, &map_k, &k_full[s], c * 64, 0,
+                      page_b * Hkv + kvh, kEvictFirst);
+        }
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], C::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < C::SUB; ++c) {
+          tma_load_3d(sV + s * C::KV_BYTES + c * (BKV * 128), &map_v, &v_full[s], c * 64, 0, page_a * Hkv + kvh, kEvictFirst);
+          tma_load_3d(sV + s * C::KV_BYTES + c * (BKV * 128) + PAGE * 128, &map_v, &v_full[s], c * 64, 0,
+                      page_b * Hkv + kvh, kEvictFirst);
+        }
       }
     }
-    for (int g = warp; g < G; g += kThreads / 32) {
-      if (lane == 0) {
-        ws_base[g * (D + 2) + D] = m_run;
-        ws_base[g * (D + 2) + D + 1] = l_run;
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BKV, NQ, 0, 0);   // A = K tile (K-major), B = Q (K-major)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, NQ, 1, 0);   // A = V tile (MN-major: d contiguous), B = P^T
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      auto issue_s = [&](int j) {
+        const int s = j % STAGES;
+        mbar_wait(&k_full[s], (j / STAGES) & 1);
+        mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + s * C::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint64_t adesc = umma_desc_kmajor_sw128(k_addr + (k >> 2) * (BKV * 128) + (k & 3) * 32);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(q_addr + (k >> 2) * (NQ * 128) + (k & 3) * 32);
+          umma_f16_ss(tmem_S + (j & 1) * NQ, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[s]);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_ready, 0);
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_s(j + 1);
+        const int s = j % STAGES;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[s], (j / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sV + s * C::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t adesc = umma_desc_mnmajor_sw128(v_addr + k * (16 * 128), BKV * 128, 1024);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(p_addr + (k >> 2) * (NQ * 128) + (k & 3) * 32);
+          umma_f16_ss(tmem_O, adesc, bdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&v_empty[s]);
+        umma_commit(pv_done);
       }
     }
+  } else {
+    const int qd = warp & 3;
+    const int t = qd * 32 + lane;  // kv position within the tile (S^T lane) / head-dim index (O^T lane)
+    const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
+    // ---- stage Q^T (G rows of D, rows G..15 zero) into the K-major swizzled B-operand layout; zero P
+    {
+      const bf16* qsrc = q + (size_t)b * ldq + (size_t)kvh * G * D;
+      constexpr int CH = D / 8;  // 16-byte chunks per row
+      for (int i = t; i < NQ * CH; i += 128) {
+        const int g = i / CH, c = i % CH;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (g < G) v = *reinterpret_cast<const uint4*>(qsrc + g * D + c * 8);
+        *reinterpret_cast<uint4*>(sQ + (c >> 3) * (NQ * 128) + g * 128 + (((c & 7) ^ (g & 7)) << 4)) = v;
+      }
+      for (int i = t; i < C::P_BYTES / 16; i += 128) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(q_ready);
+    }
+    float m_used[G], l_run[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { m_used[g] = -INFINITY; l_run[g] = 0.f; }
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[16];
+      tmem_ld_32x32b_x16(tmem_S + lane_sel + (j & 1) * NQ, sv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[j & 1]);
+      const bool valid = (t_begin + j) * BKV + t < ctx;
+      float sc[G], mx[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        sc[g] = valid ? __uint_as_float(sv[g]) * scale_log2 : -INFINITY;
+        mx[g] = sc[g];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int g = 0; g < G; ++g) mx[g] = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], o));
+      float* red = sRed + (j & 1) * 4 * kMaxG;
+      if (lane == 0)
+#pragma unroll
+        for (int g = 0; g < G; ++g) red[qd * kMaxG + g] = mx[g];
+      bar_sync(1, 128);
+      bool rescale = false;
+      float f[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float tm = fmaxf(fmaxf(red[g], red[kMaxG + g]), fmaxf(red[2 * kMaxG + g], red[3 * kMaxG + g]));
+        f[g] = 1.f;
+        if (tm > m_used[g] + kRescaleThreshold) {  // also the first tile (m_used = -inf); tm is finite: position 0 of the tile is valid
+          f[g] = (m_used[g] == -INFINITY) ? 0.f : fast_exp2(m_used[g] - tm);
+          m_used[g] = tm;
+          rescale = true;
+        }
+      }
+      float pr[G], sum[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        pr[g] = fast_exp2(sc[g] - m_used[g]);
+        sum[g] = pr[g];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int g = 0; g < G; ++g) sum[g] += __shfl_xor_sync(0xffffffffu, sum[g], o);
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // P buffer free, O^T consistent
+        tc_fence_after();
+      }
+      if (rescale && j > 0) {
+        uint32_t o[16];
+        tmem_ld_32x32b_x16(tmem_O + lane_sel, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < G; ++g) o[g] = __float_as_uint(__uint_as_float(o[g]) * f[g]);
+        tmem_st_32x32b_x16(tmem_O + lane_sel, o);
+        tmem_st_wait();
+      }
+      // P^T[g][kv = t] -> K-major swizzled B operand (row g, 128 B per 64 kv)
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int c = (t & 63) >> 3;
+        *reinterpret_cast<bf16*>(sP + (t >> 6) * (NQ * 128) + g * 128 + ((c ^ (g & 7)) << 4) + (t & 7) * 2) =
+            __float2bfloat16(pr[g]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // running sum: each thread keeps only ITS warp's partial (merged across warps at the end)
+#pragma unroll
+      for (int g = 0; g < G; ++g) l_run[g] = l_run[g] * f[g] + sum[g];
+    }
+    // ---- epilogue: O^T lane d, column g; l = sum over the 4 warps' partials
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    float* redl = sRed;  // all tiles done: reuse
+    bar_sync(1, 128);
+    if (lane == 0)
+#pragma unroll
+      for (int g = 0; g < G; ++g) redl[qd * kMaxG + g] = l_run[g];
+    bar_sync(1, 128);
+    uint32_t o[16];
+    tmem_ld_32x32b_x16(tmem_O + lane_sel, o);
+    tmem_ld_wait();
+    if (t < D) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) ws_base[g * (D + 2) + t] = __uint_as_float(o[g]);
+    }
+    if (t < G) {
+      ws_base[t * (D + 2) + D] = m_used[t];
+      ws_base[t * (D + 2) + D + 1] = redl[t] + redl[kMaxG + t] + redl[2 * kMaxG + t] + redl[3 * kMaxG + t];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
   }
 }
 
@@ -232,29 +338,20 @@ attn_decode_combine_kernel(const float* __restrict__ ws, bf16* __restrict__ out,
 }
 
 template <int D, int G>
-constexpr size_t decode_smem() {
-  return (size_t)2 * kTile * (D + 8) * 2 + (size_t)2 * kTile * D * 2 + (size_t)G * D * 4 + (size_t)G * kTile * 4 +
-         (size_t)kMaxG * 4;
-}
-template <int D, int G>
 cudaError_t set_attr() {
-  return cudaFuncSetAttribute(attn_decode_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)decode_smem<D, G>());
+  return cudaFuncSetAttribute(attn_decode_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, DCfg<D>::SMEM);
 }
 
 template <int D, int G>
 cudaError_t launch(cudaStream_t stream, const AttnDecodeArgs& a) {
-  constexpr size_t smem = decode_smem<D, G>();
-  auto kern = attn_decode_kernel<D, G>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  CUtensorMap mk, mv;
+  const uint64_t blocks = (uint64_t)a.num_pages * a.Hkv;
+  if (!make_tmap_3d(&mk, a.k_cache, TM_BF16, D, PAGE, blocks, (uint64_t)D * 2, (uint64_t)PAGE * D * 2, 64, PAGE, 1)) return cudaErrorInvalidValue;
+  if (!make_tmap_3d(&mv, a.v_cache, TM_BF16, D, PAGE, blocks, (uint64_t)D * 2, (uint64_t)PAGE * D * 2, 64, PAGE, 1)) return cudaErrorInvalidValue;
   dim3 grid(a.num_splits, a.Hkv, a.B);
-  kern<<<grid, kThreads, smem, stream>>>(a.q, a.ldq, a.k_cache, a.v_cache, a.page_table, a.max_pages, a.ctx_lens,
-                                         a.workspace, a.Hq, a.Hkv, a.num_splits, a.scale * 1.4426950408889634f);
+  attn_decode_kernel<D, G><<<grid, kThreads, DCfg<D>::SMEM, stream>>>(mk, mv, a.q, a.ldq, a.page_table, a.max_pages,
+                                                                     a.ctx_lens, a.workspace, a.Hkv, a.num_splits,
+                                                                     a.scale * 1.4426950408889634f);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   attn_decode_combine_kernel<D><<<dim3(a.Hq, a.B), D / 2, 0, stream>>>(a.workspace, a.out, a.ldo, a.Hq, a.Hkv, G,
@@ -269,9 +366,11 @@ cudaError_t attn_decode_init() {
   if ((e = set_attr<128, 1>()) != cudaSuccess) return e;
   if ((e = set_attr<128, 2>()) != cudaSuccess) return e;
   if ((e = set_attr<128, 4>()) != cudaSuccess) return e;
+  if ((e = set_attr<128, 8>()) != cudaSuccess) return e;
   if ((e = set_attr<64, 1>()) != cudaSuccess) return e;
   if ((e = set_attr<64, 2>()) != cudaSuccess) return e;
-  return set_attr<64, 4>();
+  if ((e = set_attr<64, 4>()) != cudaSuccess) return e;
+  return set_attr<64, 8>();
 }
 
 size_t attn_decode_workspace_floats(int B, int Hq, int D, int num_splits) {
@@ -280,13 +379,14 @@ size_t attn_decode_workspace_floats(int B, int Hq, int D, int num_splits) {
 
 cudaError_t attn_decode(cudaStream_t stream, const AttnDecodeArgs& a) {
   if (a.B <= 0) return cudaSuccess;
-  if (a.page_size != kTile || a.Hq % a.Hkv || a.num_splits < 1) return cudaErrorInvalidValue;
+  if (a.page_size != PAGE || a.Hq % a.Hkv || a.num_splits < 1 || a.num_pages <= 0) return cudaErrorInvalidValue;
   const int G = a.Hq / a.Hkv;
   if (a.D == 128) {
     switch (G) {
       case 1: return launch<128, 1>(stream, a);
       case 2: return launch<128, 2>(stream, a);
       case 4: return launch<128, 4>(stream, a);
+      case 8: return launch<128, 8>(stream, a);
       default: return cudaErrorInvalidValue;
     }
   }
@@ -295,6 +395,7 @@ cudaError_t attn_decode(cudaStream_t stream, const AttnDecodeArgs& a) {
       case 1: return launch<64, 1>(stream, a);
       case 2: return launch<64, 2>(stream, a);
       case 4: return launch<64, 4>(stream, a);
+      case 8: return launch<64, 8>(stream, a);
       default: return cudaErrorInvalidValue;
     }
   }

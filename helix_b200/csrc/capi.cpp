@@ -94,6 +94,18 @@ int hbk_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, c
                  (const hb::bf16*)bias, M, N, K, (hb::Epi)epi, block_n};
   return kret(hb::gemm_bf16_tn(0, g));
 }
+int hbk_gemm_skinny(const void* X, int ldx, const void* W, int ldw, float* out, int ldo, int M, int N, int K) {
+  hb::SkinnyPlan plan;
+  cudaError_t e = hb::gemm_skinny_plan(N, K, &plan);
+  if (e != cudaSuccess) return kret(e);
+  float* ws = nullptr;
+  if ((e = cudaMalloc(&ws, hb::gemm_skinny_ws_floats(plan, M, N) * 4)) != cudaSuccess) return kret(e);
+  e = hb::gemm_skinny(0, plan, (const hb::bf16*)X, ldx, (const hb::bf16*)W, ldw, ws, M, N, K);
+  if (e == cudaSuccess) e = hb::dec_sum_slabs(0, ws, plan, out, ldo, M, N);
+  cudaError_t e2 = cudaDeviceSynchronize();
+  cudaFree(ws);
+  return kret(e != cudaSuccess ? e : e2);
+}
 int hbk_gemm_naive(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K) {
   hb::GemmArgs g{(const hb::bf16*)A, lda, (const hb::bf16*)W, ldw, C, ldc, nullptr, 0, nullptr, M, N, K, hb::EPI_F32, 0};
   return kret(hb::gemm_naive_check(0, g));
@@ -147,8 +159,9 @@ int hbk_attn_naive(const void* q, int ldq, const void* k, int ldk, const void* v
 }
 int hbk_attn_decode(const void* q, int ldq, const void* k_cache, const void* v_cache, const int32_t* page_table,
                     int max_pages, const int32_t* ctx_lens, void* out, int ldo, float* workspace, int B, int Hq, int Hkv,
-                    int D, int page_size, int num_splits, float scale) {
+                    int D, int page_size, int num_splits, float scale, int num_pages) {
   hb::AttnDecodeArgs a{};
+  a.num_pages = num_pages;
   a.q = (const hb::bf16*)q; a.ldq = ldq;
   a.k_cache = (const hb::bf16*)k_cache; a.v_cache = (const hb::bf16*)v_cache;
   a.page_table = page_table; a.max_pages = max_pages; a.ctx_lens = ctx_lens;

@@ -142,8 +142,22 @@ size_t Engine::workspace_bytes() const {
     b += al256((size_t)cfg_.max_seqs * d.vocab * 4);          // logits
     b += al256(attn_decode_workspace_floats(cfg_.max_seqs, d.heads, d.head_dim, 16) * 4);
     b += al256((size_t)cfg_.max_seqs * 4);                    // sampled
+    b += al256(skinny_ws_bytes(148));                         // decode GEMM partial slabs
   }
   return b;
+}
+
+size_t Engine::skinny_ws_bytes(int sms) const {
+  const hb_model_desc& d = model_.d;
+  const size_t B = std::min(cfg_.max_seqs, 256);
+  const int H = d.hidden, QD = d.heads * d.head_dim, QKV = (d.heads + 2 * d.kv_heads) * d.head_dim, F = d.ffn;
+  size_t f = 0;
+  f = std::max(f, (size_t)gemm_skinny_max_segs(QKV, H, sms) * B * QKV);
+  f = std::max(f, (size_t)gemm_skinny_max_segs(H, QD, sms) * B * H);
+  f = std::max(f, (size_t)gemm_skinny_max_segs(2 * F, H, sms) * B * 2 * F);
+  f = std::max(f, (size_t)gemm_skinny_max_segs(H, F, sms) * B * H);
+  f = std::max(f, (size_t)gemm_skinny_max_segs(d.vocab, H, sms) * B * d.vocab);
+  return f * 4;
 }
 
 void Engine::estimate(const hb_model_desc& d, const hb_engine_cfg& c_in, uint64_t* w, uint64_t* kv, uint64_t* ws) {
@@ -249,6 +263,17 @@ int Engine::alloc_runtime() {
     logits_ = (float*)take((size_t)cfg_.max_seqs * d.vocab * 4);
     dec_ws_ = (float*)take(attn_decode_workspace_floats(cfg_.max_seqs, d.heads, d.head_dim, 16) * 4);
     sampled_ = (int32_t*)take((size_t)cfg_.max_seqs * 4);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device);
+    skinny_ws_ = (float*)take(skinny_ws_bytes(148));
+    if (skinny_ws_bytes(sms) > skinny_ws_bytes(148)) return fail(HB_ERR_INVALID, "unexpected SM count for the decode workspace");
+    skinny_max_b_ = std::min(cfg_.max_seqs, 256);
+    const int QD = d.heads * d.head_dim, QKV = model_.qkv_cols();
+    CU(gemm_skinny_plan(QKV, d.hidden, &plan_qkv_));
+    CU(gemm_skinny_plan(d.hidden, QD, &plan_o_));
+    CU(gemm_skinny_plan(2 * d.ffn, d.hidden, &plan_gu_));
+    CU(gemm_skinny_plan(d.hidden, d.ffn, &plan_down_));
+    CU(gemm_skinny_plan(d.vocab, d.hidden, &plan_head_));
   }
   step_bytes_ = layout(t_cap_, b_cap_).total;
   CU(cudaMalloc(&d_step_, step_bytes_));
@@ -274,6 +299,10 @@ int Engine::alloc_runtime() {
     num_pages_ = (int)pages;
     kv_bytes_ = pages * page_bytes;
     CU(cudaMalloc(&kv_, kv_bytes_));
+    // masked positions of a partly-filled page are still multiplied (by an exact 0) in P·V: the pool must never hold
+    // NaN/Inf bit patterns left behind by a previous owner of the memory
+    CU(cudaMemsetAsync(kv_, 0, kv_bytes_, stream_));
+    CU(cudaStreamSynchronize(stream_));
     free_pages_.resize(num_pages_);
     for (int i = 0; i < num_pages_; ++i) free_pages_[i] = num_pages_ - 1 - i;  // pop_back hands out page 0 first
   } else {
@@ -373,12 +402,24 @@ int Engine::set_profile(bool on) {
 
 // ------------------------------------------------------------------ forward passes
 int Engine::decode_splits(int B) const {
+  // one CTA per SM (190 KB TMA ring): pick the split count whose CTA total fills whole waves of the 148 SMs
   const int ctas = B * model_.d.kv_heads;
-  int s = (148 * 4 + ctas - 1) / ctas;
-  return std::max(1, std::min(16, s));
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 16; ++s) {
+    const double waves = (double)ctas * s / 148.0;
+    const double eff = waves / ceil(waves);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = s;
+    }
+    if (best_eff >= 0.9) break;
+  }
+  return best;
 }
 
 int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits) {
+  if (!prefill && !all_logits && T == B && B <= skinny_max_b_) return forward_llama_decode(B, L);
   const hb_model_desc& d = model_.d;
   const int H = d.hidden, D = d.head_dim, QD = d.heads * D, KD = d.kv_heads * D, QKV = model_.qkv_cols(), F = d.ffn;
   const int32_t* tokens = (const int32_t*)(d_step_ + L.tokens);
@@ -429,6 +470,7 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
       a.B = B; a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D; a.page_size = page_;
       a.num_splits = decode_splits(B);
       a.scale = 1.0f / sqrtf((float)D);
+      a.num_pages = num_pages_;
       SPAN(2, attn_bytes_, attn_decode(stream_, a));
       launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel
     }
@@ -458,6 +500,60 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
     SPAN(gcat, gwork(B, d.vocab, H), gemm_bf16_tn(stream_, g));
   }
   LAUNCH(sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab));
+  return HB_OK;
+}
+
+// Decode step (one token per sequence, B <= 256): every projection is a weight-streaming skinny GEMM whose
+// fp32 partial slabs are consumed by the fused row kernel that follows it in the layer.
+int Engine::forward_llama_decode(int B, const StepLayout& L) {
+  const hb_model_desc& d = model_.d;
+  const int H = d.hidden, D = d.head_dim, QD = d.heads * D, QKV = model_.qkv_cols(), F = d.ffn;
+  const int32_t* tokens = (const int32_t*)(d_step_ + L.tokens);
+  const int32_t* positions = (const int32_t*)(d_step_ + L.positions);
+  const int32_t* slots = (const int32_t*)(d_step_ + L.slots);
+  const int32_t* ctx = (const int32_t*)(d_step_ + L.ctx);
+  const int32_t* pt = (const int32_t*)(d_step_ + L.pt);
+  const float* temp = (const float*)(d_step_ + L.temp);
+  const uint64_t* seed = (const uint64_t*)(d_step_ + L.seed);
+  const size_t layer_kv = (size_t)num_pages_ * d.kv_heads * page_ * D;
+  auto wbytes = [&](double N, double K) { return 2.0 * N * K + 2.0 * B * K + 4.0 * B * N; };
+  const double rowb = 4.0 * B * H;
+
+  SPAN(3, rowb, embed_gather(stream_, tokens, model_.embed, x_, B, H));
+  SPAN(3, rowb, rmsnorm(stream_, x_, model_.ll[0].attn_norm, xn_, nullptr, B, H, d.norm_eps));
+  for (int l = 0; l < d.layers; ++l) {
+    const LlamaLayerW& w = model_.ll[l];
+    bf16* kc = kv_ + (size_t)l * 2 * layer_kv;
+    bf16* vc = kc + layer_kv;
+    SPAN(4, wbytes(QKV, H), gemm_skinny(stream_, plan_qkv_, xn_, H, w.wqkv, H, skinny_ws_, B, QKV, H));
+    SPAN(3, 8.0 * B * QKV, dec_qkv_rope_kvwrite(stream_, skinny_ws_, plan_qkv_, qkv_, positions, slots, model_.inv_freq,
+                                                 kc, vc, B, d.heads, d.kv_heads, D, page_));
+    {
+      AttnDecodeArgs a{};
+      a.q = qkv_; a.ldq = QKV;
+      a.k_cache = kc; a.v_cache = vc;
+      a.page_table = pt; a.max_pages = max_pages_per_seq_;
+      a.ctx_lens = ctx;
+      a.out = attn_; a.ldo = QD;
+      a.workspace = dec_ws_;
+      a.B = B; a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D; a.page_size = page_;
+      a.num_splits = decode_splits(B);
+      a.scale = 1.0f / sqrtf((float)D);
+      a.num_pages = num_pages_;
+      SPAN(2, attn_bytes_, attn_decode(stream_, a));
+      launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel
+    }
+    SPAN(4, wbytes(H, QD), gemm_skinny(stream_, plan_o_, attn_, QD, w.wo, QD, skinny_ws_, B, H, QD));
+    SPAN(3, 3 * rowb, dec_resid_rmsnorm(stream_, skinny_ws_, plan_o_, x_, w.mlp_norm, xn_, B, H, d.norm_eps));
+    SPAN(4, wbytes(2.0 * F, H), gemm_skinny(stream_, plan_gu_, xn_, H, w.wgu, H, skinny_ws_, B, 2 * F, H));
+    SPAN(3, 10.0 * B * F, dec_swiglu(stream_, skinny_ws_, plan_gu_, h_, B, F));
+    SPAN(4, wbytes(H, F), gemm_skinny(stream_, plan_down_, h_, F, w.wdown, F, skinny_ws_, B, H, F));
+    const bf16* next_norm = (l + 1 < d.layers) ? model_.ll[l + 1].attn_norm : model_.final_norm;
+    SPAN(3, 3 * rowb, dec_resid_rmsnorm(stream_, skinny_ws_, plan_down_, x_, next_norm, xn_, B, H, d.norm_eps));
+  }
+  SPAN(4, wbytes(d.vocab, H), gemm_skinny(stream_, plan_head_, xn_, H, model_.lm_head, H, skinny_ws_, B, d.vocab, H));
+  SPAN(3, 8.0 * B * d.vocab, dec_sum_slabs(stream_, skinny_ws_, plan_head_, logits_, d.vocab, B, d.vocab));
+  SPAN(3, 4.0 * B * d.vocab, sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab));
   return HB_OK;
 }
 

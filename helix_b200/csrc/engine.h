@@ -83,6 +83,8 @@ class Engine {
   int run_prefill(std::vector<Request*>& batch);
   int run_decode(std::vector<Request*>& batch);
   int decode_splits(int B) const;
+  int forward_llama_decode(int B, const StepLayout& L);
+  size_t skinny_ws_bytes(int sms) const;
   // profiling spans
   struct Span { int cat; cudaEvent_t a, b; double work; };
   cudaEvent_t take_event();
@@ -117,6 +119,9 @@ class Engine {
   bf16 *x_ = nullptr, *xn_ = nullptr, *qkv_ = nullptr, *attn_ = nullptr, *h_ = nullptr;
   float* logits_ = nullptr;
   float* dec_ws_ = nullptr;
+  float* skinny_ws_ = nullptr;  // fp32 partial slabs of the decode-step GEMMs
+  SkinnyPlan plan_qkv_{}, plan_o_{}, plan_gu_{}, plan_down_{}, plan_head_{};
+  int skinny_max_b_ = 0;
   int32_t* sampled_ = nullptr;
   uint8_t* d_step_ = nullptr;  // per-step int/float inputs (layout())
   uint8_t* h_step_ = nullptr;  // pinned mirror

@@ -363,6 +363,7 @@ cudaError_t kernels_init() {
   cudaError_t e;
   if ((e = gemm_init()) != cudaSuccess) return e;
   if ((e = attn_prefill_init()) != cudaSuccess) return e;
+  if ((e = gemm_skinny_init()) != cudaSuccess) return e;
   return attn_decode_init();
 }
 

@@ -103,8 +103,35 @@ struct AttnDecodeArgs {
   float* workspace;                // >= B*Hq*num_splits*(D+2) floats
   int B, Hq, Hkv, D, page_size, num_splits;
   float scale;
+  int num_pages;                   // pages in the pool (TMA tensor-map extent)
 };
 cudaError_t attn_decode(cudaStream_t stream, const AttnDecodeArgs& a);
 size_t attn_decode_workspace_floats(int B, int Hq, int D, int num_splits);
+
+
+// ---- decode-step GEMM (M <= 256): swap-AB + deterministic stream-K, fp32 partial slabs ----
+struct SkinnyPlan {
+  int grid;                  // CTAs (== SMs unless the problem is tiny)
+  int n_tiles;               // ceil(N/128)
+  int max_segs;              // max #slabs any tile is split into
+  const uint8_t* seg_count;  // device [n_tiles]: slabs of each 128-column tile
+};
+cudaError_t gemm_skinny_init();
+cudaError_t gemm_skinny_plan(int N, int K, SkinnyPlan* out);  // cached per (device, N, K)
+size_t gemm_skinny_ws_floats(const SkinnyPlan& p, int M, int N);
+int gemm_skinny_max_segs(int N, int K, int sms);  // pure host arithmetic (memory estimates)
+// ws[seg][m][n] (seg < seg_count[n/128]) = partial sums of X[M,K] . W[N,K]^T
+cudaError_t gemm_skinny(cudaStream_t stream, const SkinnyPlan& plan, const bf16* X, int ldx, const bf16* W, int ldw,
+                        float* ws, int M, int N, int K);
+// consumers of the slabs (each sums the slabs in fixed order, then applies its fused epilogue)
+cudaError_t dec_sum_slabs(cudaStream_t s, const float* ws, const SkinnyPlan& p, float* out, int ldo, int M, int N);
+cudaError_t dec_qkv_rope_kvwrite(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* qkv_out,
+                                 const int32_t* positions, const int32_t* slot_mapping, const float* inv_freq,
+                                 bf16* k_cache, bf16* v_cache, int M, int Hq, int Hkv, int D, int page_size);
+// x = bf16(x + sum); xn = rmsnorm(x) * w (w may be null: residual update only)
+cudaError_t dec_resid_rmsnorm(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* x, const bf16* w, bf16* xn,
+                              int M, int H, float eps);
+// h[m, t*128+j] = silu(sum[m, t*256+j]) * sum[m, t*256+128+j]
+cudaError_t dec_swiglu(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* h, int M, int F);
 
 }  // namespace hb

@@ -19,6 +19,8 @@ const char* hbk_last_error(void);
  * 5 swiglu (W packed [128 gate|128 up] per 256 rows, C has N/2 columns), 6 fp32 out). block_n 0 = auto. */
 int hbk_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, const void* R, int ldr, const void* bias,
              int M, int N, int K, int epi, int block_n);
+/* decode-step GEMM (M<=256): swap-AB + stream-K partial slabs summed in fixed order -> out fp32 [M,N] */
+int hbk_gemm_skinny(const void* X, int ldx, const void* W, int ldw, float* out_f32, int ldo, int M, int N, int K);
 int hbk_gemm_naive(const void* A, int lda, const void* W, int ldw, void* C_f32, int ldc, int M, int N, int K);
 
 int hbk_embed_gather(const int32_t* tokens, const void* table, void* x, int T, int H);
@@ -39,7 +41,7 @@ int hbk_attn_naive(const void* q, int ldq, const void* k, int ldk, const void* v
                    float scale);
 int hbk_attn_decode(const void* q, int ldq, const void* k_cache, const void* v_cache, const int32_t* page_table,
                     int max_pages, const int32_t* ctx_lens, void* out, int ldo, float* workspace, int B, int Hq, int Hkv,
-                    int D, int page_size, int num_splits, float scale);
+                    int D, int page_size, int num_splits, float scale, int num_pages);
 size_t hbk_attn_decode_workspace_floats(int B, int Hq, int D, int num_splits);
 
 #ifdef __cplusplus

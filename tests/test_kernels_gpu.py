@@ -245,7 +245,7 @@ def test_attn_prefill_large_logits_rescale(L):
     torch.testing.assert_close(out.float(), want, rtol=2e-2, atol=2e-2)
 
 
-@pytest.mark.parametrize("D,Hq,Hkv,splits", [(128, 32, 8, 4), (64, 32, 8, 1), (64, 4, 2, 3), (128, 8, 8, 16)])
+@pytest.mark.parametrize("D,Hq,Hkv,splits", [(128, 32, 8, 4), (64, 32, 8, 1), (64, 4, 2, 3), (128, 8, 8, 16), (128, 16, 2, 2)])
 def test_attn_decode_paged(L, D, Hq, Hkv, splits):
     page, B = 64, 5
     ctx = [1, 64, 65, 700, 2048][:B]
@@ -263,7 +263,7 @@ def test_attn_decode_paged(L, D, Hq, Hkv, splits):
     ws = torch.empty(L.hbk_attn_decode_workspace_floats(B, Hq, D, splits), device="cuda")
     ctx_t, pt_d = torch.tensor(ctx, device="cuda", dtype=torch.int32), pt.cuda()
     ck(L, L.hbk_attn_decode(p(q), Hq * D, p(kc), p(vc), p(pt_d), max_pages, p(ctx_t), p(out), Hq * D, p(ws), B, Hq, Hkv,
-                            D, page, splits, 1.0 / math.sqrt(D)))
+                            D, page, splits, 1.0 / math.sqrt(D), npages))
     g = Hq // Hkv
     for b, c in enumerate(ctx):
         pages = pt[b, :(c + page - 1) // page].long()
@@ -273,3 +273,17 @@ def test_attn_decode_paged(L, D, Hq, Hkv, splits):
         s = (Q @ K.transpose(1, 2)) / math.sqrt(D)
         want = (torch.softmax(s, -1) @ V).reshape(Hq * D)
         torch.testing.assert_close(out[b].float(), want, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 6144, 4096), (1, 4096, 4096), (7, 1000, 256), (64, 4096, 14336), (100, 28672, 4096),
+                                   (256, 128256, 2048), (200, 512, 64), (33, 128, 4096)])
+def test_gemm_skinny_stream_k(L, M, N, K):
+    X, W = rnd(M, K, seed=60), rnd(N, K, scale=0.05, seed=61)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ck(L, L.hbk_gemm_skinny(p(X), K, p(W), K, p(out), N, M, N, K))
+    ref = torch.empty(M, N, device="cuda")
+    ck(L, L.hbk_gemm_naive(p(X), K, p(W), K, p(ref), N, M, N, K))
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=2e-3)
+    out2 = torch.empty_like(out)
+    ck(L, L.hbk_gemm_skinny(p(X), K, p(W), K, p(out2), N, M, N, K))
+    assert torch.equal(out, out2)  # slab order is fixed: bit-deterministic (no atomics)
