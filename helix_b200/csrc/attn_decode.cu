@@ -16,6 +16,7 @@
 #include <stdio.h>
 
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 #include "tma_host.h"
 
@@ -75,6 +76,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
   uint64_t* pv_done = bars + 4 * STAGES + 6;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4 * STAGES + 7);
 
+  pdl_launch_dependents();
+  pdl_wait();
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ctx = ctx_lens[b];
@@ -316,6 +319,8 @@ template <int D>
 __global__ void __launch_bounds__(D / 2)
 attn_decode_combine_kernel(const float* __restrict__ ws, bf16* __restrict__ out, int ldo, int Hq, int Hkv, int G,
                            int num_splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y;
   const int kvh = h / G, g = h % G;
   const float* base = ws + ((size_t)(b * Hkv + kvh) * num_splits) * G * (D + 2) + g * (D + 2);
@@ -349,14 +354,12 @@ cudaError_t launch(cudaStream_t stream, const AttnDecodeArgs& a) {
   if (!make_tmap_3d(&mk, a.k_cache, TM_BF16, D, PAGE, blocks, (uint64_t)D * 2, (uint64_t)PAGE * D * 2, 64, PAGE, 1)) return cudaErrorInvalidValue;
   if (!make_tmap_3d(&mv, a.v_cache, TM_BF16, D, PAGE, blocks, (uint64_t)D * 2, (uint64_t)PAGE * D * 2, 64, PAGE, 1)) return cudaErrorInvalidValue;
   dim3 grid(a.num_splits, a.Hkv, a.B);
-  attn_decode_kernel<D, G><<<grid, kThreads, DCfg<D>::SMEM, stream>>>(mk, mv, a.q, a.ldq, a.page_table, a.max_pages,
-                                                                     a.ctx_lens, a.workspace, a.Hkv, a.num_splits,
-                                                                     a.scale * 1.4426950408889634f);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(attn_decode_kernel<D, G>, grid, dim3(kThreads), DCfg<D>::SMEM, stream, true, mk, mv, a.q, a.ldq,
+                           a.page_table, a.max_pages, a.ctx_lens, a.workspace, a.Hkv, a.num_splits,
+                           a.scale * 1.4426950408889634f);
   if (e != cudaSuccess) return e;
-  attn_decode_combine_kernel<D><<<dim3(a.Hq, a.B), D / 2, 0, stream>>>(a.workspace, a.out, a.ldo, a.Hq, a.Hkv, G,
-                                                                      a.num_splits);
-  return cudaGetLastError();
+  return launch_k(attn_decode_combine_kernel<D>, dim3(a.Hq, a.B), dim3(D / 2), 0, stream, true,
+                  (const float*)a.workspace, a.out, a.ldo, a.Hq, a.Hkv, G, a.num_splits);
 }
 
 }  // namespace

@@ -131,7 +131,13 @@ int hbk_rope_kv_write(void* qkv, const int32_t* positions, const int32_t* slot_m
                                 (hb::bf16*)v_cache, T, Hq, Hkv, D, page_size));
 }
 int hbk_sample(const float* logits, int ldl, const float* temperature, const uint64_t* seed, int32_t* out, int B, int V) {
-  return kret(hb::sample_tokens(0, logits, ldl, temperature, seed, out, B, V));
+  void* scratch = nullptr;
+  cudaError_t e = cudaMalloc(&scratch, hb::sample_scratch_bytes(B, V));
+  if (e != cudaSuccess) return kret(e);
+  e = hb::sample_tokens(0, logits, ldl, temperature, seed, out, B, V, scratch);
+  cudaError_t e2 = cudaDeviceSynchronize();
+  cudaFree(scratch);
+  return kret(e != cudaSuccess ? e : e2);
 }
 int hbk_cls_pool_l2(const void* x, const int32_t* first_row, float* out, int B, int H) {
   return kret(hb::cls_pool_l2(0, (const hb::bf16*)x, first_row, out, B, H));

@@ -4,6 +4,7 @@
 #include <math.h>
 
 #include "kernels.h"
+#include "launch.h"
 
 namespace hb {
 namespace {
@@ -25,6 +26,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(256)
 sum_slabs_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, float* __restrict__ out, int ldo, int M,
                  int N) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y;
   const int n = blockIdx.x * 256 + threadIdx.x;
   if (n < N) out[(size_t)m * ldo + n] = slab_sum(ws, segs, M, N, m, n);
@@ -36,6 +39,8 @@ qkv_rope_kvwrite_kernel(const float* __restrict__ ws, const uint8_t* __restrict_
                         const int32_t* __restrict__ positions, const int32_t* __restrict__ slot_mapping,
                         const float* __restrict__ inv_freq, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
                         int M, int Hq, int Hkv, int D, int page_size) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.x, m = blockIdx.y, j = threadIdx.x;
   const int half = D / 2;
   if (j >= half) return;
@@ -65,67 +70,85 @@ qkv_rope_kvwrite_kernel(const float* __restrict__ ws, const uint8_t* __restrict_
   }
 }
 
-constexpr int kRT = 128;
-constexpr int kRC = 8;  // CTAs per row (thread-block cluster): the row's sum of squares is reduced through DSMEM
-constexpr int kRMaxPer = 8;  // elements cached per thread: rows up to 8*128*8 = 8192 wide
+constexpr int kRT = 512;
+constexpr int kRMaxVec = 4;  // float4 chunks cached per thread: rows up to 512*4*4 = 8192 wide
 
-__device__ __forceinline__ float ld_dsmem_f32(const float* local_ptr, uint32_t cta) {
-  uint32_t remote;
-  float v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
-               : "=r"(remote)
-               : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(local_ptr))), "r"(cta));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-  return v;
+__device__ __forceinline__ float4 slab_sum4(const float* __restrict__ ws, const uint8_t* __restrict__ segs, int M, int N,
+                                            int m, int n) {
+  const int ns = segs[n >> 7];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    if (s < ns) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + ((size_t)s * M + m) * N + n);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  for (int s = 8; s < ns; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(ws + ((size_t)s * M + m) * N + n);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  return acc;
 }
 
-__global__ void __cluster_dims__(kRC, 1, 1) __launch_bounds__(kRT)
+// one block per row: x = bf16(x + sum of slabs); xn = x * rsqrt(mean(x^2)+eps) * w
+__global__ void __launch_bounds__(kRT)
 resid_rmsnorm_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf16* __restrict__ x,
                      const bf16* __restrict__ w, bf16* __restrict__ xn, int M, int H, float eps) {
   __shared__ float red[kRT / 32];
-  __shared__ float part;
-  const int m = blockIdx.y;
-  const int chunk = (H + kRC - 1) / kRC;
-  const int n0 = blockIdx.x * chunk, n1 = min(H, n0 + chunk);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x;
   bf16* xr = x + (size_t)m * H;
-  float cache[kRMaxPer];
+  float4 cache[kRMaxVec];
   float ss = 0.f;
 #pragma unroll
-  for (int j = 0; j < kRMaxPer; ++j) {
-    const int n = n0 + threadIdx.x + j * kRT;
-    if (n < n1) {
-      const float v = bf16_round(__bfloat162float(xr[n]) + slab_sum(ws, segs, M, H, m, n));
-      cache[j] = v;
-      xr[n] = __float2bfloat16(v);
-      ss += v * v;
+  for (int j = 0; j < kRMaxVec; ++j) {
+    const int n = (threadIdx.x + j * kRT) * 4;
+    if (n < H) {
+      const float4 a = slab_sum4(ws, segs, M, H, m, n);
+      const uint2 xb = *reinterpret_cast<const uint2*>(xr + n);
+      const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb.x));
+      const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xb.y));
+      __nv_bfloat162 o01 = __floats2bfloat162_rn(x01.x + a.x, x01.y + a.y);
+      __nv_bfloat162 o23 = __floats2bfloat162_rn(x23.x + a.z, x23.y + a.w);
+      uint2 ob;
+      ob.x = *reinterpret_cast<uint32_t*>(&o01);
+      ob.y = *reinterpret_cast<uint32_t*>(&o23);
+      *reinterpret_cast<uint2*>(xr + n) = ob;
+      const float2 r01 = __bfloat1622float2(o01), r23 = __bfloat1622float2(o23);
+      cache[j] = make_float4(r01.x, r01.y, r23.x, r23.y);  // the ROUNDED residual feeds the norm (as in prefill)
+      ss += r01.x * r01.x + r01.y * r01.y + r23.x * r23.x + r23.y * r23.y;
     }
   }
-  if (!w) return;  // residual update only (uniform across the whole cluster)
+  if (!w) return;
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < kRT / 32; ++i) t += red[i];
-    part = t;
-  }
-  // publish `part` to the cluster, then read all kRC partials in rank order (fixed order -> deterministic)
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  float tot = 0.f;
+  float t = (threadIdx.x & 31) < kRT / 32 ? red[threadIdx.x & 31] : 0.f;
+  t = warp_sum(t);
+  const float inv = rsqrtf(t / (float)H + eps);
 #pragma unroll
-  for (int c = 0; c < kRC; ++c) tot += ld_dsmem_f32(&part, c);
-  const float inv = rsqrtf(tot / (float)H + eps);
-#pragma unroll
-  for (int j = 0; j < kRMaxPer; ++j) {
-    const int n = n0 + threadIdx.x + j * kRT;
-    if (n < n1) xn[(size_t)m * H + n] = __float2bfloat16(cache[j] * inv * __bfloat162float(w[n]));
+  for (int j = 0; j < kRMaxVec; ++j) {
+    const int n = (threadIdx.x + j * kRT) * 4;
+    if (n < H) {
+      const uint2 wb = *reinterpret_cast<const uint2*>(w + n);
+      const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wb.x));
+      const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wb.y));
+      __nv_bfloat162 o01 = __floats2bfloat162_rn(cache[j].x * inv * w01.x, cache[j].y * inv * w01.y);
+      __nv_bfloat162 o23 = __floats2bfloat162_rn(cache[j].z * inv * w23.x, cache[j].w * inv * w23.y);
+      uint2 ob;
+      ob.x = *reinterpret_cast<uint32_t*>(&o01);
+      ob.y = *reinterpret_cast<uint32_t*>(&o23);
+      *reinterpret_cast<uint2*>(xn + (size_t)m * H + n) = ob;
+    }
   }
-  // no CTA may exit while a peer can still read its `part`
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256)
 swiglu_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf16* __restrict__ h, int M, int F) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y;
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= F) return;
@@ -138,25 +161,21 @@ swiglu_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf
 }  // namespace
 
 cudaError_t dec_sum_slabs(cudaStream_t s, const float* ws, const SkinnyPlan& p, float* out, int ldo, int M, int N) {
-  sum_slabs_kernel<<<dim3((N + 255) / 256, M), 256, 0, s>>>(ws, p.seg_count, out, ldo, M, N);
-  return cudaGetLastError();
+  return launch_k(sum_slabs_kernel, dim3((N + 255) / 256, M), dim3(256), 0, s, true, ws, p.seg_count, out, ldo, M, N);
 }
 cudaError_t dec_qkv_rope_kvwrite(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* qkv_out,
                                  const int32_t* positions, const int32_t* slot_mapping, const float* inv_freq,
                                  bf16* k_cache, bf16* v_cache, int M, int Hq, int Hkv, int D, int page_size) {
-  qkv_rope_kvwrite_kernel<<<dim3(Hq + 2 * Hkv, M), D / 2, 0, s>>>(ws, p.seg_count, qkv_out, positions, slot_mapping,
-                                                                  inv_freq, k_cache, v_cache, M, Hq, Hkv, D, page_size);
-  return cudaGetLastError();
+  return launch_k(qkv_rope_kvwrite_kernel, dim3(Hq + 2 * Hkv, M), dim3(D / 2), 0, s, true, ws, p.seg_count, qkv_out,
+                  positions, slot_mapping, inv_freq, k_cache, v_cache, M, Hq, Hkv, D, page_size);
 }
 cudaError_t dec_resid_rmsnorm(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* x, const bf16* w, bf16* xn,
                               int M, int H, float eps) {
-  if (H > kRC * kRT * kRMaxPer) return cudaErrorInvalidValue;
-  resid_rmsnorm_kernel<<<dim3(kRC, M), kRT, 0, s>>>(ws, p.seg_count, x, w, xn, M, H, eps);
-  return cudaGetLastError();
+  if (H > kRT * kRMaxVec * 4 || (H % 4)) return cudaErrorInvalidValue;
+  return launch_k(resid_rmsnorm_kernel, dim3(M), dim3(kRT), 0, s, true, ws, p.seg_count, x, w, xn, M, H, eps);
 }
 cudaError_t dec_swiglu(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* h, int M, int F) {
-  swiglu_kernel<<<dim3((F + 255) / 256, M), 256, 0, s>>>(ws, p.seg_count, h, M, F);
-  return cudaGetLastError();
+  return launch_k(swiglu_kernel, dim3((F + 255) / 256, M), dim3(256), 0, s, true, ws, p.seg_count, h, M, F);
 }
 
 }  // namespace hb

@@ -142,6 +142,7 @@ size_t Engine::workspace_bytes() const {
     b += al256((size_t)cfg_.max_seqs * d.vocab * 4);          // logits
     b += al256(attn_decode_workspace_floats(cfg_.max_seqs, d.heads, d.head_dim, 16) * 4);
     b += al256((size_t)cfg_.max_seqs * 4);                    // sampled
+    b += al256(sample_scratch_bytes(cfg_.max_seqs, d.vocab)); // argmax partials
     b += al256(skinny_ws_bytes(148));                         // decode GEMM partial slabs
   }
   return b;
@@ -263,6 +264,7 @@ int Engine::alloc_runtime() {
     logits_ = (float*)take((size_t)cfg_.max_seqs * d.vocab * 4);
     dec_ws_ = (float*)take(attn_decode_workspace_floats(cfg_.max_seqs, d.heads, d.head_dim, 16) * 4);
     sampled_ = (int32_t*)take((size_t)cfg_.max_seqs * 4);
+    sample_ws_ = take(sample_scratch_bytes(cfg_.max_seqs, d.vocab));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device);
     skinny_ws_ = (float*)take(skinny_ws_bytes(148));
@@ -499,7 +501,7 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
     GemmArgs g{h_, H, model_.lm_head, H, logits_, d.vocab, nullptr, 0, nullptr, B, d.vocab, H, EPI_F32, 0};
     SPAN(gcat, gwork(B, d.vocab, H), gemm_bf16_tn(stream_, g));
   }
-  LAUNCH(sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab));
+  LAUNCH(sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab, sample_ws_));
   return HB_OK;
 }
 
@@ -553,7 +555,7 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
   }
   SPAN(4, wbytes(d.vocab, H), gemm_skinny(stream_, plan_head_, xn_, H, model_.lm_head, H, skinny_ws_, B, d.vocab, H));
   SPAN(3, 8.0 * B * d.vocab, dec_sum_slabs(stream_, skinny_ws_, plan_head_, logits_, d.vocab, B, d.vocab));
-  SPAN(3, 4.0 * B * d.vocab, sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab));
+  SPAN(3, 4.0 * B * d.vocab, sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab, sample_ws_));
   return HB_OK;
 }
 

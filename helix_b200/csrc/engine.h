@@ -123,6 +123,7 @@ class Engine {
   SkinnyPlan plan_qkv_{}, plan_o_{}, plan_gu_{}, plan_down_{}, plan_head_{};
   int skinny_max_b_ = 0;
   int32_t* sampled_ = nullptr;
+  void* sample_ws_ = nullptr;
   uint8_t* d_step_ = nullptr;  // per-step int/float inputs (layout())
   uint8_t* h_step_ = nullptr;  // pinned mirror
   int32_t* h_sampled_ = nullptr;

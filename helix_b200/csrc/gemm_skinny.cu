@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 #include "tma_host.h"
 
@@ -27,7 +28,7 @@ constexpr int BLOCK_N = 128;  // weight rows per tile (UMMA M)
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
-constexpr int kSmemBudget = 227 * 1024;
+constexpr int kSmemBudget = 110 * 1024;  // two CTAs per SM: the NEXT kernel's CTA prefetches its weights while this one drains
 
 template <int MPAD>
 struct SCfg {
@@ -52,7 +53,7 @@ __host__ __device__ inline int owner_of(long long u, long long U, int G) {
 }
 
 template <int MPAD>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                    float* __restrict__ ws, int M, int N, int K) {
   using C = SCfg<MPAD>;
@@ -75,6 +76,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   const int G = gridDim.x;
   const long long u0 = range_start(blockIdx.x, U, G), u1 = range_start(blockIdx.x + 1, U, G);
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_w);
     tma_prefetch_desc(&map_x);
@@ -99,9 +101,23 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
+      // Weights are static: fill the whole ring with W tiles BEFORE waiting for the producer of X
+      // (programmatic dependent launch) - the HBM stream never stops between back-to-back projections.
+      const long long pre_end = min(u1, u0 + STAGES);
+      for (long long u = u0; u < pre_end; ++u) {
+        const int s = (int)(u - u0);
+        mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+        tma_load_2d(smem_w + s * C::W_BYTES, &map_w, &full_bar[s], (int)(u % KB) * BLOCK_K, (int)(u / KB) * BLOCK_N, kEvictFirst);
+      }
+      pdl_wait();
+      for (long long u = u0; u < pre_end; ++u) {
+        const int s = (int)(u - u0);
+        tma_load_2d(smem_x + s * C::X_BYTES, &map_x, &full_bar[s], (int)(u % KB) * BLOCK_K, 0, kEvictLast);
+      }
       int s = 0;
-      uint32_t phase = 0;
-      for (long long u = u0; u < u1; ++u) {
+      uint32_t phase = 1;  // the ring has been filled once
+      if (pre_end - u0 < STAGES) { s = (int)(pre_end - u0); phase = 0; }
+      for (long long u = pre_end; u < u1; ++u) {
         const int tile = (int)(u / KB), kb = (int)(u % KB);
         mbar_wait(&empty_bar[s], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
@@ -148,6 +164,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     const int row = q * 32 + lane;  // weight row within the tile == TMEM lane
     int it = 0;
     long long u = u0;
+    pdl_wait();  // ws is an activation buffer: never written before the predecessors are done
     while (u < u1) {
       const int tile = (int)(u / KB);
       const long long seg_end = min(u1, (long long)(tile + 1) * KB);
@@ -201,8 +218,7 @@ cudaError_t launch(cudaStream_t stream, const SkinnyPlan& plan, const bf16* X, i
   CUtensorMap mw, mx;
   if (!make_tmap_2d(&mw, W, TM_BF16, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BLOCK_K, BLOCK_N)) return cudaErrorInvalidValue;
   if (!make_tmap_2d(&mx, X, TM_BF16, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, BLOCK_K, MPAD)) return cudaErrorInvalidValue;
-  gemm_skinny_kernel<MPAD><<<plan.grid, kThreads, C::SMEM, stream>>>(mw, mx, ws, M, N, K);
-  return cudaGetLastError();
+  return launch_k(gemm_skinny_kernel<MPAD>, dim3(plan.grid), dim3(kThreads), C::SMEM, stream, true, mw, mx, ws, M, N, K);
 }
 
 template <int MPAD>

@@ -3,6 +3,7 @@
 #include <math.h>
 
 #include "kernels.h"
+#include "launch.h"
 
 namespace hb {
 namespace {
@@ -44,6 +45,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 __global__ void embed_gather_kernel(const int32_t* __restrict__ tokens, const bf16* __restrict__ table,
                                     bf16* __restrict__ x, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x;
   const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)tokens[t] * H);
   uint4* dst = reinterpret_cast<uint4*>(x + (size_t)t * H);
@@ -54,6 +57,8 @@ __global__ void __launch_bounds__(kRowThreads)
 rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ out,
                const int32_t* __restrict__ row_index, int H, float eps) {
   __shared__ float red[kRowThreads / 32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x;
   const size_t src_row = row_index ? (size_t)row_index[r] : (size_t)r;
   const uint4* src = reinterpret_cast<const uint4*>(x + src_row * H);
@@ -213,12 +218,43 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
   return z ^ (z >> 31);
 }
 
-__global__ void __launch_bounds__(1024)
-sample_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ temperature,
-              const uint64_t* __restrict__ seed, int32_t* __restrict__ out, int V) {
-  __shared__ float sval[32];
-  __shared__ int sidx[32];
-  const int b = blockIdx.x;
+constexpr int kSampleChunk = 4096;  // vocabulary columns per stage-1 block
+
+__device__ __forceinline__ void argmax_merge(float& best, int& bi, float ov, int oi) {
+  if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+}
+template <int NT>
+__device__ __forceinline__ void block_argmax(float& best, int& bi, float* sval, int* sidx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    argmax_merge(best, bi, ov, oi);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sval[w] = best; sidx[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    best = (l < NT / 32) ? sval[l] : -INFINITY;
+    bi = (l < NT / 32) ? sidx[l] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      argmax_merge(best, bi, ov, oi);
+    }
+  }
+}
+
+// stage 1: grid (chunks, B): per-chunk argmax of logits/T + Gumbel noise -> part[b][chunk]
+__global__ void __launch_bounds__(256)
+sample_stage1_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ temperature,
+                     const uint64_t* __restrict__ seed, float* __restrict__ part_val, int* __restrict__ part_idx, int V) {
+  __shared__ float sval[8];
+  __shared__ int sidx[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y, chunk = blockIdx.x;
   const float* row = logits + (size_t)b * ldl;
   const float temp = temperature ? temperature[b] : 0.f;
   const bool greedy = !(temp > 0.f);
@@ -226,35 +262,39 @@ sample_kernel(const float* __restrict__ logits, int ldl, const float* __restrict
   const uint64_t sd = seed ? seed[b] : 0;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+  const int v_end = min(V, (chunk + 1) * kSampleChunk);
+  for (int v = chunk * kSampleChunk + threadIdx.x; v < v_end; v += 256) {
     float x = row[v] * inv_t;
     if (!greedy) {
       const uint64_t h = mix64(sd ^ (0xD1B54A32D192ED03ull * (uint64_t)(v + 1)));
-      const float u = ((h >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+      const float u = ((float)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0,1]
       x += -__logf(-__logf(u));
     }
     if (x > best || (x == best && v < bi)) { best = x; bi = v; }
   }
+  block_argmax<256>(best, bi, sval, sidx);
+  if (threadIdx.x == 0) {
+    part_val[b * gridDim.x + chunk] = best;
+    part_idx[b * gridDim.x + chunk] = bi;
+  }
+}
+// stage 2: one warp per row merges the chunk winners (lowest index wins ties, as in stage 1)
+__global__ void __launch_bounds__(32)
+sample_stage2_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int32_t* __restrict__ out,
+                     int chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < chunks; c += 32) argmax_merge(best, bi, part_val[b * chunks + c], part_idx[b * chunks + c]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    argmax_merge(best, bi, ov, oi);
   }
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { sval[w] = best; sidx[w] = bi; }
-  __syncthreads();
-  if (w == 0) {
-    best = (l < (int)(blockDim.x >> 5)) ? sval[l] : -INFINITY;
-    bi = (l < (int)(blockDim.x >> 5)) ? sidx[l] : 0x7fffffff;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (l == 0) out[b] = bi;
-  }
+  if (threadIdx.x == 0) out[b] = bi < 0x7fffffff ? bi : 0;  // all-NaN row: emit a valid id, never an out-of-range one
 }
 
 __global__ void __launch_bounds__(kRowThreads)
@@ -277,15 +317,13 @@ cls_pool_l2_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ first
 cudaError_t embed_gather(cudaStream_t s, const int32_t* tokens, const bf16* table, bf16* x, int T, int H) {
   if (T <= 0) return cudaSuccess;
   if (H % 8) return cudaErrorInvalidValue;
-  embed_gather_kernel<<<T, 128, 0, s>>>(tokens, table, x, H);
-  return cudaGetLastError();
+  return launch_k(embed_gather_kernel, dim3(T), dim3(128), 0, s, true, tokens, table, x, H);
 }
 cudaError_t rmsnorm(cudaStream_t s, const bf16* x, const bf16* w, bf16* out, const int32_t* row_index, int rows, int H,
                     float eps) {
   if (rows <= 0) return cudaSuccess;
   if (H % 8) return cudaErrorInvalidValue;
-  rmsnorm_kernel<<<rows, kRowThreads, 0, s>>>(x, w, out, row_index, H, eps);
-  return cudaGetLastError();
+  return launch_k(rmsnorm_kernel, dim3(rows), dim3(kRowThreads), 0, s, true, x, w, out, row_index, H, eps);
 }
 cudaError_t layernorm(cudaStream_t s, const bf16* x, const bf16* gamma, const bf16* beta, bf16* out, int rows, int H,
                       float eps) {
@@ -311,11 +349,18 @@ cudaError_t rope_kv_write(cudaStream_t s, bf16* qkv, const int32_t* positions, c
                                                          Hkv, D, page_size);
   return cudaGetLastError();
 }
+size_t sample_scratch_bytes(int B, int V) { return (size_t)B * ((V + kSampleChunk - 1) / kSampleChunk) * 8; }
+
 cudaError_t sample_tokens(cudaStream_t s, const float* logits, int ldl, const float* temperature, const uint64_t* seed,
-                          int32_t* out, int B, int V) {
+                          int32_t* out, int B, int V, void* scratch) {
   if (B <= 0) return cudaSuccess;
-  sample_kernel<<<B, 1024, 0, s>>>(logits, ldl, temperature, seed, out, V);
-  return cudaGetLastError();
+  const int chunks = (V + kSampleChunk - 1) / kSampleChunk;
+  float* pv = static_cast<float*>(scratch);
+  int* pi = reinterpret_cast<int*>(pv + (size_t)B * chunks);
+  cudaError_t e = launch_k(sample_stage1_kernel, dim3(chunks, B), dim3(256), 0, s, true, logits, ldl, temperature, seed, pv,
+                           pi, V);
+  if (e != cudaSuccess) return e;
+  return launch_k(sample_stage2_kernel, dim3(B), dim3(32), 0, s, true, (const float*)pv, (const int*)pi, out, chunks);
 }
 cudaError_t cls_pool_l2(cudaStream_t s, const bf16* x, const int32_t* first_row, float* out, int B, int H) {
   if (B <= 0) return cudaSuccess;

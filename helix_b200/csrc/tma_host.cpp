@@ -1,5 +1,10 @@
 #include "tma_host.h"
 
+#include <stdlib.h>
+#include <string.h>
+
+#include "launch.h"
+
 #include <stdio.h>
 
 #include <mutex>
@@ -22,6 +27,14 @@ void resolve() {
 }  // namespace
 
 const char* tmap_last_error() { return g_err; }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("HB_PDL");
+    return !(e && !strcmp(e, "0"));
+  }();
+  return on;
+}
 
 bool make_tmap_2d(CUtensorMap* out, const void* gptr, TmDtype dt, uint64_t inner, uint64_t outer,
                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
