@@ -95,13 +95,6 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-class ArenaView:
-    """Exposes the engine's weight arena to torch (for the NCCL broadcast) without copying."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-
-
 def make_prompts(rank, sessions, seq, vocab):
     return [np.random.default_rng(1000 * rank + i).integers(0, vocab, size=seq, dtype=np.int64).astype(np.int32)
             for i in range(sessions)]
@@ -204,6 +197,7 @@ def main():
     import torch.distributed as dist
     import helix_b200 as hb
     from helix_b200 import configs
+    from helix_b200.replica import ArenaView, broadcast_buffer
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -229,7 +223,7 @@ def main():
         probe = arena[:: max(1, nbytes // 65536)].clone()
         barrier()
         t0 = time.perf_counter()
-        dist.broadcast(arena, src=0)
+        broadcast_buffer(dist, arena, src=0)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         chk = arena[:: max(1, nbytes // 65536)].to(torch.int32).sum().reshape(1).float()

@@ -1,0 +1,203 @@
+"""OpenAI-compatible HTTP front of a B200Runtime (`Runtime.URL()` must serve
+POST /v1/chat/completions (JSON and `stream:true` SSE ending in a chunk with a non-empty finish_reason, which is what
+closes the control-plane stream — api/pkg/openai/helix_openai_client.go:197), POST /v1/embeddings and GET /v1/models).
+
+Row F1 of the scope table: a small stdlib server, one thread per connection, token ids in/out of the engine C ABI.
+Tokenisation is pluggable; without a tokenizer file (no checkpoints offline) a byte-level stand-in is used and
+`input` / `prompt` may also be given as token-id arrays (the reference accepts `[][]int`, types/types.go:2707-2730).
+"""
+import json
+import threading
+import time
+import uuid
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+
+from .engine import HBError, Sampling
+
+
+class ByteTokenizer:
+    """UTF-8 bytes shifted past a few control ids; deterministic stand-in for random-init models."""
+    BOS, EOS, OFFSET = 1, 2, 3
+
+    def encode(self, text):
+        return [self.BOS] + [b + self.OFFSET for b in text.encode("utf-8")]
+
+    def decode(self, ids):
+        return bytes((i - self.OFFSET) % 256 for i in ids if i >= self.OFFSET).decode("utf-8", errors="replace")
+
+    def chat(self, messages):
+        return self.encode("".join(f"<|{m.get('role', 'user')}|>\n{m.get('content', '')}\n" for m in messages) + "<|assistant|>\n")
+
+
+class HFTokenizer:
+    """`tokenizers` JSON file + the Llama-3 chat template."""
+
+    def __init__(self, path, eos_token="<|eot_id|>"):
+        from tokenizers import Tokenizer
+        self.tk = Tokenizer.from_file(path)
+        self.EOS = self.tk.token_to_id(eos_token) if self.tk.token_to_id(eos_token) is not None else -1
+
+    def encode(self, text):
+        return self.tk.encode(text, add_special_tokens=False).ids
+
+    def decode(self, ids):
+        return self.tk.decode(ids)
+
+    def chat(self, messages):
+        s = "<|begin_of_text|>"
+        for m in messages:
+            s += f"<|start_header_id|>{m.get('role', 'user')}<|end_header_id|>\n\n{m.get('content', '')}<|eot_id|>"
+        return self.encode(s + "<|start_header_id|>assistant<|end_header_id|>\n\n")
+
+
+def chat_chunk(cid, model, created, delta, finish_reason):
+    return {"id": cid, "object": "chat.completion.chunk", "created": created, "model": model,
+            "choices": [{"index": 0, "delta": delta, "finish_reason": finish_reason}]}
+
+
+class OpenAIServer:
+    def __init__(self, runtime, tokenizer=None, host="127.0.0.1", port=0):
+        self.rt = runtime
+        self.tok = tokenizer or ByteTokenizer()
+        self.host, self.port = host, port
+        self.httpd = None
+
+    # ---- request handlers (pure functions of the parsed body: unit-testable without sockets)
+    def models(self):
+        return {"object": "list", "data": [{"id": m, "object": "model", "owned_by": "helix-b200"} for m in self.rt.list_models()]}
+
+    def embeddings(self, body):
+        inp = body.get("input")
+        if isinstance(inp, str):
+            seqs = [self.tok.encode(inp)]
+        elif isinstance(inp, list) and inp and isinstance(inp[0], int):
+            seqs = [inp]
+        elif isinstance(inp, list):
+            seqs = [self.tok.encode(x) if isinstance(x, str) else list(x) for x in inp]
+        else:
+            raise ValueError("input must be a string, a list of strings or token arrays")
+        vocab = self.rt.engine.desc.vocab
+        seqs = [[t % vocab for t in s][: self.rt.engine.cfg.max_ctx] for s in seqs]
+        vecs = self.rt.engine.embed(seqs)
+        return {"object": "list", "model": body.get("model", self.rt.p.model),
+                "data": [{"object": "embedding", "index": i, "embedding": [float(x) for x in v]} for i, v in enumerate(vecs)],
+                "usage": {"prompt_tokens": sum(map(len, seqs)), "total_tokens": sum(map(len, seqs))}}
+
+    def _submit_chat(self, body):
+        if body.get("model") and body["model"] != self.rt.p.model:
+            raise ValueError(f"model mismatch, expecting {self.rt.p.model}")  # openai_chat_handlers.go:44-50
+        msgs = body.get("messages")
+        ids = self.tok.chat(msgs) if msgs is not None else body["prompt"]
+        vocab = self.rt.engine.desc.vocab
+        ids = [t % vocab for t in ids]
+        temp = body.get("temperature", 0.0) or 0.0   # the runner already rewrote 0 -> 0.1 (openai_chat_handlers.go:52-58)
+        sp = Sampling(temperature=float(temp), seed=int(body.get("seed", 0) or 0),
+                      max_tokens=int(body.get("max_tokens") or body.get("max_completion_tokens") or 256),
+                      eos_token=getattr(self.tok, "EOS", -1))
+        return self.rt.engine.submit(ids, sp), len(ids), sp
+
+    def chat_stream(self, body):
+        """Yields SSE chunk dicts; the last one carries finish_reason."""
+        eng = self.rt.engine
+        rid, n_prompt, sp = self._submit_chat(body)
+        cid, created, model = "chatcmpl-" + uuid.uuid4().hex[:24], int(time.time()), self.rt.p.model
+        yield chat_chunk(cid, model, created, {"role": "assistant", "content": ""}, None)
+        n, fin = 0, 0
+        try:
+            while not fin:
+                eng.wait(rid, 30000)
+                toks, fin = eng.poll(rid)
+                if toks:
+                    n += len(toks)
+                    text = self.tok.decode([t for t in toks if t != sp.eos_token])
+                    if text:
+                        yield chat_chunk(cid, model, created, {"content": text}, None)
+            reason = "length" if n >= sp.max_tokens else "stop"
+            yield chat_chunk(cid, model, created, {}, reason if fin == 1 else "stop")
+        finally:
+            try:
+                if not fin:
+                    eng.cancel(rid)      # client went away: free the sequence's KV pages
+                else:
+                    eng.release(rid)
+            except HBError:
+                pass
+
+    def chat(self, body):
+        text, reason, cid = "", "stop", None
+        for ch in self.chat_stream(body):
+            cid = ch["id"]
+            c = ch["choices"][0]
+            text += c["delta"].get("content", "") or ""
+            reason = c["finish_reason"] or reason
+        return {"id": cid, "object": "chat.completion", "created": int(time.time()), "model": self.rt.p.model,
+                "choices": [{"index": 0, "message": {"role": "assistant", "content": text}, "finish_reason": reason}],
+                "usage": {"prompt_tokens": 0, "completion_tokens": 0, "total_tokens": 0}}
+
+    # ---- socket plumbing
+    def start(self):
+        srv = self
+
+        class H(BaseHTTPRequestHandler):
+            protocol_version = "HTTP/1.1"
+
+            def log_message(self, *a):
+                pass
+
+            def _json(self, code, obj):
+                data = json.dumps(obj).encode()
+                self.send_response(code)
+                self.send_header("Content-Type", "application/json")
+                self.send_header("Content-Length", str(len(data)))
+                self.end_headers()
+                self.wfile.write(data)
+
+            def do_GET(self):
+                if self.path.rstrip("/") in ("/v1/models", "/models"):
+                    self._json(200, srv.models())
+                elif self.path == "/healthz":
+                    self._json(200 if srv.rt.status() else 503, {"status": srv.rt.status()})
+                else:
+                    self._json(404, {"error": "not found"})
+
+            def do_POST(self):
+                try:
+                    n = int(self.headers.get("Content-Length", "0"))
+                    if n > 10 * 1024 * 1024:   # openai_chat_handlers.go:40
+                        return self._json(413, {"error": "request too large"})
+                    body = json.loads(self.rfile.read(n) or b"{}")
+                    path = self.path.rstrip("/")
+                    if path.endswith("/embeddings"):
+                        return self._json(200, srv.embeddings(body))
+                    if path.endswith("/chat/completions") or path.endswith("/completions"):
+                        if not body.get("stream"):
+                            return self._json(200, srv.chat(body))
+                        self.send_response(200)
+                        self.send_header("Content-Type", "text/event-stream")
+                        self.send_header("Cache-Control", "no-cache")
+                        self.send_header("Connection", "close")
+                        self.end_headers()
+                        for ch in srv.chat_stream(body):
+                            self.wfile.write(b"data: " + json.dumps(ch).encode() + b"\n\n")
+                            self.wfile.flush()
+                        self.wfile.write(b"data: [DONE]\n\n")
+                        self.wfile.flush()
+                        self.close_connection = True
+                        return
+                    self._json(404, {"error": "not found"})
+                except (ValueError, KeyError, HBError) as e:
+                    self._json(400, {"error": {"message": str(e), "type": "invalid_request_error"}})
+                except (BrokenPipeError, ConnectionResetError):
+                    pass
+
+        self.httpd = ThreadingHTTPServer((self.host, self.port), H)
+        self.httpd.daemon_threads = True
+        self.port = self.httpd.server_address[1]
+        threading.Thread(target=self.httpd.serve_forever, daemon=True).start()
+        return f"http://{self.host}:{self.port}"
+
+    def stop(self):
+        if self.httpd:
+            self.httpd.shutdown()
+            self.httpd.server_close()
+            self.httpd = None

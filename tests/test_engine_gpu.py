@@ -194,3 +194,57 @@ def test_bert_embed_matches_golden_and_oracle(golden_dir):
             e.submit([1, 2], hb.Sampling())
     seqs = [g["tokens"][offs[i]:offs[i + 1]] for i in range(len(lens))]
     assert np.abs(out - bert_embed(d, sd, seqs)).max() <= 1e-2
+
+
+def test_runtime_lifecycle_and_openai_http_front():
+    """runner.Runtime mirror end to end on the GPU: Start -> Warm -> URL() serves the three OpenAI routes -> Stop."""
+    import json
+    import urllib.request
+    from helix_b200.runtime import B200Runtime, B200RuntimeParams
+
+    d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000)
+    rt = B200Runtime(B200RuntimeParams(model="tiny", desc=d, state_dict=weights.llama_state_dict(d, 0, 0.02),
+                                       args=["--max-num-seqs", "4", "--max-model-len", "256"]))
+    assert rt.status() == ""
+    rt.start()
+    try:
+        rt.warm("tiny")
+        assert rt.status().startswith("running") and rt.runtime() == "vllm" and rt.list_models() == ["tiny"]
+        base = rt.url()
+        models = json.load(urllib.request.urlopen(base + "/v1/models"))
+        assert models["data"][0]["id"] == "tiny"
+
+        def post(path, body):
+            req = urllib.request.Request(base + path, json.dumps(body).encode(), {"Content-Type": "application/json"})
+            return urllib.request.urlopen(req, timeout=60)
+        r = json.load(post("/v1/chat/completions", {"model": "tiny", "messages": [{"role": "user", "content": "hello"}],
+                                                     "max_tokens": 6}))
+        assert r["object"] == "chat.completion" and r["choices"][0]["finish_reason"] in ("stop", "length")
+        lines = [l for l in post("/v1/chat/completions", {"model": "tiny", "stream": True, "max_tokens": 5,
+                                                          "messages": [{"role": "user", "content": "hello"}]}).read().decode().split("\n\n") if l]
+        assert lines[-1] == "data: [DONE]" and all(l.startswith("data: ") for l in lines)
+        last = json.loads(lines[-2][6:])
+        assert last["choices"][0]["finish_reason"]
+        try:
+            post("/v1/chat/completions", {"model": "wrong", "messages": []})
+            assert False
+        except urllib.error.HTTPError as e:
+            assert e.code == 400
+    finally:
+        rt.stop()
+    assert rt.status() == ""
+    # encoder runtime (--task embed)
+    b = configs.tiny_bert(layers=2, vocab=1000)
+    rt = B200Runtime(B200RuntimeParams(model="tiny-embed", desc=b, state_dict=weights.bert_state_dict(b, 5, 0.05),
+                                       args=["--task", "embed", "--max-model-len", "512"]))
+    rt.start()
+    try:
+        rt.warm("tiny-embed")
+        req = urllib.request.Request(rt.url() + "/v1/embeddings", json.dumps({"input": ["abc", "defgh"], "model": "tiny-embed"}).encode(),
+                                     {"Content-Type": "application/json"})
+        out = json.load(urllib.request.urlopen(req, timeout=60))
+        assert len(out["data"]) == 2 and len(out["data"][0]["embedding"]) == b.hidden
+        v = np.array(out["data"][1]["embedding"])
+        assert abs(np.linalg.norm(v) - 1.0) < 1e-3
+    finally:
+        rt.stop()

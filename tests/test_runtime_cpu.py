@@ -1,0 +1,101 @@
+"""CPU: host-side Runtime mirror — vLLM-arg contract (bit-exact integers) and OpenAI wire framing (stub engine)."""
+import json
+
+import pytest
+
+from helix_b200 import runtime as R
+from helix_b200.server import ByteTokenizer, OpenAIServer, chat_chunk
+from oracle import scheduler_ref as S
+
+GB = 1024 ** 3
+
+
+def test_args_from_the_scheduler_round_trip():
+    # what RunnerController.substituteVLLMArgsPlaceholders emits (scheduler/runner.go:1222-1259) ...
+    args = S.substitute_vllm_args(["--max-model-len", "8192", "--max-num-seqs", "64"], 80 * GB, 8 * GB)
+    p = R.parse_vllm_args(["--host", "127.0.0.1", "--port", "1234"] + args)
+    assert p.gpu_memory_utilization == 0.10 and p.max_num_seqs == 64 and p.max_model_len == 8192 and not p.task_embed
+    assert R.parse_vllm_args(["--task", "embed", "--trust-remote-code"]).task_embed
+    assert R.parse_vllm_args([]).max_num_seqs == 256  # types/memory.go:11
+    # ... and the budget the engine derives: exact bytes when the slot carries them, ratio*perGPU otherwise
+    assert R.memory_budget(8 * GB, 80 * GB, 0.10) == 8 * GB
+    assert R.memory_budget(0, 80 * GB, 0.10) == 8 * GB
+    assert R.memory_budget(0, 0, None) == 0
+
+
+class StubEngine:
+    """Scripted engine: yields the given token groups, one group per poll."""
+
+    class _D:
+        vocab = 260
+        hidden = 4
+
+    class _C:
+        max_ctx = 64
+
+    def __init__(self, groups):
+        self.groups, self.i, self.desc, self.cfg = groups, 0, self._D(), self._C()
+        self.cancelled = self.released = False
+
+    def submit(self, ids, sp):
+        self.prompt, self.sp = list(ids), sp
+        return 7
+
+    def wait(self, rid, ms):
+        return True
+
+    def poll(self, rid):
+        g = self.groups[self.i]
+        self.i += 1
+        return g, (1 if self.i == len(self.groups) else 0)
+
+    def cancel(self, rid):
+        self.cancelled = True
+
+    def release(self, rid):
+        self.released = True
+
+    def embed(self, seqs):
+        return [[float(len(s)), 0.0, 0.0, 1.0] for s in seqs]
+
+
+class StubRuntime:
+    def __init__(self, eng):
+        self.engine = eng
+        self.p = R.B200RuntimeParams(model="m")
+
+    def list_models(self):
+        return ["m"]
+
+    def status(self):
+        return "running"
+
+
+def test_chat_sse_framing_and_finish_reason():
+    tok = ByteTokenizer()
+    hi = [b + tok.OFFSET for b in b"hi"]
+    eng = StubEngine([hi[:1], hi[1:], []])
+    srv = OpenAIServer(StubRuntime(eng), tok)
+    chunks = list(srv.chat_stream({"model": "m", "messages": [{"role": "user", "content": "x"}], "max_tokens": 5, "stream": True}))
+    assert chunks[0]["choices"][0]["delta"] == {"role": "assistant", "content": ""}
+    assert "".join(c["choices"][0]["delta"].get("content", "") for c in chunks) == "hi"
+    assert [c["choices"][0]["finish_reason"] for c in chunks[:-1]] == [None] * (len(chunks) - 1)
+    assert chunks[-1]["choices"][0]["finish_reason"] == "stop"      # non-empty: closes the control-plane stream
+    assert all(c["object"] == "chat.completion.chunk" and c["id"] == chunks[0]["id"] for c in chunks)
+    assert eng.released and eng.prompt[0] == tok.BOS and eng.sp.max_tokens == 5
+    json.dumps(chunks)  # serialisable
+    with pytest.raises(ValueError):
+        list(srv.chat_stream({"model": "other", "messages": []}))
+    eng2 = StubEngine([hi, hi[:1]])
+    out = OpenAIServer(StubRuntime(eng2), tok).chat({"messages": [{"role": "user", "content": "x"}], "max_tokens": 3})
+    assert out["choices"][0]["message"]["content"] == "hih" and out["choices"][0]["finish_reason"] == "length"
+
+
+def test_embeddings_accepts_all_reference_input_forms():
+    srv = OpenAIServer(StubRuntime(StubEngine([])), ByteTokenizer())
+    for inp, n in (("abc", 1), (["a", "bcd"], 2), ([[1, 2, 3], [4]], 2), ([5, 6], 1)):
+        r = srv.embeddings({"input": inp, "model": "m"})
+        assert len(r["data"]) == n and r["data"][0]["object"] == "embedding" and len(r["data"][0]["embedding"]) == 4
+        assert r["usage"]["prompt_tokens"] > 0
+    assert srv.models()["data"][0]["id"] == "m"
+    assert chat_chunk("i", "m", 1, {}, "stop")["choices"][0]["finish_reason"] == "stop"
