@@ -115,6 +115,58 @@ def serve_once(e, hb, prompts, decode):
     return got
 
 
+def bench_bge(args):
+    """BASELINE configs[2] (extra line, not the headline): bge-base-en-shaped encoder, batch-encode `--chunks` x 512-token
+    synthetic chunks through hb_embed (host token buffers in, fp32 vectors out)."""
+    import torch
+    import helix_b200 as hb
+    from helix_b200 import configs
+    desc = configs.bge_base()
+    e = hb.Engine(hb.EngineConfig(device=0, max_seqs=64, max_ctx=512, max_batched_tokens=args.max_batched_tokens * 4))
+    e.load_random(desc, 2)
+    n, L = args.chunks, 512
+    rng = np.random.default_rng(2)
+    toks = rng.integers(0, desc.vocab, size=n * L, dtype=np.int64).astype(np.int32)
+    offs = (np.arange(n + 1, dtype=np.int64) * L).astype(np.int32)
+    out = np.empty((n, desc.hidden), np.float32)
+    warm = min(n, 2048)
+    for _ in range(max(1, args.warmup)):
+        e.embed_flat(toks[:warm * L], offs[:warm + 1], out[:warm])
+    torch.cuda.synchronize()
+    s0 = e.stats()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e.embed_flat(toks, offs, out)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / args.steps
+    s1 = e.stats()
+    dev = (s1["gpu_ms_prefill"] - s0["gpu_ms_prefill"]) / args.steps / 1e3
+    e.set_profile(True)
+    p0 = e.stats()
+    sub = min(n, 8192)
+    e.embed_flat(toks[:sub * L], offs[:sub + 1], out[:sub])
+    p1 = e.stats()
+    e.set_profile(False)
+    fam = {}
+    for i, name in ((0, "gemm"), (1, "attention"), (3, "row_kernels")):
+        ms = p1["prof_ms"][i] - p0["prof_ms"][i]
+        w = p1["prof_work"][i] - p0["prof_work"][i]
+        fam[name] = {"ms": ms, "launches": p1["prof_launches"][i] - p0["prof_launches"][i],
+                     "tflops" if i < 2 else "gbs": (w / (ms * 1e-3) / (1e12 if i < 2 else 1e9)) if ms else 0.0}
+    flops = n * L * 188.8e6
+    peaks = measured_peaks()
+    line = {"metric": "chunks/sec bge-base-en-shaped batch encode (512-token chunks)", "value": n / dev, "unit": "chunks/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"bge-base-en shape random-init, {n} chunks x 512 tokens, CLS+L2, fp32 out"},
+            "e2e": {"value": n / wall, "unit": "chunks/s", "h2d_bytes_per_step": int(toks.nbytes * 2), "d2h_bytes_per_step": int(out.nbytes)},
+            "model_tflops": flops / dev / 1e12, "frac_of_measured_sustained": flops / dev / 1e12 / peaks["bf16_tflops_sustained"],
+            "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]), "tokens_per_s": n * L / dev,
+            "kernels_profiled_subset": fam, "finite": bool(np.isfinite(out).all()), "unit_norm_err": float(np.abs(np.linalg.norm(out, axis=1) - 1).max())}
+    print(json.dumps(line), flush=True)
+    e.close()
+
+
 def cpu_sample(layers=4, prompt=512, decode=8, threads=None):
     """Oracle port on the host cores: L8B shape truncated to `layers` layers, 1 session; linear extrapolation to 32."""
     from helix_b200 import configs
@@ -184,6 +236,8 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=0, help="debug: truncate the model (INVALID as a bench number)")
+    ap.add_argument("--workload", default="llama8b", choices=["llama8b", "bge"])
+    ap.add_argument("--chunks", type=int, default=100000)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -191,6 +245,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.workload == "bge":
+        if rank == 0:
+            bench_bge(args)
         return
 
     import torch

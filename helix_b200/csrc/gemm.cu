@@ -4,9 +4,16 @@
 //   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma cta_group::1, M=128 x N=BLOCK_N x K=16, fp32 accum in TMEM,
 //                                   double-buffered accumulators so tile i+1's MMAs overlap tile i's epilogue)
-//   warps 2..5    : epilogue       (tcgen05.ld -> fused bias / GELU / residual / SwiGLU -> swizzled smem -> TMA store)
+//   warps 2..9    : epilogue       (tcgen05.ld -> fused bias / GELU / residual / SwiGLU -> swizzled smem -> TMA store);
+//                                   two groups of four warps (one warp per TMEM lane quadrant) take alternate 64-column
+//                                   chunks with their own staging buffer, so two warps per SM sub-partition hide each
+//                                   other's TMEM/global latencies and short-K tiles (BERT) are not epilogue-bound
 // M, N, K tails are handled by TMA (zero fill on load, clipping on store).
+#include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -19,9 +26,9 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 192;
-constexpr int kEpiThreads = 128;
-constexpr int kEpiBarrier = 1;
+constexpr int kNumThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups of four)
+constexpr int kEpiThreads = 128;   // per epilogue group
+constexpr int kEpiBarrier = 1;     // named barrier id of group 0 (group 1 uses +1)
 constexpr int kStagingBytes = BLOCK_M * 128;  // one 128-row x 128-byte chunk
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -37,24 +44,39 @@ struct Cfg {
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
-__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mi, int& ni) {
-  constexpr int GM = 16;  // m-tiles swept together so concurrently-resident CTAs share W tiles in L2
-  const int per_group = GM * num_n;
+// Tile order: a group of `grp` tiles along one dimension stays L2-resident (<= ~64 MB of that operand) while the other
+// operand streams past it once per group; the host picks the dimension that minimises total DRAM traffic.
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int grp, int group_n, int& mi, int& ni) {
+  const int num_a = group_n ? num_n : num_m;  // grouped dimension
+  const int num_b = group_n ? num_m : num_n;  // swept dimension
+  const int per_group = grp * num_b;
   const int g = t / per_group, r = t % per_group;
-  const int m_first = g * GM;
-  const int gm = min(GM, num_m - m_first);
-  mi = m_first + r % gm;
-  ni = r / gm;
+  const int first = g * grp;
+  const int ga = min(grp, num_a - first);
+  const int a = first + r % ga, b = r / ga;
+  mi = group_n ? b : a;
+  ni = group_n ? a : b;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU; erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16 resolution): one ex2 + one rcp
+// instead of libdevice erff's branchy polynomial, which made the FFN1 epilogue the bottleneck of the encoder.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
-               const bf16* __restrict__ bias, int M, int N, int K) {
+               const bf16* __restrict__ bias, int M, int N, int K, int tile_grp, int tile_group_n) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   constexpr bool kF32 = (EPI == EPI_F32);
@@ -77,8 +99,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
-  uint64_t* resid_bar = bars + 2 * STAGES + 4;  // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+  uint64_t* resid_bar = bars + 2 * STAGES + 4;  // [2] one per epilogue group
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,9 +121,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
-    mbar_init(resid_bar, 1);
+    mbar_init(&resid_bar[0], 1);
+    mbar_init(&resid_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -120,7 +143,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int mi, ni;
-        tile_coords(t, num_m, num_n, mi, ni);
+        tile_coords(t, num_m, num_n, tile_grp, tile_group_n, mi, ni);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
@@ -161,17 +184,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;               // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;        // row within the 128-row tile == TMEM lane
-    const int epi_tid = threadIdx.x - 64;
-    const bool leader = (epi_tid == 0);
+    const int grp = (warp - 2) >> 2;      // epilogue group: chunks c == grp (mod 2), staging buffer `grp`
+    const bool leader = ((threadIdx.x - 64) & 127) == 0;
+    uint8_t* const buf = staging + grp * kStagingBytes;
+    uint8_t* const my_row = buf + row * 128;
+    uint64_t* const my_resid_bar = &resid_bar[grp];
     uint32_t resid_phase = 0;
     int it = 0;
-    int chunk_ctr = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       int mi, ni;
-      tile_coords(t, num_m, num_n, mi, ni);
+      tile_coords(t, num_m, num_n, tile_grp, tile_group_n, mi, ni);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = mi * BLOCK_M;
@@ -180,18 +205,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const uint32_t t_tile = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
+      int last_c = -1;
+      for (int c = grp; c < NCHUNK; c += 2) last_c = c;
+      if (last_c < 0) {  // this group has no chunk in such a narrow tile: release the accumulator right away
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      }
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c, ++chunk_ctr) {
-        uint8_t* buf = staging + (chunk_ctr & 1) * kStagingBytes;
-        uint8_t* my_row = buf + row * 128;
+      for (int c = grp; c < NCHUNK; c += 2) {
         if (leader) {
-          tma_store_wait_read<1>();  // the store that last read `buf` (2 chunks ago) is done with smem
+          tma_store_wait_read<0>();  // this group's previous store is done reading `buf`
           if (kResid) {
-            mbar_arrive_expect_tx(resid_bar, kStagingBytes);
-            tma_load_2d(buf, &map_r, resid_bar, n_out0 + c * CHUNK_COLS, m0, kEvictFirst);
+            mbar_arrive_expect_tx(my_resid_bar, kStagingBytes);
+            tma_load_2d(buf, &map_r, my_resid_bar, n_out0 + c * CHUNK_COLS, m0, kEvictFirst);
           }
         }
-        bar_sync(kEpiBarrier, kEpiThreads);
+        bar_sync(kEpiBarrier + grp, kEpiThreads);
 
         if constexpr (kF32) {
           uint32_t v[32];
@@ -222,10 +252,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if constexpr (kBias) {
               const int nb = n_out0 + col;
+              if (nb + 32 <= N) {  // warp-uniform: four 16-byte read-only loads instead of 32 scalar ones
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int n = nb + j;
-                f[j] += (n < N) ? __bfloat162float(bias[n]) : 0.0f;
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + nb) + j);
+                  const float2 b0 = unpack_bf16x2(bv.x), b1 = unpack_bf16x2(bv.y), b2 = unpack_bf16x2(bv.z),
+                               b3 = unpack_bf16x2(bv.w);
+                  f[8 * j + 0] += b0.x; f[8 * j + 1] += b0.y; f[8 * j + 2] += b1.x; f[8 * j + 3] += b1.y;
+                  f[8 * j + 4] += b2.x; f[8 * j + 5] += b2.y; f[8 * j + 6] += b3.x; f[8 * j + 7] += b3.y;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int n = nb + j;
+                  f[j] += (n < N) ? __bfloat162float(bias[n]) : 0.0f;
+                }
               }
             }
             if constexpr (EPI == EPI_BIAS_GELU) {
@@ -234,7 +275,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if constexpr (kResid) {
               if (h == 0) {
-                mbar_wait(resid_bar, resid_phase);
+                mbar_wait(my_resid_bar, resid_phase);
                 resid_phase ^= 1;
               }
 #pragma unroll
@@ -257,14 +298,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
         }
-        if (c == NCHUNK - 1) {
-          // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
+        if (c == last_c) {
+          // this group's TMEM reads of the accumulator stage are complete -> hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[as]);
         }
         fence_proxy_async_smem();
-        bar_sync(kEpiBarrier, kEpiThreads);
+        bar_sync(kEpiBarrier + grp, kEpiThreads);
         if (leader) {
           tma_store_2d(&map_c, buf, n_out0 + c * CHUNK_COLS, m0);
           tma_store_commit();
@@ -311,7 +352,18 @@ cudaError_t launch_cfg(cudaStream_t stream, const GemmArgs& g, int num_sms) {
   const int num_m = (g.M + BLOCK_M - 1) / BLOCK_M, num_n = (g.N + BN - 1) / BN;
   const int tiles = num_m * num_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, kNumThreads, C::SMEM, stream>>>(ma, mb, mc, mr, g.bias, g.M, g.N, g.K);
+  // rasterisation: keep <= 64 MB of one operand L2-resident, stream the other
+  static const double budget = [] { const char* e = getenv("HB_GEMM_L2MB"); return (e ? atof(e) : 32.0) * 1e6; }();
+  const double a_tile = (double)BLOCK_M * g.K * 2, w_tile = (double)BN * g.K * 2;
+  const int gm = (int)std::max(1.0, std::min((double)num_m, floor(budget / a_tile)));
+  const int gn = (int)std::max(1.0, std::min((double)num_n, floor(budget / w_tile)));
+  const double A = a_tile * num_m, W = w_tile * num_n;
+  const double t_m = A + W * ceil((double)num_m / gm), t_n = W + A * ceil((double)num_n / gn);
+  int group_n = t_n < t_m ? 1 : 0;
+  int grp = group_n ? gn : gm;
+  static const int force_gm = [] { const char* e = getenv("HB_GEMM_GM"); return e ? atoi(e) : 0; }();  // A/B knob
+  if (force_gm > 0) { group_n = 0; grp = std::min(force_gm, num_m); }
+  kern<<<grid, kNumThreads, C::SMEM, stream>>>(ma, mb, mc, mr, g.bias, g.M, g.N, g.K, grp, group_n);
   return cudaGetLastError();
 }
 

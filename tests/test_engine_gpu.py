@@ -248,3 +248,40 @@ def test_runtime_lifecycle_and_openai_http_front():
         assert abs(np.linalg.norm(v) - 1.0) < 1e-3
     finally:
         rt.stop()
+
+
+def test_multi_model_pack_on_one_gpu():
+    """BASELINE configs[3] in miniature: a decoder and an encoder engine co-resident on one device (one CUDA stream each,
+    budgets honoured), driven concurrently from two host threads, produce exactly their solo results."""
+    import threading
+    d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000)
+    b = configs.tiny_bert(layers=2, vocab=1000)
+    sd, sb = weights.llama_state_dict(d, 7, 0.05), weights.bert_state_dict(b, 5, 0.05)
+    prompts = [weights.random_tokens(200 + i, n, d.vocab) for i, n in enumerate([40, 130, 7, 300])]
+    seqs = [weights.random_tokens(300 + i, n, b.vocab) for i, n in enumerate([64, 512, 3, 200, 129])]
+    cfg = dict(max_seqs=4, max_ctx=512, max_batched_tokens=1024)
+    est_l = hb.engine.memory_estimate(d, hb.EngineConfig(**cfg))
+    est_b = hb.engine.memory_estimate(b, hb.EngineConfig(**cfg))
+    with hb.Engine(hb.EngineConfig(memory_budget_bytes=sum(est_l.values()) + (64 << 20), **cfg)) as el, \
+            hb.Engine(hb.EngineConfig(memory_budget_bytes=sum(est_b.values()) + (64 << 20), **cfg)) as eb:
+        el.load_state_dict(d, sd)
+        eb.load_state_dict(b, sb)
+        solo_gen = el.generate(prompts, hb.Sampling(max_tokens=12))[1]
+        solo_emb = eb.embed(seqs)
+        res = {}
+
+        def chat():
+            for _ in range(3):
+                res["gen"] = el.generate(prompts, hb.Sampling(max_tokens=12))[1]
+
+        def embed():
+            for _ in range(6):
+                res["emb"] = eb.embed(seqs)
+        ts = [threading.Thread(target=chat), threading.Thread(target=embed)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert res["gen"] == solo_gen
+        assert np.array_equal(res["emb"], solo_emb)
+        sl, sbb = el.stats(), eb.stats()
+        assert sl["weights_bytes"] + sl["kv_bytes"] + sl["workspace_bytes"] <= sl["budget_bytes"]
+        assert sbb["weights_bytes"] + sbb["workspace_bytes"] <= sbb["budget_bytes"]
