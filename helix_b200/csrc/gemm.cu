@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -32,10 +33,12 @@ constexpr int kEpiBarrier = 1;     // named barrier id of group 0 (group 1 uses 
 constexpr int kStagingBytes = BLOCK_M * 128;  // one 128-row x 128-byte chunk
 constexpr int kSmemBudget = 227 * 1024;
 
-template <int BN>
+// CG = CTAs cooperating on one UMMA (cta_group): with CG == 2 a CTA pair (cluster of 2 = one TPC) computes a 256 x BN
+// tile; each CTA stages its own 128 rows of A and HALF of the W tile, so per-SM smem/L2 operand traffic drops by a third.
+template <int BN, int CG = 1>
 struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BN / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int FIXED = 2 * kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
   static constexpr int STAGES_RAW = (kSmemBudget - FIXED) / STAGE_BYTES;
@@ -72,12 +75,17 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG = 1>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
                const bf16* __restrict__ bias, int M, int N, int K, int tile_grp, int tile_group_n) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
+  constexpr int TILE_M = BLOCK_M * CG;  // rows of one UMMA tile (per CTA: BLOCK_M)
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  const int tile_worker = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;       // CTA pairs walk the tile list together
+  const int tile_workers = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
   constexpr int STAGES = C::STAGES;
   constexpr bool kF32 = (EPI == EPI_F32);
   constexpr bool kSwiGLU = (EPI == EPI_SWIGLU);
@@ -105,7 +113,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_m = (M + TILE_M - 1) / TILE_M;
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
@@ -116,23 +124,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_c);
     if (kResid) tma_prefetch_desc(&map_r);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&full_bar[i], CG);   // leader: own arrive.expect_tx (+ the peer producer's remote arrive)
+      mbar_init(&empty_bar[i], 1);   // tcgen05.commit (multicast to both CTAs when CG == 2)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 8 * CG);  // epilogue warps of BOTH CTAs release the leader's accumulator stage
     }
     mbar_init(&resid_bar[0], 1);
     mbar_init(&resid_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_2sm(tmem_ptr, C::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -141,26 +154,36 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = tile_worker; t < num_tiles; t += tile_workers) {
         int mi, ni;
         tile_coords(t, num_m, num_n, tile_grp, tile_group_n, mi, ni);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-          tma_load_2d(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, mi * BLOCK_M, kEvictNormal);
-          tma_load_2d(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K, ni * BN, kEvictNormal);
+          if constexpr (CG == 2) {
+            // both CTAs' bytes complete on the LEADER's barrier (its MMA thread is the only consumer)
+            if (is_leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+            else mbar_arrive_cluster(&full_bar[s], 0);
+            tma_load_2d_2sm(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K,
+                            mi * TILE_M + (int)cta_rank * BLOCK_M, kEvictNormal);
+            tma_load_2d_2sm(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K,
+                            ni * BN + (int)cta_rank * (BN / 2), kEvictNormal);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+            tma_load_2d(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, mi * BLOCK_M, kEvictNormal);
+            tma_load_2d(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K, ni * BN, kEvictNormal);
+          }
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
       int s = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int t = tile_worker; t < num_tiles; t += tile_workers, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -175,12 +198,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + k * UMMA_K * 2);
             const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + k * UMMA_K * 2);
-            umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2) umma_f16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above retire
+          // frees this smem stage (in both CTAs when paired) once the MMAs above retire
+          if constexpr (CG == 2) umma_commit_2sm_mc(&empty_bar[s], 0x3); else umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CG == 2) umma_commit_2sm_mc(&tmem_full[as], 0x3); else umma_commit(&tmem_full[as]);
       }
     }
   } else {
@@ -194,12 +220,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* const my_resid_bar = &resid_bar[grp];
     uint32_t resid_phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = tile_worker; t < num_tiles; t += tile_workers, ++it) {
       int mi, ni;
       tile_coords(t, num_m, num_n, tile_grp, tile_group_n, mi, ni);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = mi * BLOCK_M;
+      const int m0 = mi * TILE_M + (int)cta_rank * BLOCK_M;
       const int n_out0 = ni * OUT_BN;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
@@ -210,7 +236,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (last_c < 0) {  // this group has no chunk in such a narrow tile: release the accumulator right away
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]); }
       }
 #pragma unroll 1
       for (int c = grp; c < NCHUNK; c += 2) {
@@ -302,7 +328,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // this group's TMEM reads of the accumulator stage are complete -> hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]); }
         }
         fence_proxy_async_smem();
         bar_sync(kEpiBarrier + grp, kEpiThreads);
@@ -316,22 +342,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 cudaError_t launch_cfg(cudaStream_t stream, const GemmArgs& g, int num_sms) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   constexpr bool kF32 = (EPI == EPI_F32);
   constexpr bool kSwiGLU = (EPI == EPI_SWIGLU);
+  constexpr int TILE_M = BLOCK_M * CG;
   CUtensorMap ma, mb, mc, mr;
   const int n_out = kSwiGLU ? g.N / 2 : g.N;
   if (!make_tmap_2d(&ma, g.A, TM_BF16, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, BLOCK_K, BLOCK_M)) return cudaErrorInvalidValue;
-  if (!make_tmap_2d(&mb, g.W, TM_BF16, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldw * 2, BLOCK_K, BN)) return cudaErrorInvalidValue;
+  if (!make_tmap_2d(&mb, g.W, TM_BF16, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldw * 2, BLOCK_K, BN / CG)) return cudaErrorInvalidValue;
   if (kF32) {
     if (!make_tmap_2d(&mc, g.C, TM_F32, (uint64_t)n_out, (uint64_t)g.M, (uint64_t)g.ldc * 4, 32, BLOCK_M)) return cudaErrorInvalidValue;
   } else {
@@ -342,19 +369,19 @@ cudaError_t launch_cfg(cudaStream_t stream, const GemmArgs& g, int num_sms) {
   } else {
     mr = mc;
   }
-  auto kern = gemm_tn_kernel<BN, EPI>;
+  auto kern = gemm_tn_kernel<BN, EPI, CG>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int num_m = (g.M + BLOCK_M - 1) / BLOCK_M, num_n = (g.N + BN - 1) / BN;
+  const int num_m = (g.M + TILE_M - 1) / TILE_M, num_n = (g.N + BN - 1) / BN;
   const int tiles = num_m * num_n;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  // rasterisation: keep <= 64 MB of one operand L2-resident, stream the other
+  const int workers = std::min(tiles, num_sms / CG);
+  // rasterisation: keep <= ~32 MB of one operand L2-resident, stream the other
   static const double budget = [] { const char* e = getenv("HB_GEMM_L2MB"); return (e ? atof(e) : 32.0) * 1e6; }();
-  const double a_tile = (double)BLOCK_M * g.K * 2, w_tile = (double)BN * g.K * 2;
+  const double a_tile = (double)TILE_M * g.K * 2, w_tile = (double)BN * g.K * 2;
   const int gm = (int)std::max(1.0, std::min((double)num_m, floor(budget / a_tile)));
   const int gn = (int)std::max(1.0, std::min((double)num_n, floor(budget / w_tile)));
   const double A = a_tile * num_m, W = w_tile * num_n;
@@ -363,8 +390,24 @@ cudaError_t launch_cfg(cudaStream_t stream, const GemmArgs& g, int num_sms) {
   int grp = group_n ? gn : gm;
   static const int force_gm = [] { const char* e = getenv("HB_GEMM_GM"); return e ? atoi(e) : 0; }();  // A/B knob
   if (force_gm > 0) { group_n = 0; grp = std::min(force_gm, num_m); }
-  kern<<<grid, kNumThreads, C::SMEM, stream>>>(ma, mb, mc, mr, g.bias, g.M, g.N, g.K, grp, group_n);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(workers * CG);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (CG > 1) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mr, g.bias, g.M, g.N, g.K, grp, group_n);
+}
+
+bool use_pair() {  // HB_GEMM_2CTA=0 falls back to single-CTA tiles (A/B measurements)
+  static const bool on = [] { const char* e = getenv("HB_GEMM_2CTA"); return !(e && !strcmp(e, "0")); }();
+  return on;
 }
 
 template <int EPI>
@@ -377,9 +420,16 @@ cudaError_t launch_epi(cudaStream_t stream, const GemmArgs& g, int num_sms) {
     while (bn > 64 && (long)num_m * ((g.N + bn - 1) / bn) < 2L * num_sms) bn >>= 1;
   }
   switch (bn) {
-    case 256: return launch_cfg<256, EPI>(stream, g, num_sms);
-    case 128: return launch_cfg<128, EPI>(stream, g, num_sms);
-    case 64: return launch_cfg<64, EPI>(stream, g, num_sms);
+    case 256:
+      // CTA pairs (256 x 256 tiles) once the problem has at least a wave of them
+      if (use_pair() && (long)((g.M + 255) / 256) * ((g.N + 255) / 256) >= num_sms / 2) return launch_cfg<256, EPI, 2>(stream, g, num_sms);
+      return launch_cfg<256, EPI, 1>(stream, g, num_sms);
+    case 128:
+      if constexpr (EPI != EPI_SWIGLU) return launch_cfg<128, EPI, 1>(stream, g, num_sms);
+      return cudaErrorInvalidValue;
+    case 64:
+      if constexpr (EPI != EPI_SWIGLU) return launch_cfg<64, EPI, 1>(stream, g, num_sms);
+      return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }
@@ -387,16 +437,20 @@ cudaError_t launch_epi(cudaStream_t stream, const GemmArgs& g, int num_sms) {
 }  // namespace
 
 namespace {
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 cudaError_t set_attr() {
-  return cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM);
+  return cudaFuncSetAttribute(gemm_tn_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::SMEM);
 }
 template <int EPI>
 cudaError_t set_attr_epi() {
   cudaError_t e;
-  if ((e = set_attr<256, EPI>()) != cudaSuccess) return e;
-  if ((e = set_attr<128, EPI>()) != cudaSuccess) return e;
-  return set_attr<64, EPI>();
+  if ((e = set_attr<256, EPI, 2>()) != cudaSuccess) return e;
+  if ((e = set_attr<256, EPI, 1>()) != cudaSuccess) return e;
+  if constexpr (EPI != EPI_SWIGLU) {
+    if ((e = set_attr<128, EPI, 1>()) != cudaSuccess) return e;
+    return set_attr<64, EPI, 1>();
+  }
+  return cudaSuccess;
 }
 }  // namespace
 
@@ -408,7 +462,7 @@ cudaError_t gemm_init() {
   if ((e = set_attr_epi<EPI_RESID>()) != cudaSuccess) return e;
   if ((e = set_attr_epi<EPI_BIAS_RESID>()) != cudaSuccess) return e;
   if ((e = set_attr_epi<EPI_F32>()) != cudaSuccess) return e;
-  return set_attr<256, EPI_SWIGLU>();
+  return set_attr_epi<EPI_SWIGLU>();
 }
 
 cudaError_t kernels_init() {
@@ -438,7 +492,7 @@ cudaError_t gemm_bf16_tn(cudaStream_t stream, const GemmArgs& g) {
       if (g.N % 256) return cudaErrorInvalidValue;
       GemmArgs h = g;
       h.block_n = 256;
-      return launch_cfg<256, EPI_SWIGLU>(stream, h, num_sms);
+      return launch_epi<EPI_SWIGLU>(stream, h, num_sms);
     }
     case EPI_F32: return launch_epi<EPI_F32>(stream, g, num_sms);
   }
