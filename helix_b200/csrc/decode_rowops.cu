@@ -150,12 +150,17 @@ swiglu_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf
   pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.y;
-  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int j = (blockIdx.x * 256 + threadIdx.x) * 4;  // 4 consecutive outputs: never straddles a 128-column tile
   if (j >= F) return;
   const int t = j >> 7, r = j & 127;
-  const float g = slab_sum(ws, segs, M, 2 * F, m, t * 256 + r);
-  const float u = slab_sum(ws, segs, M, 2 * F, m, t * 256 + 128 + r);
-  h[(size_t)m * F + j] = __float2bfloat16(g / (1.0f + __expf(-g)) * u);
+  const float4 g = slab_sum4(ws, segs, M, 2 * F, m, t * 256 + r);
+  const float4 u = slab_sum4(ws, segs, M, 2 * F, m, t * 256 + 128 + r);
+  __nv_bfloat162 o01 = __floats2bfloat162_rn(g.x / (1.0f + __expf(-g.x)) * u.x, g.y / (1.0f + __expf(-g.y)) * u.y);
+  __nv_bfloat162 o23 = __floats2bfloat162_rn(g.z / (1.0f + __expf(-g.z)) * u.z, g.w / (1.0f + __expf(-g.w)) * u.w);
+  uint2 ob;
+  ob.x = *reinterpret_cast<uint32_t*>(&o01);
+  ob.y = *reinterpret_cast<uint32_t*>(&o23);
+  *reinterpret_cast<uint2*>(h + (size_t)m * F + j) = ob;
 }
 
 }  // namespace
@@ -175,7 +180,8 @@ cudaError_t dec_resid_rmsnorm(cudaStream_t s, const float* ws, const SkinnyPlan&
   return launch_k(resid_rmsnorm_kernel, dim3(M), dim3(kRT), 0, s, true, ws, p.seg_count, x, w, xn, M, H, eps);
 }
 cudaError_t dec_swiglu(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* h, int M, int F) {
-  return launch_k(swiglu_kernel, dim3((F + 255) / 256, M), dim3(256), 0, s, true, ws, p.seg_count, h, M, F);
+  if (F % 4) return cudaErrorInvalidValue;
+  return launch_k(swiglu_kernel, dim3((F / 4 + 255) / 256, M), dim3(256), 0, s, true, ws, p.seg_count, h, M, F);
 }
 
 }  // namespace hb

@@ -285,3 +285,20 @@ def test_multi_model_pack_on_one_gpu():
         sl, sbb = el.stats(), eb.stats()
         assert sl["weights_bytes"] + sl["kv_bytes"] + sl["workspace_bytes"] <= sl["budget_bytes"]
         assert sbb["weights_bytes"] + sbb["workspace_bytes"] <= sbb["budget_bytes"]
+
+
+def test_safetensors_checkpoint_load_is_bit_identical(tmp_path):
+    from helix_b200 import weights_io
+    d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000)
+    sd = weights.llama_state_dict(d, 0, 0.05)
+    path = tmp_path / "model.safetensors"
+    weights_io.write_safetensors(path, sd)
+    prompt = weights.random_tokens(1, 48, d.vocab)
+    cfg = hb.EngineConfig(max_seqs=4, max_ctx=256, max_batched_tokens=256)
+    with hb.Engine(cfg) as a, hb.Engine(cfg) as b:
+        a.load_state_dict(d, sd)
+        weights_io.load_safetensors(b, d, path)
+        ra, oa = a.generate([prompt], hb.Sampling(max_tokens=6, capture=CAPTURE_STEP_LOGITS))
+        rb, ob = b.generate([prompt], hb.Sampling(max_tokens=6, capture=CAPTURE_STEP_LOGITS))
+        assert oa == ob
+        assert np.array_equal(a.captured_logits(ra[0], CAPTURE_STEP_LOGITS), b.captured_logits(rb[0], CAPTURE_STEP_LOGITS))

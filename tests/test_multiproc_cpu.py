@@ -55,7 +55,8 @@ WORKER = textwrap.dedent("""
     dist.all_gather_object(gathered, routes)
     assert all(x == gathered[0] for x in gathered)   # every rank derives the same routing
     dist.destroy_process_group()
-    print("ok", rank)
+    sys.stdout.write("rank" + str(rank) + "-ok" + chr(10))
+    sys.stdout.flush()
 """)
 
 
@@ -70,4 +71,4 @@ def test_gloo_world_size_2(tmp_path):
     env = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "ok 0" in out.stdout and "ok 1" in out.stdout
+    assert "rank0-ok" in out.stdout and "rank1-ok" in out.stdout, out.stdout
