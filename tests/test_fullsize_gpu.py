@@ -1,0 +1,77 @@
+"""Full-size cases on the GPU (BASELINE.json configs[0] and size-independent properties at configs[1] shapes)."""
+import numpy as np
+import pytest
+
+import helix_b200 as hb
+from helix_b200 import configs
+from helix_b200.engine import CAPTURE_PROMPT_LOGITS, CAPTURE_STEP_LOGITS
+from oracle import weights
+from oracle.llama_ref import LlamaOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config1_llama32_1b_full_model_vs_oracle():
+    """configs[0]: single chat request, 128-token prefill + 32-token decode, Llama-3.2-1B shape (16 layers, head_dim 64,
+    GQA 32/8, tied 128256-row LM head, llama3 rope scaling), seeded random init — CUDA path vs the fp32 CPU oracle.
+    Tolerance: per-token logit max-abs-diff <= 3e-2*max(1,|logits|_inf); token ids exact outside near-ties."""
+    d = configs.llama32_1b()
+    sd = weights.llama_state_dict(d, 0, 0.02)
+    prompt = weights.random_tokens(1, 128, d.vocab)
+    with hb.Engine(hb.EngineConfig(max_seqs=2, max_ctx=256, max_batched_tokens=256, use_cuda_graphs=1)) as e:
+        e.load_state_dict(d, sd)
+        rids, outs = e.generate([prompt], hb.Sampling(max_tokens=32, capture=CAPTURE_STEP_LOGITS))
+        got = e.captured_logits(rids[0], CAPTURE_STEP_LOGITS)
+        assert e.stats()["weights_bytes"] == hb.engine.memory_estimate(d, e.cfg)["weights"]
+    o = LlamaOracle(d, sd)
+    logits = o.forward(prompt)[-1]
+    worst = 0.0
+    for i, t in enumerate(outs[0]):  # teacher-forced on the engine's tokens
+        bound = 3e-2 * max(1.0, float(np.abs(logits).max()))
+        diff = float(np.abs(got[i] - logits).max())
+        worst = max(worst, diff / bound)
+        assert diff <= bound, (i, diff, bound)
+        best = int(np.argmax(logits))
+        assert t == best or logits[best] - logits[t] <= 2 * bound, (i, t, best)
+        logits = o.forward([t])[-1]
+    assert len(outs[0]) == 32 and worst < 1.0
+
+
+def test_llama3_8b_prefill_and_decode_paths_agree_at_full_size():
+    """Size-independent property at the configs[1] shape (Llama-3-8B, 2048-token context): the logits of position n are
+    the same whether the token was processed by the DECODE path (swap-AB stream-K GEMMs + paged split-KV attention
+    over the cache) or by the PREFILL path (256x256 CTA-pair GEMMs + flash attention) — two disjoint kernel sets."""
+    d = configs.llama3_8b()
+    d.layers = 8  # 8 of 32 identical layers keep the test to a few seconds; every kernel shape is the full-size one
+    n = 2047
+    prompt = weights.random_tokens(5, n, d.vocab)
+    with hb.Engine(hb.EngineConfig(max_seqs=4, max_ctx=2304, max_batched_tokens=4096)) as e:
+        e.load_random(d, seed=11)
+        ra, oa = e.generate([prompt], hb.Sampling(max_tokens=3, capture=CAPTURE_STEP_LOGITS))
+        la = e.captured_logits(ra[0], CAPTURE_STEP_LOGITS)          # la[1]: decode path at position n, la[2]: n+1
+        ext = np.concatenate([prompt, np.array(oa[0][:2], np.int32)])
+        rb, ob = e.generate([ext], hb.Sampling(max_tokens=1, capture=CAPTURE_PROMPT_LOGITS))
+        lb = e.captured_logits(rb[0], CAPTURE_PROMPT_LOGITS)        # prefill path, all positions
+        st = e.stats()
+    assert lb.shape == (n + 2, d.vocab)
+    scale = max(1.0, float(np.abs(lb[n - 1:]).max()))
+    assert np.abs(la[0] - lb[n - 1]).max() <= 1e-2 * scale          # same path (prefill) both times: only batching differs
+    assert np.abs(la[1] - lb[n]).max() <= 3e-2 * scale              # decode path vs prefill path
+    assert np.abs(la[2] - lb[n + 1]).max() <= 3e-2 * scale
+    assert np.isfinite(lb).all() and st["kv_pages_free"] == st["kv_pages_total"]
+
+
+def test_bge_base_full_shape_embeddings_are_unit_and_order_invariant():
+    """configs[2] shape: ragged batch of 512-token-capped chunks through the full 12-layer encoder; every vector is unit
+    norm, finite, and independent of what else was in the batch (bit-exact)."""
+    d = configs.bge_base()
+    rng = np.random.default_rng(3)
+    lens = [512, 64, 511, 1, 300, 128, 129, 512, 7, 256] * 6
+    seqs = [rng.integers(0, d.vocab, size=n).astype(np.int32) for n in lens]
+    with hb.Engine(hb.EngineConfig(max_seqs=64, max_ctx=512, max_batched_tokens=8192)) as e:
+        e.load_random(d, seed=2)
+        full = e.embed(seqs)                       # several engine batches
+        rev = e.embed(seqs[::-1])[::-1]
+        solo = e.embed([seqs[2]])
+    assert np.isfinite(full).all() and np.abs(np.linalg.norm(full, axis=1) - 1).max() < 1e-5
+    assert np.array_equal(full, rev) and np.array_equal(solo[0], full[2])
