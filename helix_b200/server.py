@@ -50,6 +50,69 @@ class HFTokenizer:
         return self.encode(s + "<|start_header_id|>assistant<|end_header_id|>\n\n")
 
 
+class EmbedBatcher:
+    """Server-side coalescing of embedding requests (scope row F4).  The reference's RAG caller sends ONE chunk per
+    request with 10 concurrent workers (api/pkg/rag/rag_pgvector.go:70-83) in batches of 50
+    (controller/knowledge/knowledge_indexer.go:586-603); encoding them one by one would leave the GPU idle, so requests
+    that arrive within `window_s` (or until `max_seqs`) are encoded by a single hb_embed call."""
+
+    def __init__(self, engine, window_s=0.002, max_seqs=256):
+        self.engine, self.window_s, self.max_seqs = engine, window_s, max_seqs
+        self.cv = threading.Condition()
+        self.pending = []   # [seqs, event, result slot]
+        self.stop_flag = False
+        self.batches = 0
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def embed(self, seqs):
+        item = {"seqs": seqs, "done": threading.Event(), "out": None, "err": None}
+        with self.cv:
+            self.pending.append(item)
+            self.cv.notify()
+        item["done"].wait()
+        if item["err"] is not None:
+            raise item["err"]
+        return item["out"]
+
+    def _run(self):
+        while True:
+            with self.cv:
+                while not self.pending and not self.stop_flag:
+                    self.cv.wait()
+                if self.stop_flag and not self.pending:
+                    return
+                deadline = time.monotonic() + self.window_s
+                while sum(len(i["seqs"]) for i in self.pending) < self.max_seqs:
+                    left = deadline - time.monotonic()
+                    if left <= 0:
+                        break
+                    self.cv.wait(left)
+                batch, self.pending = self.pending, []
+            flat = [s for i in batch for s in i["seqs"]]
+            try:
+                vecs = self.engine.embed(flat)
+                k = 0
+                for i in batch:
+                    i["out"] = vecs[k:k + len(i["seqs"])]
+                    k += len(i["seqs"])
+            except Exception as e:  # one bad sequence must not poison its neighbours: retry each request alone
+                for i in batch:
+                    try:
+                        i["out"] = self.engine.embed(i["seqs"])
+                    except Exception as e2:
+                        i["err"] = e2
+            self.batches += 1
+            for i in batch:
+                i["done"].set()
+
+    def close(self):
+        with self.cv:
+            self.stop_flag = True
+            self.cv.notify_all()
+        self.thread.join(timeout=5)
+
+
 def chat_chunk(cid, model, created, delta, finish_reason):
     return {"id": cid, "object": "chat.completion.chunk", "created": created, "model": model,
             "choices": [{"index": 0, "delta": delta, "finish_reason": finish_reason}]}
@@ -61,6 +124,7 @@ class OpenAIServer:
         self.tok = tokenizer or ByteTokenizer()
         self.host, self.port = host, port
         self.httpd = None
+        self.batcher = None
 
     # ---- request handlers (pure functions of the parsed body: unit-testable without sockets)
     def models(self):
@@ -78,7 +142,9 @@ class OpenAIServer:
             raise ValueError("input must be a string, a list of strings or token arrays")
         vocab = self.rt.engine.desc.vocab
         seqs = [[t % vocab for t in s][: self.rt.engine.cfg.max_ctx] for s in seqs]
-        vecs = self.rt.engine.embed(seqs)
+        if self.batcher is None:
+            self.batcher = EmbedBatcher(self.rt.engine)
+        vecs = self.batcher.embed(seqs)
         return {"object": "list", "model": body.get("model", self.rt.p.model),
                 "data": [{"object": "embedding", "index": i, "embedding": [float(x) for x in v]} for i, v in enumerate(vecs)],
                 "usage": {"prompt_tokens": sum(map(len, seqs)), "total_tokens": sum(map(len, seqs))}}
@@ -197,6 +263,9 @@ class OpenAIServer:
         return f"http://{self.host}:{self.port}"
 
     def stop(self):
+        if self.batcher:
+            self.batcher.close()
+            self.batcher = None
         if self.httpd:
             self.httpd.shutdown()
             self.httpd.server_close()

@@ -99,3 +99,47 @@ def test_embeddings_accepts_all_reference_input_forms():
         assert r["usage"]["prompt_tokens"] > 0
     assert srv.models()["data"][0]["id"] == "m"
     assert chat_chunk("i", "m", 1, {}, "stop")["choices"][0]["finish_reason"] == "stop"
+
+
+def test_embedding_micro_batcher_coalesces_concurrent_single_chunk_requests():
+    """The RAG caller's pattern (1 chunk per request, 10 workers): requests landing inside the window share one hb_embed."""
+    import threading
+    import time
+    from helix_b200.server import EmbedBatcher
+
+    class CountingEngine(StubEngine):
+        def __init__(self):
+            super().__init__([])
+            self.calls = []
+
+        def embed(self, seqs):
+            self.calls.append(len(seqs))
+            time.sleep(0.01)
+            if any(len(s) == 0 for s in seqs):
+                raise ValueError("empty sequence")
+            return [[float(s[0]), 0.0, 0.0, 1.0] for s in seqs]
+
+    eng = CountingEngine()
+    b = EmbedBatcher(eng, window_s=0.05, max_seqs=64)
+    out = {}
+
+    def worker(i):
+        out[i] = b.embed([[i, i + 1]])
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(10)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(out[i][0][0] == float(i) for i in range(10))       # every caller got ITS vector back
+    assert sum(eng.calls) == 10 and len(eng.calls) <= 3            # coalesced (normally a single call)
+    # a failing request is isolated: its neighbours still succeed
+    res = {}
+
+    def worker2(i, seq):
+        try:
+            res[i] = b.embed([seq])
+        except ValueError as e:
+            res[i] = e
+    ts = [threading.Thread(target=worker2, args=(0, [])), threading.Thread(target=worker2, args=(1, [5]))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert isinstance(res[0], ValueError) and res[1][0][0] == 5.0
+    b.close()
