@@ -617,6 +617,7 @@ int Engine::submit(const int32_t* toks, int n, const hb_sampling* sp, uint64_t* 
   if (!loaded_) return fail(HB_ERR_STATE, "hb_submit before a model is loaded");
   if (model_.d.arch != HB_ARCH_LLAMA) return fail(HB_ERR_INVALID, "hb_submit needs a decoder model");
   if (!toks || n <= 0 || !sp || !id) return fail(HB_ERR_INVALID, "null/empty argument");
+  if (cuda_error_.load()) return fail(HB_ERR_CUDA, "engine is in a sticky CUDA error state");
   if (n >= cfg_.max_ctx) return fail(HB_ERR_INVALID, "prompt does not fit context_length");
   if (n > t_cap_) return fail(HB_ERR_INVALID, "prompt longer than max_batched_tokens");
   for (int i = 0; i < n; ++i)
