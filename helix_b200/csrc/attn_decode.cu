@@ -6,7 +6,8 @@
 //   O^T[d =128 lanes, 16 cols] += V_tile^T (A, read MN-major straight from the [kv][d] page layout) · P^T (B)
 //
 // Split-KV grid (num_splits, Hkv, B): each CTA streams its share of the sequence's pages for ONE kv head with
-// TMA (3-D tensor map over [page*Hkv][64 tok][D], 8 KB boxes, 3-stage ring -> ~190 KB in flight per SM) and
+// TMA (3-D tensor map over [page*Hkv][64 tok][D], 8 KB boxes; K_j and V_j tiles alternate through one 3-slot ring,
+// ~106 KB per CTA, so TWO CTAs share an SM and one CTA's prologue / epilogue hides behind the other's stream) and
 // serves all G query heads from the same bytes: every KV byte is read from HBM exactly once per step.
 //   warp 0 lane 0 : TMA producer      warp 1 lane 0 : MMA issuer
 //   warps 2..5    : softmax — thread <-> kv position (4 fp32 scores each): tile max / sum by warp shuffles +
@@ -38,19 +39,19 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 template <int D>
 struct DCfg {
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = 3;                   // ring slots; K_j and V_j tiles alternate through ONE ring
   static constexpr int KV_BYTES = BKV * D * 2;       // one K (or V) tile
   static constexpr int Q_BYTES = NQ * D * 2;
   static constexpr int P_BYTES = NQ * BKV * 2;
   static constexpr int TAIL = (D == 64) ? BKV * 128 : 0;  // the M=128 PV MMA of a D=64 head reads one tile-chunk past V
-  static constexpr int SMEM = 2 * STAGES * KV_BYTES + TAIL + Q_BYTES + P_BYTES + 1024 + 1024;
+  static constexpr int SMEM = STAGES * KV_BYTES + TAIL + Q_BYTES + P_BYTES + 1024 + 1024;  // ~106 KB at D=128: 2 CTAs/SM
   static constexpr int SUB = D / 64;
 };
 
 // MN-major A/B operand descriptor and instruction descriptor with A MN-major are shared with attn_prefill (ptx.cuh).
 
 template <int D, int G>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                    const bf16* __restrict__ q, int ldq, const int32_t* __restrict__ page_table, int max_pages,
                    const int32_t* __restrict__ ctx_lens, float* __restrict__ ws, int Hkv, int num_splits,
@@ -59,22 +60,19 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;                                   // [STAGES][KV_BYTES]
-  uint8_t* sV = sK + STAGES * C::KV_BYTES;              // [STAGES][KV_BYTES] (+TAIL)
-  uint8_t* sQ = sV + STAGES * C::KV_BYTES + C::TAIL;    // [SUB][16 rows][128 B]
+  uint8_t* ring = smem;                                 // [STAGES][KV_BYTES] (+TAIL): items K_0 V_0 K_1 V_1 ...
+  uint8_t* sQ = ring + STAGES * C::KV_BYTES + C::TAIL;  // [SUB][16 rows][128 B]
   uint8_t* sP = sQ + C::Q_BYTES;                        // [2][16 rows][128 B]
   float* sRed = reinterpret_cast<float*>(sP + C::P_BYTES);  // [2][4 warps][G]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + 2 * 4 * kMaxG);
-  uint64_t* k_full = bars;                  // [STAGES]
-  uint64_t* k_empty = bars + STAGES;        // [STAGES]
-  uint64_t* v_full = bars + 2 * STAGES;     // [STAGES]
-  uint64_t* v_empty = bars + 3 * STAGES;    // [STAGES]
-  uint64_t* s_full = bars + 4 * STAGES;     // [2]
-  uint64_t* s_empty = bars + 4 * STAGES + 2;  // [2]
-  uint64_t* q_ready = bars + 4 * STAGES + 4;
-  uint64_t* p_full = bars + 4 * STAGES + 5;
-  uint64_t* pv_done = bars + 4 * STAGES + 6;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4 * STAGES + 7);
+  uint64_t* r_full = bars;                  // [STAGES]
+  uint64_t* r_empty = bars + STAGES;        // [STAGES]
+  uint64_t* s_full = bars + 2 * STAGES;     // [2]
+  uint64_t* s_empty = bars + 2 * STAGES + 2;  // [2]
+  uint64_t* q_ready = bars + 2 * STAGES + 4;
+  uint64_t* p_full = bars + 2 * STAGES + 5;
+  uint64_t* pv_done = bars + 2 * STAGES + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 7);
 
   pdl_launch_dependents();
   pdl_wait();
@@ -98,10 +96,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&r_full[i], 1);
+      mbar_init(&r_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -126,26 +122,22 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % STAGES;
-        const uint32_t ph = (j / STAGES) & 1;
         const int pg0 = (t_begin + j) * 2;
         // a tile's second page may not exist yet: re-load the first one (finite data, masked by the softmax)
         const int page_a = pt[pg0], page_b = pt[min(pg0 + 1, n_pages - 1)];
-        mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[s], C::KV_BYTES);
 #pragma unroll
-        for (int c = 0; c < C::SUB; ++c) {
-          tma_load_3d(sK + s * C::KV_BYTES + c * (BKV * 128), &map_k, &k_full[s], c * 64, 0, page_a * Hkv + kvh, kEvictFirst);
-          tma_load_3d(sK + s * C::KV_BYTES + c * (BKV * 128) + PAGE * 128, &map_k, &k_full[s], c * 64, 0,
-                      page_b * Hkv + kvh, kEvictFirst);
-        }
-        mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[s], C::KV_BYTES);
+        for (int kv = 0; kv < 2; ++kv) {  // item 2j = K_j, item 2j+1 = V_j
+          const int item = 2 * j + kv;
+          const int s = item % STAGES;
+          mbar_wait(&r_empty[s], ((item / STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&r_full[s], C::KV_BYTES);
+          const CUtensorMap* mp = kv ? &map_v : &map_k;
+          uint8_t* dst = ring + s * C::KV_BYTES;
 #pragma unroll
-        for (int c = 0; c < C::SUB; ++c) {
-          tma_load_3d(sV + s * C::KV_BYTES + c * (BKV * 128), &map_v, &v_full[s], c * 64, 0, page_a * Hkv + kvh, kEvictFirst);
-          tma_load_3d(sV + s * C::KV_BYTES + c * (BKV * 128) + PAGE * 128, &map_v, &v_full[s], c * 64, 0,
-                      page_b * Hkv + kvh, kEvictFirst);
+          for (int c = 0; c < C::SUB; ++c) {
+            tma_load_3d(dst + c * (BKV * 128), mp, &r_full[s], c * 64, 0, page_a * Hkv + kvh, kEvictFirst);
+            tma_load_3d(dst + c * (BKV * 128) + PAGE * 128, mp, &r_full[s], c * 64, 0, page_b * Hkv + kvh, kEvictFirst);
+          }
         }
       }
     }
@@ -155,36 +147,36 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, NQ, 1, 0);   // A = V tile (MN-major: d contiguous), B = P^T
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       auto issue_s = [&](int j) {
-        const int s = j % STAGES;
-        mbar_wait(&k_full[s], (j / STAGES) & 1);
+        const int item = 2 * j, s = item % STAGES;
+        mbar_wait(&r_full[s], (item / STAGES) & 1);
         mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + s * C::KV_BYTES);
+        const uint32_t k_addr = smem_u32(ring + s * C::KV_BYTES);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint64_t adesc = umma_desc_kmajor_sw128(k_addr + (k >> 2) * (BKV * 128) + (k & 3) * 32);
           const uint64_t bdesc = umma_desc_kmajor_sw128(q_addr + (k >> 2) * (NQ * 128) + (k & 3) * 32);
           umma_f16_ss(tmem_S + (j & 1) * NQ, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
         }
-        umma_commit(&k_empty[s]);
+        umma_commit(&r_empty[s]);
         umma_commit(&s_full[j & 1]);
       };
       mbar_wait(q_ready, 0);
       issue_s(0);
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) issue_s(j + 1);
-        const int s = j % STAGES;
+        const int item = 2 * j + 1, s = item % STAGES;
         mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[s], (j / STAGES) & 1);
+        mbar_wait(&r_full[s], (item / STAGES) & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + s * C::KV_BYTES);
+        const uint32_t v_addr = smem_u32(ring + s * C::KV_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t adesc = umma_desc_mnmajor_sw128(v_addr + k * (16 * 128), BKV * 128, 1024);
           const uint64_t bdesc = umma_desc_kmajor_sw128(p_addr + (k >> 2) * (NQ * 128) + (k & 3) * 32);
           umma_f16_ss(tmem_O, adesc, bdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&v_empty[s]);
+        umma_commit(&r_empty[s]);
         umma_commit(pv_done);
       }
     }

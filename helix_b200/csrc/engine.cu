@@ -2,6 +2,7 @@
 
 #include "tma_host.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -405,6 +406,8 @@ int Engine::set_profile(bool on) {
 // ------------------------------------------------------------------ forward passes
 int Engine::decode_splits(int B) const {
   // one CTA per SM (190 KB TMA ring): pick the split count whose CTA total fills whole waves of the 148 SMs
+  static const int forced = [] { const char* e = getenv("HB_DECODE_SPLITS"); return e ? atoi(e) : 0; }();  // A/B knob
+  if (forced > 0) return std::min(16, forced);
   const int ctas = B * model_.d.kv_heads;
   int best = 1;
   double best_eff = 0.0;
