@@ -82,8 +82,12 @@ int Engine::fail_cuda(cudaError_t e, const char* what) {
                                std::string(tmap_last_error()) + "]");
 }
 const char* Engine::last_error() {
+  // copy under the lock into a per-thread buffer: the returned pointer stays valid for the calling thread even if
+  // another thread records a newer error meanwhile
+  thread_local std::string tl;
   std::lock_guard<std::mutex> g(err_mu_);
-  return last_error_.c_str();
+  tl = last_error_;
+  return tl.c_str();
 }
 
 int Engine::init() {

@@ -17,7 +17,6 @@ sys.path.insert(0, ROOT)
 import helix_b200 as hb  # noqa: E402
 from helix_b200 import configs  # noqa: E402
 from helix_b200.engine import memory_estimate  # noqa: E402
-from oracle import scheduler_ref  # noqa: E402  (the packing arithmetic is checker-side here: this is a measurement tool)
 
 GB = 1024 ** 3
 
@@ -60,7 +59,8 @@ def main():
     for name, d, cfg in specs:
         est = memory_estimate(d, cfg)
         need = sum(est.values()) + (256 << 20)
-        assert scheduler_ref.single_gpu_fit({0: total}, {0: allocated}, need) == [0], "scheduler would not place this slot"
+        # the reference's single-GPU fit rule (api/pkg/scheduler/global_allocator.go:349-452): total - allocated >= need
+        assert total - allocated >= need, "scheduler would not place this slot"
         budgets[name] = need
         allocated += need
         cfg.memory_budget_bytes = need
