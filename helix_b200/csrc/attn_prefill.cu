@@ -196,20 +196,26 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const int kv0 = j * BKV;
       const bool need_mask = (kv0 + BKV > len) || (causal && (kv0 + BKV - 1 > qt0));
       const int lim = causal ? min(len - 1, qpos) : len - 1;  // last valid kv position for this row
-      // ---- pass 1: row max straight from TMEM
-      float mx = -INFINITY;
+      // ---- the S row: four back-to-back TMEM loads, ONE wait (a warpgroup has a single warp per SM sub-partition, so
+      //      nothing else hides the load latency), then max / exp2 / pack entirely in registers
+      uint32_t sv[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tS + c * 32, v);
-        tmem_ld_wait();
-        if (need_mask) {
+        uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]);
+        tmem_ld_32x32b_x32(tS + c * 32, dst);
+      }
+      tmem_ld_wait();
+      float mx = -INFINITY;
+      if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (kv0 + c * 32 + i <= lim) ? __uint_as_float(v[i]) : -INFINITY);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 128; ++i) {
+          const float x = (kv0 + i <= lim) ? __uint_as_float(sv[i]) : -INFINITY;
+          sv[i] = __float_as_uint(x);
+          mx = fmaxf(mx, x);
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
       }
       float m_new = (mx == -INFINITY) ? m_used : mx * scale_log2;
       if (j == 0) {
@@ -224,36 +230,30 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           m_used = m_new;
           l *= f;
 #pragma unroll
-          for (int c = 0; c < D / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld_32x32b_x16(tO + c * 16, o);
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tO + c * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st_32x32b_x16(tO + c * 16, o);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_32x32b_x16(tO + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+            tmem_st_32x32b_x16(tO + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
           }
         }
       }
-      // ---- pass 2: p = exp2(s*scale - m), row sum, P (bf16x2) written over the consumed part of the S row
+      // ---- p = exp2(s*scale - m) (masked entries are -inf -> 0), row sum, P (bf16x2) written over the S row
       float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tS + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      for (int c = 0; c < 8; ++c) {
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = fast_exp2(__uint_as_float(v[2 * i]) * scale_log2 - m_used);
-          float p1 = fast_exp2(__uint_as_float(v[2 * i + 1]) * scale_log2 - m_used);
-          if (need_mask) {
-            p0 = (kv0 + c * 32 + 2 * i <= lim) ? p0 : 0.f;
-            p1 = (kv0 + c * 32 + 2 * i + 1 <= lim) ? p1 : 0.f;
-          }
+        for (int i = 0; i < 8; ++i) {
+          const float p0 = fast_exp2(__uint_as_float(sv[c * 16 + 2 * i]) * scale_log2 - m_used);
+          const float p1 = fast_exp2(__uint_as_float(sv[c * 16 + 2 * i + 1]) * scale_log2 - m_used);
           sum += p0 + p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
-        tmem_st_32x32b_x16(tS + c * 16, pk);  // columns [16c,16c+16) were read in chunk <= c: never a live S value
+        tmem_st_32x32b_x8(tS + c * 8, pk);
       }
       l += sum;
       tmem_st_wait();

@@ -143,3 +143,29 @@ def test_embedding_micro_batcher_coalesces_concurrent_single_chunk_requests():
     [t.join() for t in ts]
     assert isinstance(res[0], ValueError) and res[1][0][0] == 5.0
     b.close()
+
+
+def test_hf_tokenizer_wrapper_and_llama3_chat_template(tmp_path):
+    """Row F2: the `tokenizers`-backed wrapper (no real Llama-3 vocabulary exists offline, so a tiny BPE with the same
+    special tokens is trained here): chat() must produce exactly the Llama-3 template, token ids bit-exact vs the library."""
+    from tokenizers import Tokenizer, models, pre_tokenizers, trainers, decoders
+    from helix_b200.server import HFTokenizer
+    specials = ["<|begin_of_text|>", "<|start_header_id|>", "<|end_header_id|>", "<|eot_id|>"]
+    tk = Tokenizer(models.BPE())
+    tk.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    tk.decoder = decoders.ByteLevel()
+    tk.train_from_iterator(["hello world, say the word warm", "system user assistant"] * 20,
+                           trainers.BpeTrainer(vocab_size=300, special_tokens=specials,
+                                               initial_alphabet=pre_tokenizers.ByteLevel.alphabet()))
+    path = str(tmp_path / "tokenizer.json")
+    tk.save(path)
+    w = HFTokenizer(path)
+    msgs = [{"role": "system", "content": "be brief"}, {"role": "user", "content": "Say the word 'warm'."}]
+    ids = w.chat(msgs)
+    want = ("<|begin_of_text|><|start_header_id|>system<|end_header_id|>\n\nbe brief<|eot_id|>"
+            "<|start_header_id|>user<|end_header_id|>\n\nSay the word 'warm'.<|eot_id|>"
+            "<|start_header_id|>assistant<|end_header_id|>\n\n")
+    assert ids == tk.encode(want, add_special_tokens=False).ids          # bit-exact ids vs the library
+    assert ids[0] == tk.token_to_id("<|begin_of_text|>") and w.EOS == tk.token_to_id("<|eot_id|>")
+    assert tk.decode(ids, skip_special_tokens=False) == want
+    assert w.decode(w.encode("hello world")) == "hello world"
