@@ -311,6 +311,7 @@ def main():
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     s1 = e.stats()
+    barrier()
     clocks = sampler.stop() if sampler else None
     dev_ms = (s1["gpu_ms_prefill"] - s0["gpu_ms_prefill"]) + (s1["gpu_ms_decode"] - s0["gpu_ms_decode"])
     times = torch.tensor([dev_ms / 1e3, wall], device="cuda", dtype=torch.float64)

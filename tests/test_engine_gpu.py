@@ -302,3 +302,52 @@ def test_safetensors_checkpoint_load_is_bit_identical(tmp_path):
         rb, ob = b.generate([prompt], hb.Sampling(max_tokens=6, capture=CAPTURE_STEP_LOGITS))
         assert oa == ob
         assert np.array_equal(a.captured_logits(ra[0], CAPTURE_STEP_LOGITS), b.captured_logits(rb[0], CAPTURE_STEP_LOGITS))
+
+
+def test_random_arrivals_cancellations_never_leak_pages_and_stay_deterministic():
+    """Scheduler bookkeeping under churn (bit-exact integer work): requests arrive while others decode, a third are
+    cancelled at random points, the queue outruns max_seqs; afterwards every KV page is back, and every request that
+    ran to completion produced exactly the tokens it produces alone."""
+    d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000)
+    sd = weights.llama_state_dict(d, 9, 0.05)
+    rng = np.random.default_rng(0)
+    n = 40
+    prompts = [weights.random_tokens(400 + i, int(rng.integers(1, 300)), d.vocab) for i in range(n)]
+    max_new = [int(rng.integers(1, 24)) for _ in range(n)]
+    with hb.Engine(hb.EngineConfig(max_seqs=6, max_ctx=384, max_batched_tokens=512, use_cuda_graphs=1)) as e:
+        e.load_state_dict(d, sd)
+        solo = {}
+        for i in (0, 7, 13, 21, 39):
+            solo[i] = e.generate([prompts[i]], hb.Sampling(max_tokens=max_new[i]))[1][0]
+        total_pages = e.stats()["kv_pages_total"]
+        rids, outs, done, cancelled = {}, {}, set(), set()
+        submitted, steps = 0, 0
+        while len(done) < n:
+            while submitted < n and rng.random() < 0.6:   # bursty arrivals
+                rids[submitted] = e.submit(prompts[submitted], hb.Sampling(max_tokens=max_new[submitted]))
+                outs[submitted] = []
+                submitted += 1
+            e.step()
+            steps += 1
+            st = e.stats()
+            assert st["running"] <= 6 and 0 <= st["kv_pages_free"] <= total_pages
+            for i, r in list(rids.items()):
+                if i in done:
+                    continue
+                if i not in solo and i % 3 == 0 and i not in cancelled and rng.random() < 0.3:
+                    e.cancel(r)
+                    cancelled.add(i)
+                t, fin = e.poll(r)
+                outs[i] += t
+                if fin:
+                    done.add(i)
+            assert steps < 5000
+        for _ in range(3):
+            e.step()   # retire anything cancelled on the last pass
+        st = e.stats()
+        assert st["kv_pages_free"] == total_pages and st["running"] == 0 and st["waiting"] == 0
+        for i, want in solo.items():
+            assert outs[i] == want
+        for i in range(n):
+            if i not in cancelled:
+                assert len(outs[i]) == max_new[i]
