@@ -205,18 +205,13 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tmem_ld_32x32b_x32(tS + c * 32, dst);
       }
       tmem_ld_wait();
-      float mx = -INFINITY;
-      if (need_mask) {
+      if (need_mask) {  // diagonal / ragged tiles only: knock the invalid columns out once, the hot loops stay branch-free
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          const float x = (kv0 + i <= lim) ? __uint_as_float(sv[i]) : -INFINITY;
-          sv[i] = __float_as_uint(x);
-          mx = fmaxf(mx, x);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        for (int i = 0; i < 128; ++i) sv[i] = (kv0 + i <= lim) ? sv[i] : 0xff800000u;  // -inf
       }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
       float m_new = (mx == -INFINITY) ? m_used : mx * scale_log2;
       if (j == 0) {
         m_used = m_new;
