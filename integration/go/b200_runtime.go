@@ -31,6 +31,7 @@ type B200RuntimeParams struct {
 	Args                   []string // vLLM-style args from the scheduler (scheduler/runner.go:1187-1259,1344-1397)
 	Desc                   C.hb_model_desc
 	Seed                   uint64
+	Tokenizer              Tokenizer // see b200_front.go
 }
 
 type B200Runtime struct {
