@@ -279,6 +279,7 @@ def main():
         ptr, nbytes = e.weights_arena()
         arena = torch.as_tensor(ArenaView(ptr, nbytes), device=f"cuda:{local_rank}")
         probe = arena[:: max(1, nbytes // 65536)].clone()
+        dist.broadcast(torch.zeros(1 << 18, device=f"cuda:{local_rank}"), src=0)  # NCCL channel setup is not part of the measured copy
         barrier()
         t0 = time.perf_counter()
         broadcast_buffer(dist, arena, src=0)

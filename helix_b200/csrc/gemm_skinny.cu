@@ -28,7 +28,9 @@ constexpr int BLOCK_N = 128;  // weight rows per tile (UMMA M)
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
-constexpr int kSmemBudget = 110 * 1024;  // two CTAs per SM: the NEXT kernel's CTA prefetches its weights while this one drains
+// batch <= 64: ~110 KB so two CTAs share an SM (the NEXT kernel's CTA prefetches its weights while this one drains);
+// larger batches need the whole SM for a deep enough ring (the activation tile alone is 16-32 KB per stage)
+constexpr int smem_budget(int mpad) { return (mpad <= 64 ? 110 : 227) * 1024; }
 
 template <int MPAD>
 struct SCfg {
@@ -36,7 +38,7 @@ struct SCfg {
   static constexpr int X_BYTES = MPAD * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
   static constexpr int FIXED = 1024 + 512;
-  static constexpr int STAGES_RAW = (kSmemBudget - FIXED) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (smem_budget(MPAD) - FIXED) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
   static constexpr int SMEM = STAGES * STAGE_BYTES + FIXED;
   static constexpr int TMEM_COLS = (2 * MPAD <= 64) ? 64 : (2 * MPAD <= 128) ? 128 : (2 * MPAD <= 256) ? 256 : 512;
@@ -53,7 +55,7 @@ __host__ __device__ inline int owner_of(long long u, long long U, int G) {
 }
 
 template <int MPAD>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, (MPAD <= 64 ? 2 : 1))
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                    float* __restrict__ ws, int M, int N, int K) {
   using C = SCfg<MPAD>;
