@@ -33,6 +33,8 @@ std::string validate_desc(const hb_model_desc& d) {
     if (g != 1 && g != 2 && g != 4) return "GQA group (heads/kv_heads) must be 1, 2 or 4";
     if (d.ffn % 128) return "ffn must be a multiple of 128 (SwiGLU tile packing)";
     if (d.rope_theta <= 0.f) return "rope_theta must be positive";
+    if (d.vocab % 4) return "vocab must be a multiple of 4 (16-byte rows of the fp32 logits)";
+    if (d.hidden > 8192) return "hidden > 8192 unsupported (decode residual+RMSNorm register budget)";
   } else {
     if (d.heads * d.head_dim != d.hidden) return "BERT needs heads*head_dim == hidden";
     if (d.hidden > 4096) return "BERT hidden > 4096 unsupported (LayerNorm register budget)";
