@@ -61,17 +61,25 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int grp
   ni = group_n ? a : b;
 }
 
-// exact-erf GELU; erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16 resolution): one ex2 + one rcp
-// instead of libdevice erff's branchy polynomial, which made the FFN1 epilogue the bottleneck of the encoder.
+// erf-GELU without special-function units: erf(z) = z * g(z^2) with a degree-8 polynomial g fitted on |z| <= 3.4
+// (|erf error| <= 2.8e-4, |gelu error| <= 6.5e-4 — below bf16 resolution of the output), clamped to [-1, 1] beyond.
+// 16 FMA-pipe instructions per element instead of libdevice erff (branchy) or rcp+ex2: the FFN1 epilogue of the
+// encoder (K = 768, i.e. only 6144 tensor cycles per tile) must stay shorter than its mainloop.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  const float z = x * 0.70710678118654752f;
+  const float u = fminf(z * z, 3.4f * 3.4f);
+  float g = 2.409683474979829e-08f;
+  g = fmaf(g, u, -1.3351223060453776e-06f);
+  g = fmaf(g, u, 3.208911948604509e-05f);
+  g = fmaf(g, u, -0.00044352986151352525f);
+  g = fmaf(g, u, 0.003962765447795391f);
+  g = fmaf(g, u, -0.024541884660720825f);
+  g = fmaf(g, u, 0.11060382425785065f);
+  g = fmaf(g, u, -0.3752793073654175f);
+  g = fmaf(g, u, 1.1283255815505981f);
+  const float e = fmaxf(fminf(z * g, 1.0f), -1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, e, hx);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 

@@ -166,6 +166,65 @@ layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, con
   }
 }
 
+// Warp-per-row LayerNorm for narrow rows (H <= 1024, e.g. the 768-wide encoder): no shared memory, no block barrier,
+// four rows per 128-thread block; the block-per-row kernel above leaves a quarter of its threads idle at H = 768.
+template <bool kEmbed>
+__global__ void __launch_bounds__(128)
+layernorm_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                      bf16* __restrict__ out, int rows, int H, float eps, const int32_t* __restrict__ tokens,
+                      const int32_t* __restrict__ positions, const bf16* __restrict__ word, const bf16* __restrict__ pos,
+                      const bf16* __restrict__ type0) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int nvec = H / 8;
+  float vals[4][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = lane + j * 32;
+    if (i < nvec) {
+      if (kEmbed) {
+        float a[8], b[8], c[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(word + (size_t)tokens[r] * H) + i), a);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(pos + (size_t)positions[r] * H) + i), b);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(type0) + i), c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) vals[j][k] = a[k] + b[k] + c[k];
+      } else {
+        unpack8(reinterpret_cast<const uint4*>(x + (size_t)r * H)[i], vals[j]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += vals[j][k];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (lane + j * 32 < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = vals[j][k] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float inv = rsqrtf(warp_sum(sq) / (float)H + eps);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = lane + j * 32;
+    if (i < nvec) {
+      float g[8], b[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + i), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + i), b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (vals[j][k] - mean) * inv * g[k] + b[k];
+      reinterpret_cast<uint4*>(out + (size_t)r * H)[i] = pack8(o);
+    }
+  }
+}
+
 // One block per token. Pairs (i, i+D/2) of each q/k head are rotated; k,v rows go to the paged cache.
 __global__ void __launch_bounds__(256)
 rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positions,
@@ -329,7 +388,11 @@ cudaError_t layernorm(cudaStream_t s, const bf16* x, const bf16* gamma, const bf
                       float eps) {
   if (rows <= 0) return cudaSuccess;
   if (H % 8 || H > kMaxVec * kRowThreads * 8) return cudaErrorInvalidValue;
-  layernorm_kernel<false><<<rows, kRowThreads, 0, s>>>(x, gamma, beta, out, H, eps, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (H <= 1024)
+    layernorm_warp_kernel<false><<<(rows + 3) / 4, 128, 0, s>>>(x, gamma, beta, out, rows, H, eps, nullptr, nullptr, nullptr,
+                                                                nullptr, nullptr);
+  else
+    layernorm_kernel<false><<<rows, kRowThreads, 0, s>>>(x, gamma, beta, out, H, eps, nullptr, nullptr, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 cudaError_t bert_embed_ln(cudaStream_t s, const int32_t* tokens, const int32_t* positions, const bf16* word,
@@ -337,7 +400,10 @@ cudaError_t bert_embed_ln(cudaStream_t s, const int32_t* tokens, const int32_t* 
                           float eps) {
   if (T <= 0) return cudaSuccess;
   if (H % 8 || H > kMaxVec * kRowThreads * 8) return cudaErrorInvalidValue;
-  layernorm_kernel<true><<<T, kRowThreads, 0, s>>>(nullptr, gamma, beta, x, H, eps, tokens, positions, word, pos, type0);
+  if (H <= 1024)
+    layernorm_warp_kernel<true><<<(T + 3) / 4, 128, 0, s>>>(nullptr, gamma, beta, x, T, H, eps, tokens, positions, word, pos, type0);
+  else
+    layernorm_kernel<true><<<T, kRowThreads, 0, s>>>(nullptr, gamma, beta, x, H, eps, tokens, positions, word, pos, type0);
   return cudaGetLastError();
 }
 cudaError_t rope_kv_write(cudaStream_t s, bf16* qkv, const int32_t* positions, const int32_t* slot_mapping,
