@@ -4,6 +4,8 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tma_host.h"
@@ -31,19 +33,21 @@ struct ACfg {
   static constexpr int SUB = D / 64;  // 64-column swizzle sub-tiles per row
 };
 
-// One CTA = one (sequence, q-head, 256-row q pair).  TMEM: S0 | S1 (128 fp32 columns each; P_t, packed bf16x2,
-// aliases the first 64 columns of S_t) | O0 | O1.
-//   warp 0 lane 0 : TMA producer (Q0,Q1 once; K_j / V_j through 2-stage rings)
+// PERSISTENT kernel: one CTA per SM walks a static list of (256-row q pair, sequence, q-head) items, heaviest
+// (latest, most kv tiles under the causal mask) first, so the TMEM allocation, barrier setup and — above all — the
+// latency of an item's first loads and of its output write-back overlap with the neighbouring items' work.
+// TMEM: S0 | S1 (128 fp32 columns each; P_t, packed bf16x2, aliases the first 64 columns of S_t) | O0 | O1.
+//   warp 0 lane 0 : TMA producer (Q pair of the next item as soon as the last S MMA of the current one retired;
+//                   K_j / V_j through 2-stage rings that keep running across items)
 //   warp 1 lane 0 : MMA issuer, ping-pong order  PV0(j) S0(j+1) PV1(j) S1(j+1):  while one warpgroup runs its
 //                   softmax the tensor pipe works for the other one.  P is consumed straight from TMEM
 //                   (tcgen05.mma A-from-TMEM), V straight from its [kv][d] layout (MN-major B): no smem round trip.
-//   warps 2..5 / 6..9 : softmax warpgroup of q tile 0 / 1, one thread per q row, two passes over the S row in TMEM
-//                   (max, then exp2/sum/pack) so a row never has to live in registers; lazy O rescale.
+//   warps 2..5 / 6..9 : softmax warpgroup of q tile 0 / 1, one thread per q row; lazy O rescale; O/l -> global.
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, bf16* __restrict__ out, int ldo,
-                    const int32_t* __restrict__ cu_seqlens, int group, int causal, float scale_log2,
+                    const int32_t* __restrict__ cu_seqlens, int B, int Hq, int group, int causal, float scale_log2,
                     int max_q_pairs) {
   using C = ACfg<D>;
   extern __shared__ uint8_t smem_raw[];
@@ -53,35 +57,50 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint8_t* sV = sK + 2 * C::KV_BYTES;        // [2][KV_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * C::KV_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;    // [2] per q tile
-  uint64_t* p_full = bars + 11;   // [2]
-  uint64_t* pv_done = bars + 13;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;    // [2]
+  uint64_t* k_empty = bars + 4;   // [2]
+  uint64_t* v_full = bars + 6;    // [2]
+  uint64_t* v_empty = bars + 8;   // [2]
+  uint64_t* s_full = bars + 10;   // [2] per q tile
+  uint64_t* p_full = bars + 12;   // [2]
+  uint64_t* pv_done = bars + 14;  // [2]
+  uint64_t* o_free = bars + 16;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qp = max_q_pairs - 1 - blockIdx.x;  // heaviest (latest) q rows first
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int seq0 = cu_seqlens[b];
-  const int len = cu_seqlens[b + 1] - seq0;  // q_len == kv_len (whole-prompt prefill / encoder)
-  const int q0 = qp * QPAIR;
-  if (q0 >= len) return;
-  const int kvh = h / group;
-  const int kv_tiles = (len + BKV - 1) / BKV;
-  const bool act1 = q0 + BQ < len;
-  const int n0 = causal ? min(kv_tiles, q0 / BKV + 1) : kv_tiles;
-  const int n1 = act1 ? (causal ? min(kv_tiles, q0 / BKV + 2) : kv_tiles) : 0;
-  const int n = max(n0, n1);
+  const int num_items = max_q_pairs * B * Hq;
+
+  struct Item {
+    int b, h, kvh, q0, seq0, len, n0, n1, n;
+    bool valid, act1;
+  };
+  auto get_item = [&](int idx) {
+    Item it;
+    const int per_qp = B * Hq;
+    const int qp = max_q_pairs - 1 - idx / per_qp;  // heaviest (latest) q rows first, one "round" per q pair index
+    const int rem = idx % per_qp;
+    it.b = rem / Hq;
+    it.h = rem % Hq;
+    it.kvh = it.h / group;
+    it.seq0 = cu_seqlens[it.b];
+    it.len = cu_seqlens[it.b + 1] - it.seq0;  // q_len == kv_len (whole-prompt prefill / encoder)
+    it.q0 = qp * QPAIR;
+    it.valid = it.q0 < it.len;
+    const int kv_tiles = (it.len + BKV - 1) / BKV;
+    it.act1 = it.q0 + BQ < it.len;
+    it.n0 = causal ? min(kv_tiles, it.q0 / BKV + 1) : kv_tiles;
+    it.n1 = it.act1 ? (causal ? min(kv_tiles, it.q0 / BKV + 2) : kv_tiles) : 0;
+    it.n = max(it.n0, it.n1);
+    return it;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
@@ -90,6 +109,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&o_free[i], 4);
     }
     fence_barrier_init();
   }
@@ -104,35 +124,43 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, (act1 ? 2 : 1) * C::Q_BYTES);
-      for (int t = 0; t < (act1 ? 2 : 1); ++t)
+      int kt = 0, qi = 0;  // running kv-tile / item counters: barrier phases continue across items
+      for (int idx = blockIdx.x; idx < num_items; idx += gridDim.x) {
+        const Item it = get_item(idx);
+        if (!it.valid) continue;
+        mbar_wait(q_empty, (qi & 1) ^ 1);  // every S MMA of the previous item has retired: the Q pair buffer is free
+        mbar_arrive_expect_tx(q_full, (it.act1 ? 2 : 1) * C::Q_BYTES);
+        for (int t = 0; t < (it.act1 ? 2 : 1); ++t)
 #pragma unroll
-        for (int c = 0; c < C::SUB; ++c)
-          tma_load_2d(sQ + t * C::Q_BYTES + c * (BQ * 128), &map_q, q_full, h * D + c * 64, seq0 + q0 + t * BQ, kEvictFirst);
-      for (int j = 0; j < n; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[s], C::KV_BYTES);
+          for (int c = 0; c < C::SUB; ++c)
+            tma_load_2d(sQ + t * C::Q_BYTES + c * (BQ * 128), &map_q, q_full, it.h * D + c * 64, it.seq0 + it.q0 + t * BQ,
+                        kEvictFirst);
+        ++qi;
+        for (int j = 0; j < it.n; ++j, ++kt) {
+          const int s = kt & 1;
+          const uint32_t ph = (kt >> 1) & 1;
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[s], C::KV_BYTES);
 #pragma unroll
-        for (int c = 0; c < C::SUB; ++c)
-          tma_load_2d(sK + s * C::KV_BYTES + c * (BKV * 128), &map_k, &k_full[s], kvh * D + c * 64, seq0 + j * BKV,
-                      kEvictLast);
-        mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[s], C::KV_BYTES);
+          for (int c = 0; c < C::SUB; ++c)
+            tma_load_2d(sK + s * C::KV_BYTES + c * (BKV * 128), &map_k, &k_full[s], it.kvh * D + c * 64,
+                        it.seq0 + j * BKV, kEvictLast);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[s], C::KV_BYTES);
 #pragma unroll
-        for (int c = 0; c < C::SUB; ++c)
-          tma_load_2d(sV + s * C::KV_BYTES + c * (BKV * 128), &map_v, &v_full[s], kvh * D + c * 64, seq0 + j * BKV,
-                      kEvictLast);
+          for (int c = 0; c < C::SUB; ++c)
+            tma_load_2d(sV + s * C::KV_BYTES + c * (BKV * 128), &map_v, &v_full[s], it.kvh * D + c * 64,
+                        it.seq0 + j * BKV, kEvictLast);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // A = P from TMEM, B = V is MN-major
-      auto issue_s = [&](int t, int j) {  // S_t = Q_t · K_j^T
+      auto issue_s = [&](int t, int slot) {  // S_t = Q_t · K^T (K tile in ring slot `slot`)
         const uint32_t q_addr = smem_u32(sQ + t * C::Q_BYTES);
-        const uint32_t k_addr = smem_u32(sK + (j & 1) * C::KV_BYTES);
+        const uint32_t k_addr = smem_u32(sK + slot * C::KV_BYTES);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
           const uint32_t off = (k >> 2) * (128 * 128) + (k & 3) * 32;
@@ -141,127 +169,152 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         umma_commit(&s_full[t]);
       };
-      auto issue_pv = [&](int t, int j) {  // O_t += P_t · V_j
-        const uint32_t v_addr = smem_u32(sV + (j & 1) * C::KV_BYTES);
+      auto issue_pv = [&](int t, int slot, bool first) {  // O_t (+)= P_t · V
+        const uint32_t v_addr = smem_u32(sV + slot * C::KV_BYTES);
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t bdesc = umma_desc_mnmajor_sw128(v_addr + k * (16 * 128), BKV * 128, 1024);
-          umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * BKV + k * 8, bdesc, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * BKV + k * 8, bdesc, idesc_pv, (!first || k != 0) ? 1u : 0u);
         }
         umma_commit(&pv_done[t]);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      if (n0 > 0) issue_s(0, 0);
-      if (n1 > 0) issue_s(1, 0);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n; ++j) {
-        const int s = j & 1;
-        mbar_wait(&v_full[s], (j >> 1) & 1);
-        if (j < n0) {
-          mbar_wait(&p_full[0], j & 1);
-          tc_fence_after();
-          issue_pv(0, j);
+      int kt = 0, qi = 0;
+      int jt[2] = {0, 0};  // kv tiles processed so far per q tile (phases of s_full / p_full / pv_done)
+      int oi[2] = {0, 0};  // items processed so far per q tile (phase of o_free)
+      for (int idx = blockIdx.x; idx < num_items; idx += gridDim.x) {
+        const Item it = get_item(idx);
+        if (!it.valid) continue;
+        const int n0 = it.n0, n1 = it.n1, n = it.n;
+        mbar_wait(q_full, qi & 1);
+        mbar_wait(&k_full[kt & 1], (kt >> 1) & 1);
+        tc_fence_after();
+        if (n0 > 0) issue_s(0, kt & 1);  // S_t is free: the previous item's last PV_t was issued before (in-order retire)
+        if (n1 > 0) issue_s(1, kt & 1);
+        umma_commit(&k_empty[kt & 1]);
+        if (n == 1) umma_commit(q_empty);
+        for (int j = 0; j < n; ++j) {
+          const int s = (kt + j) & 1;
+          mbar_wait(&v_full[s], ((kt + j) >> 1) & 1);
+          if (j < n0) {
+            if (j == 0) mbar_wait(&o_free[0], (oi[0] & 1) ^ 1);  // the previous item's O_0 has been read out
+            mbar_wait(&p_full[0], (jt[0] + j) & 1);
+            tc_fence_after();
+            issue_pv(0, s, j == 0);
+          }
+          if (j + 1 < n) {
+            mbar_wait(&k_full[s ^ 1], ((kt + j + 1) >> 1) & 1);
+            tc_fence_after();
+          }
+          if (j + 1 < n0) issue_s(0, s ^ 1);  // overwrites S0/P0 strictly after PV0(j): same-thread MMAs retire in order
+          if (j < n1) {
+            if (j == 0) mbar_wait(&o_free[1], (oi[1] & 1) ^ 1);
+            mbar_wait(&p_full[1], (jt[1] + j) & 1);
+            tc_fence_after();
+            issue_pv(1, s, j == 0);
+          }
+          umma_commit(&v_empty[s]);
+          if (j + 1 < n1) issue_s(1, s ^ 1);
+          if (j + 1 < n) {
+            umma_commit(&k_empty[s ^ 1]);
+            if (j + 2 == n) umma_commit(q_empty);  // that was the item's last S MMA: Q may be overwritten
+          }
         }
-        if (j + 1 < n) {
-          mbar_wait(&k_full[s ^ 1], ((j + 1) >> 1) & 1);
-          tc_fence_after();
-        }
-        if (j + 1 < n0) issue_s(0, j + 1);  // overwrites S0/P0 strictly after PV0(j): same-thread MMAs retire in order
-        if (j < n1) {
-          mbar_wait(&p_full[1], j & 1);
-          tc_fence_after();
-          issue_pv(1, j);
-        }
-        umma_commit(&v_empty[s]);
-        if (j + 1 < n1) issue_s(1, j + 1);
-        if (j + 1 < n) umma_commit(&k_empty[s ^ 1]);
+        kt += n;
+        jt[0] += n0;
+        jt[1] += n1;
+        oi[0] += n0 > 0;
+        oi[1] += n1 > 0;
+        ++qi;
       }
     }
   } else {
     const int t = (warp - 2) >> 2;  // q tile of this warpgroup
-    const int nt = t == 0 ? n0 : n1;
     const int qd = warp & 3;
     const int r = qd * 32 + lane;  // q row in tile == TMEM lane
-    const int qt0 = q0 + t * BQ;
-    const int qpos = qt0 + r;
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t tS = tmem_base + lane_sel + t * BKV;
     const uint32_t tO = tmem_base + lane_sel + 256 + t * 128;
-    float m_used = 0.f, l = 0.f;
-    for (int j = 0; j < nt; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      const int kv0 = j * BKV;
-      const bool need_mask = (kv0 + BKV > len) || (causal && (kv0 + BKV - 1 > qt0));
-      const int lim = causal ? min(len - 1, qpos) : len - 1;  // last valid kv position for this row
-      // ---- the S row: four back-to-back TMEM loads, ONE wait (a warpgroup has a single warp per SM sub-partition, so
-      //      nothing else hides the load latency), then max / exp2 / pack entirely in registers
-      uint32_t sv[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]);
-        tmem_ld_32x32b_x32(tS + c * 32, dst);
-      }
-      tmem_ld_wait();
-      if (need_mask) {  // diagonal / ragged tiles only: knock the invalid columns out once, the hot loops stay branch-free
-#pragma unroll
-        for (int i = 0; i < 128; ++i) sv[i] = (kv0 + i <= lim) ? sv[i] : 0xff800000u;  // -inf
-      }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
-      float m_new = (mx == -INFINITY) ? m_used : mx * scale_log2;
-      if (j == 0) {
-        m_used = m_new;
-      } else {
-        const bool need = m_new > m_used + kRescaleThreshold;
-        mbar_wait(&pv_done[t], (j - 1) & 1);  // O_t consistent (and P_t consumed) before anything below touches them
+    int jt = 0;  // kv tiles this warpgroup has processed so far (barrier phases)
+    for (int idx = blockIdx.x; idx < num_items; idx += gridDim.x) {
+      const Item it = get_item(idx);
+      if (!it.valid) continue;
+      const int nt = t == 0 ? it.n0 : it.n1;
+      if (nt == 0) continue;
+      const int len = it.len;
+      const int qt0 = it.q0 + t * BQ;
+      const int qpos = qt0 + r;
+      float m_used = 0.f, l = 0.f;
+      for (int j = 0; j < nt; ++j) {
+        mbar_wait(&s_full[t], (jt + j) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
-          m_new = fmaxf(m_new, m_used);
-          const float f = fast_exp2(m_used - m_new);
+        const int kv0 = j * BKV;
+        const bool need_mask = (kv0 + BKV > len) || (causal && (kv0 + BKV - 1 > qt0));
+        const int lim = causal ? min(len - 1, qpos) : len - 1;  // last valid kv position for this row
+        // ---- the S row: four back-to-back TMEM loads, ONE wait (a warpgroup has a single warp per SM sub-partition, so
+        //      nothing else hides the load latency), then max / exp2 / pack entirely in registers
+        uint32_t sv[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]);
+          tmem_ld_32x32b_x32(tS + c * 32, dst);
+        }
+        tmem_ld_wait();
+        if (need_mask) {  // diagonal / ragged tiles only: knock the invalid columns out once, the hot loops stay branch-free
+#pragma unroll
+          for (int i = 0; i < 128; ++i) sv[i] = (kv0 + i <= lim) ? sv[i] : 0xff800000u;  // -inf
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        float m_new = (mx == -INFINITY) ? m_used : mx * scale_log2;
+        if (j == 0) {
           m_used = m_new;
-          l *= f;
+        } else {
+          const bool need = m_new > m_used + kRescaleThreshold;
+          mbar_wait(&pv_done[t], (jt + j - 1) & 1);  // O_t consistent (and P_t consumed) before anything below touches them
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {
+            m_new = fmaxf(m_new, m_used);
+            const float f = fast_exp2(m_used - m_new);
+            m_used = m_new;
+            l *= f;
 #pragma unroll
-          for (int c = 0; c < D / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32b_x32(tO + c * 32, o);
-            tmem_ld_wait();
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(tO + c * 32, o);
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st_32x32b_x16(tO + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
-            tmem_st_32x32b_x16(tO + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+              tmem_st_32x32b_x16(tO + c * 32, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+              tmem_st_32x32b_x16(tO + c * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&o[16]));
+            }
           }
         }
-      }
-      // ---- p = exp2(s*scale - m) (masked entries are -inf -> 0), row sum, P (bf16x2) written over the S row
-      float sum = 0.f;
+        // ---- p = exp2(s*scale - m) (masked entries are -inf -> 0), row sum, P (bf16x2) written over the S row
+        float sum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t pk[8];
+        for (int c = 0; c < 8; ++c) {
+          uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float p0 = fast_exp2(__uint_as_float(sv[c * 16 + 2 * i]) * scale_log2 - m_used);
-          const float p1 = fast_exp2(__uint_as_float(sv[c * 16 + 2 * i + 1]) * scale_log2 - m_used);
-          sum += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 8; ++i) {
+            const float p0 = fast_exp2(__uint_as_float(sv[c * 16 + 2 * i]) * scale_log2 - m_used);
+            const float p1 = fast_exp2(__uint_as_float(sv[c * 16 + 2 * i + 1]) * scale_log2 - m_used);
+            sum += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x32b_x8(tS + c * 8, pk);
         }
-        tmem_st_32x32b_x8(tS + c * 8, pk);
+        l += sum;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
       }
-      l += sum;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
-    }
-    // ---- epilogue: O / l -> global
-    if (nt > 0) {
-      mbar_wait(&pv_done[t], (nt - 1) & 1);
+      // ---- item epilogue: O / l -> global, then hand O_t back to the MMA issuer
+      mbar_wait(&pv_done[t], (jt + nt - 1) & 1);
       tc_fence_after();
       const float inv_l = l > 0.f ? 1.0f / l : 0.f;
-      bf16* orow = out + (size_t)(seq0 + qpos) * ldo + h * D;
+      bf16* orow = out + (size_t)(it.seq0 + qpos) * ldo + it.h * D;
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
         uint32_t o[32];
@@ -279,6 +332,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);
+      jt += nt;
     }
   }
 
@@ -304,11 +361,18 @@ cudaError_t launch(cudaStream_t stream, const AttnPrefillArgs& a) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
   const int max_q_pairs = (a.max_seqlen + QPAIR - 1) / QPAIR;
-  dim3 grid(max_q_pairs, a.Hq, a.B);
+  const long long items = (long long)max_q_pairs * a.B * a.Hq;
+  const int grid = (int)std::min<long long>(items, num_sms);
   const float scale_log2 = a.scale * 1.4426950408889634f;
-  kern<<<grid, kThreads, C::SMEM, stream>>>(mq, mk, mv, a.out, a.ldo, a.cu_seqlens, a.Hq / a.Hkv, a.causal, scale_log2,
-                                            max_q_pairs);
+  kern<<<grid, kThreads, C::SMEM, stream>>>(mq, mk, mv, a.out, a.ldo, a.cu_seqlens, a.B, a.Hq, a.Hq / a.Hkv, a.causal,
+                                            scale_log2, max_q_pairs);
   return cudaGetLastError();
 }
 
