@@ -115,6 +115,30 @@ def serve_once(e, hb, prompts, decode):
     return got
 
 
+def serve_latency(e, hb, prompts, decode):
+    """Untimed extra pass: time to first token and inter-token latency as a client polling the
+    C ABI sees them, all sessions submitted at t=0."""
+    sp = hb.Sampling(max_tokens=decode, temperature=0.0)
+    t0 = time.perf_counter()
+    rids = [e.submit(p, sp) for p in prompts]
+    stamps = {r: [] for r in rids}
+    active = list(rids)
+    while active:
+        e.wait(active[0], 5)
+        now = time.perf_counter()
+        for r in list(active):
+            toks, fin = e.poll(r)
+            stamps[r] += [now] * len(toks)
+            if fin:
+                active.remove(r)
+                e.release(r)
+    ttft = np.array([s[0] - t0 for s in stamps.values() if s]) * 1e3
+    itl = np.concatenate([np.diff(s) for s in stamps.values() if len(s) > 1]) * 1e3
+    q = lambda a, p: float(np.percentile(a, p)) if len(a) else None
+    return {"ttft_ms": {"p50": q(ttft, 50), "max": q(ttft, 100)}, "itl_ms": {"p50": q(itl, 50), "p99": q(itl, 99)},
+            "note": "all sessions submitted at t=0; prefill has priority, so TTFT includes the queued prompts ahead"}
+
+
 def bench_bge(args):
     """BASELINE configs[2] (extra line, not the headline): bge-base-en-shaped encoder, batch-encode `--chunks` x 512-token
     synthetic chunks through hb_embed (host token buffers in, fp32 vectors out)."""
@@ -321,6 +345,7 @@ def main():
     dev_s, wall_s = float(times[0]), float(times[1])
     launches = s1["kernel_launches"] - s0["kernel_launches"]
 
+    latency = serve_latency(e, hb, prompts, args.decode)
     # ---- one profiled step: CUDA-event span around every launch on the engine stream
     e.set_profile(True)
     p0 = e.stats()
@@ -391,7 +416,8 @@ def main():
                 "e2e": {"value": world * tokens_per_step * args.steps / wall_s, "unit": UNIT, "ms_per_step": wall_s * 1e3 / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "hb_submit/hb_wait/hb_poll (C ABI, host buffers, step-loop thread)"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "phases": phases}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "phases": phases,
+                "latency": latency}
         if world == 1 and not args.no_cpu_baseline:
             run, toks, scale, sample = cpu_sample()
             t = run() * scale

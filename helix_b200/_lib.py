@@ -81,6 +81,7 @@ SIGNATURES = {
     "hbk_sample": (I, [P, I, P, P, P, I, I]),
     "hbk_cls_pool_l2": (I, [P, P, P, I, I]),
     "hbk_attn_prefill": (I, [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, I, C.c_float]),
+    "hbk_attn_prefill_paged": (I, [P, I, P, P, P, I, P, P, I, P, I, I, I, I, I, I, I, C.c_float, I]),
     "hbk_attn_naive": (I, [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, I, C.c_float]),
     "hbk_attn_decode": (I, [P, I, P, P, P, I, P, P, I, P, I, I, I, I, I, I, C.c_float, I]),
     "hbk_attn_decode_workspace_floats": (C.c_size_t, [I, I, I, I]),

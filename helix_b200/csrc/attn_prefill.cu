@@ -43,12 +43,19 @@ struct ACfg {
 //                   softmax the tensor pipe works for the other one.  P is consumed straight from TMEM
 //                   (tcgen05.mma A-from-TMEM), V straight from its [kv][d] layout (MN-major B): no smem round trip.
 //   warps 2..5 / 6..9 : softmax warpgroup of q tile 0 / 1, one thread per q row; lazy O rescale; O/l -> global.
-template <int D>
+//
+// PAGED = false: K/V rows come from the same packed [T, ...] activation as Q (whole-prompt prefill, encoder), kv_len == q_len.
+// PAGED = true : the q rows are the LAST q_len positions of a kv_len-long sequence whose K/V (including the chunk's own,
+//                written by the RoPE/KV-write kernel just before) live in the paged pool: chunked prefill of prompts
+//                longer than one step's token budget.  A K/V tile is two 64-position pages, fetched by two TMA boxes
+//                into the two halves of the same swizzled smem tile the contiguous path uses.
+template <int D, bool PAGED>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, bf16* __restrict__ out, int ldo,
                     const int32_t* __restrict__ cu_seqlens, int B, int Hq, int group, int causal, float scale_log2,
-                    int max_q_pairs) {
+                    int max_q_pairs, const int32_t* __restrict__ kv_lens, const int32_t* __restrict__ page_table,
+                    int max_pages, int Hkv) {
   using C = ACfg<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -72,7 +79,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int num_items = max_q_pairs * B * Hq;
 
   struct Item {
-    int b, h, kvh, q0, seq0, len, n0, n1, n;
+    int b, h, kvh, q0, seq0, len, kv_len, q_off, n0, n1, n;
     bool valid, act1;
   };
   auto get_item = [&](int idx) {
@@ -84,13 +91,16 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     it.h = rem % Hq;
     it.kvh = it.h / group;
     it.seq0 = cu_seqlens[it.b];
-    it.len = cu_seqlens[it.b + 1] - it.seq0;  // q_len == kv_len (whole-prompt prefill / encoder)
+    it.len = cu_seqlens[it.b + 1] - it.seq0;  // q rows of this sequence in the step
+    it.kv_len = PAGED ? kv_lens[it.b] : it.len;
+    it.q_off = it.kv_len - it.len;  // position of the first q row (0 unless this is a later chunk of a long prompt)
     it.q0 = qp * QPAIR;
     it.valid = it.q0 < it.len;
-    const int kv_tiles = (it.len + BKV - 1) / BKV;
+    const int kv_tiles = (it.kv_len + BKV - 1) / BKV;
     it.act1 = it.q0 + BQ < it.len;
-    it.n0 = causal ? min(kv_tiles, it.q0 / BKV + 1) : kv_tiles;
-    it.n1 = it.act1 ? (causal ? min(kv_tiles, it.q0 / BKV + 2) : kv_tiles) : 0;
+    // causal: q tile t needs kv tiles up to the one holding its last row's own position
+    it.n0 = causal ? min(kv_tiles, (it.q_off + it.q0 + BQ - 1) / BKV + 1) : kv_tiles;
+    it.n1 = it.act1 ? (causal ? min(kv_tiles, (it.q_off + it.q0 + 2 * BQ - 1) / BKV + 1) : kv_tiles) : 0;
     it.n = max(it.n0, it.n1);
     return it;
   };
@@ -139,18 +149,38 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int j = 0; j < it.n; ++j, ++kt) {
           const int s = kt & 1;
           const uint32_t ph = (kt >> 1) & 1;
+          int blk0 = 0, blk1 = 0;  // PAGED: (page, kv head) blocks of the tile's two pages
+          if constexpr (PAGED) {
+            const int32_t* pt = page_table + (size_t)it.b * max_pages;
+            const int npages = (it.kv_len + 63) >> 6;
+            blk0 = pt[2 * j] * Hkv + it.kvh;
+            // a ragged last tile re-reads its first page for the (fully masked) second half: always finite data
+            blk1 = (2 * j + 1 < npages ? pt[2 * j + 1] : pt[2 * j]) * Hkv + it.kvh;
+          }
           mbar_wait(&k_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&k_full[s], C::KV_BYTES);
 #pragma unroll
-          for (int c = 0; c < C::SUB; ++c)
-            tma_load_2d(sK + s * C::KV_BYTES + c * (BKV * 128), &map_k, &k_full[s], it.kvh * D + c * 64,
-                        it.seq0 + j * BKV, kEvictLast);
+          for (int c = 0; c < C::SUB; ++c) {
+            uint8_t* dst = sK + s * C::KV_BYTES + c * (BKV * 128);
+            if constexpr (PAGED) {
+              tma_load_3d(dst, &map_k, &k_full[s], c * 64, 0, blk0, kEvictLast);
+              tma_load_3d(dst + 64 * 128, &map_k, &k_full[s], c * 64, 0, blk1, kEvictLast);
+            } else {
+              tma_load_2d(dst, &map_k, &k_full[s], it.kvh * D + c * 64, it.seq0 + j * BKV, kEvictLast);
+            }
+          }
           mbar_wait(&v_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&v_full[s], C::KV_BYTES);
 #pragma unroll
-          for (int c = 0; c < C::SUB; ++c)
-            tma_load_2d(sV + s * C::KV_BYTES + c * (BKV * 128), &map_v, &v_full[s], it.kvh * D + c * 64,
-                        it.seq0 + j * BKV, kEvictLast);
+          for (int c = 0; c < C::SUB; ++c) {
+            uint8_t* dst = sV + s * C::KV_BYTES + c * (BKV * 128);
+            if constexpr (PAGED) {
+              tma_load_3d(dst, &map_v, &v_full[s], c * 64, 0, blk0, kEvictLast);
+              tma_load_3d(dst + 64 * 128, &map_v, &v_full[s], c * 64, 0, blk1, kEvictLast);
+            } else {
+              tma_load_2d(dst, &map_v, &v_full[s], it.kvh * D + c * 64, it.seq0 + j * BKV, kEvictLast);
+            }
+          }
         }
       }
     }
@@ -240,9 +270,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       if (!it.valid) continue;
       const int nt = t == 0 ? it.n0 : it.n1;
       if (nt == 0) continue;
-      const int len = it.len;
-      const int qt0 = it.q0 + t * BQ;
+      const int len = it.kv_len;             // kv positions of the sequence
+      const int qt0 = it.q_off + it.q0 + t * BQ;  // absolute position of the tile's first q row
       const int qpos = qt0 + r;
+      const int qrow = it.q0 + t * BQ + r;   // row within the sequence's q rows of this step
       float m_used = 0.f, l = 0.f;
       for (int j = 0; j < nt; ++j) {
         mbar_wait(&s_full[t], (jt + j) & 1);
@@ -314,13 +345,13 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_wait(&pv_done[t], (jt + nt - 1) & 1);
       tc_fence_after();
       const float inv_l = l > 0.f ? 1.0f / l : 0.f;
-      bf16* orow = out + (size_t)(it.seq0 + qpos) * ldo + it.h * D;
+      bf16* orow = out + (size_t)(it.seq0 + qrow) * ldo + it.h * D;
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
         uint32_t o[32];
         tmem_ld_32x32b_x32(tO + c * 32, o);
         tmem_ld_wait();
-        if (qpos < len) {
+        if (qrow < it.len) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 w;
@@ -347,20 +378,21 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
 }
 
-template <int D>
+template <int D, bool PAGED>
 cudaError_t launch(cudaStream_t stream, const AttnPrefillArgs& a) {
   using C = ACfg<D>;
   CUtensorMap mq, mk, mv;
   if (!make_tmap_2d(&mq, a.q, TM_BF16, (uint64_t)a.Hq * D, (uint64_t)a.T, (uint64_t)a.ldq * 2, 64, BQ)) return cudaErrorInvalidValue;
-  if (!make_tmap_2d(&mk, a.k, TM_BF16, (uint64_t)a.Hkv * D, (uint64_t)a.T, (uint64_t)a.ldk * 2, 64, BKV)) return cudaErrorInvalidValue;
-  if (!make_tmap_2d(&mv, a.v, TM_BF16, (uint64_t)a.Hkv * D, (uint64_t)a.T, (uint64_t)a.ldv * 2, 64, BKV)) return cudaErrorInvalidValue;
-  auto kern = attn_prefill_kernel<D>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+  if (PAGED) {
+    // pool plane = [page][kv head][64 positions][D]: one 3-D block per (page, kv head), as in the decode kernel
+    const uint64_t blocks = (uint64_t)a.num_pages * a.Hkv;
+    if (!make_tmap_3d(&mk, a.k_cache, TM_BF16, D, 64, blocks, (uint64_t)D * 2, (uint64_t)64 * D * 2, 64, 64, 1)) return cudaErrorInvalidValue;
+    if (!make_tmap_3d(&mv, a.v_cache, TM_BF16, D, 64, blocks, (uint64_t)D * 2, (uint64_t)64 * D * 2, 64, 64, 1)) return cudaErrorInvalidValue;
+  } else {
+    if (!make_tmap_2d(&mk, a.k, TM_BF16, (uint64_t)a.Hkv * D, (uint64_t)a.T, (uint64_t)a.ldk * 2, 64, BKV)) return cudaErrorInvalidValue;
+    if (!make_tmap_2d(&mv, a.v, TM_BF16, (uint64_t)a.Hkv * D, (uint64_t)a.T, (uint64_t)a.ldv * 2, 64, BKV)) return cudaErrorInvalidValue;
   }
+  auto kern = attn_prefill_kernel<D, PAGED>;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -372,7 +404,7 @@ cudaError_t launch(cudaStream_t stream, const AttnPrefillArgs& a) {
   const int grid = (int)std::min<long long>(items, num_sms);
   const float scale_log2 = a.scale * 1.4426950408889634f;
   kern<<<grid, kThreads, C::SMEM, stream>>>(mq, mk, mv, a.out, a.ldo, a.cu_seqlens, a.B, a.Hq, a.Hq / a.Hkv, a.causal,
-                                            scale_log2, max_q_pairs);
+                                            scale_log2, max_q_pairs, a.kv_lens, a.page_table, a.max_pages, a.Hkv);
   return cudaGetLastError();
 }
 
@@ -407,17 +439,29 @@ __global__ void attn_naive_kernel(const bf16* q, int ldq, const bf16* k, int ldk
 }  // namespace
 
 cudaError_t attn_prefill_init() {
-  cudaError_t e = cudaFuncSetAttribute(attn_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<128>::SMEM);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(attn_prefill_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACfg<64>::SMEM);
+  cudaError_t e;
+#define HB_ATTR(D_, P_)                                                                                              \
+  if ((e = cudaFuncSetAttribute(attn_prefill_kernel<D_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                ACfg<D_>::SMEM)) != cudaSuccess)                                                     \
+    return e;
+  HB_ATTR(128, false) HB_ATTR(128, true) HB_ATTR(64, false) HB_ATTR(64, true)
+#undef HB_ATTR
+  return cudaSuccess;
 }
 
 cudaError_t attn_prefill(cudaStream_t stream, const AttnPrefillArgs& a) {
   if (a.B <= 0 || a.T <= 0) return cudaSuccess;
   if (a.Hq % a.Hkv) return cudaErrorInvalidValue;
   if ((a.ldq % 8) || (a.ldk % 8) || (a.ldv % 8) || (a.ldo % 8)) return cudaErrorInvalidValue;
-  if (a.D == 128) return launch<128>(stream, a);
-  if (a.D == 64) return launch<64>(stream, a);
+  const bool paged = a.k_cache != nullptr;
+  if (paged) {
+    if (!a.v_cache || !a.page_table || !a.kv_lens || a.max_pages <= 0 || a.num_pages <= 0 || a.page_size != 64) return cudaErrorInvalidValue;
+    if (a.D == 128) return launch<128, true>(stream, a);
+    if (a.D == 64) return launch<64, true>(stream, a);
+    return cudaErrorInvalidValue;
+  }
+  if (a.D == 128) return launch<128, false>(stream, a);
+  if (a.D == 64) return launch<64, false>(stream, a);
   return cudaErrorInvalidValue;
 }
 

@@ -159,6 +159,14 @@ int hbk_attn_prefill(const void* q, int ldq, const void* k, int ldk, const void*
                      const int32_t* cu, int B, int T, int max_seqlen, int Hq, int Hkv, int D, int causal, float scale) {
   return kret(hb::attn_prefill(0, mk_prefill(q, ldq, k, ldk, v, ldv, out, ldo, cu, B, T, max_seqlen, Hq, Hkv, D, causal, scale)));
 }
+int hbk_attn_prefill_paged(const void* q, int ldq, const void* k_cache, const void* v_cache, const int32_t* page_table,
+                           int max_pages, const int32_t* kv_lens, void* out, int ldo, const int32_t* cu, int B, int T,
+                           int max_q_len, int Hq, int Hkv, int D, int causal, float scale, int num_pages) {
+  hb::AttnPrefillArgs a = mk_prefill(q, ldq, nullptr, 0, nullptr, 0, out, ldo, cu, B, T, max_q_len, Hq, Hkv, D, causal, scale);
+  a.k_cache = (const hb::bf16*)k_cache; a.v_cache = (const hb::bf16*)v_cache;
+  a.page_table = page_table; a.max_pages = max_pages; a.kv_lens = kv_lens; a.num_pages = num_pages;
+  return kret(hb::attn_prefill(0, a));
+}
 int hbk_attn_naive(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, float* out, int ldo,
                    const int32_t* cu, int B, int T, int max_seqlen, int Hq, int Hkv, int D, int causal, float scale) {
   return kret(hb::attn_naive_check(0, mk_prefill(q, ldq, k, ldk, v, ldv, nullptr, ldo, cu, B, T, max_seqlen, Hq, Hkv, D, causal, scale), out));

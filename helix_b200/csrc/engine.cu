@@ -170,6 +170,7 @@ void Engine::estimate(const hb_model_desc& d, const hb_engine_cfg& c_in, uint64_
   Engine tmp(c_in);
   tmp.model_.d = d;
   tmp.t_cap_ = tmp.cfg_.max_batched_tokens;
+  if (d.arch == HB_ARCH_BERT) tmp.t_cap_ = std::max(tmp.t_cap_, std::min(tmp.cfg_.max_ctx, d.max_pos));
   if (w) *w = arena_bytes_for(d);
   if (ws) *ws = tmp.workspace_bytes();
   if (kv) {
@@ -247,7 +248,7 @@ int Engine::alloc_runtime() {
   const hb_model_desc& d = model_.d;
   t_cap_ = cfg_.max_batched_tokens;
   if (d.arch == HB_ARCH_BERT && cfg_.max_ctx > d.max_pos) cfg_.max_ctx = d.max_pos;
-  if (t_cap_ < cfg_.max_ctx) t_cap_ = cfg_.max_ctx;  // a whole prompt must fit one prefill step
+  if (d.arch == HB_ARCH_BERT && t_cap_ < cfg_.max_ctx) t_cap_ = cfg_.max_ctx;  // an encoder sequence is never split
   b_cap_ = std::max(cfg_.max_seqs, d.arch == HB_ARCH_BERT ? 4096 : cfg_.max_seqs);
   max_pages_per_seq_ = (cfg_.max_ctx + page_ - 1) / page_;
 
@@ -427,7 +428,7 @@ int Engine::decode_splits(int B) const {
   return best;
 }
 
-int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits) {
+int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits, bool paged) {
   if (!prefill && !all_logits && T == B && B <= skinny_max_b_) return forward_llama_decode(B, L);
   const hb_model_desc& d = model_.d;
   const int H = d.hidden, D = d.head_dim, QD = d.heads * D, KD = d.kv_heads * D, QKV = model_.qkv_cols(), F = d.ffn;
@@ -467,6 +468,12 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
       a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D;
       a.causal = 1;
       a.scale = 1.0f / sqrtf((float)D);
+      if (paged) {  // some sequence continues a partly prefilled prompt: K/V (this chunk's were just written) from the pool
+        a.k_cache = kc; a.v_cache = vc;
+        a.page_table = pt; a.max_pages = max_pages_per_seq_;
+        a.kv_lens = ctx;
+        a.num_pages = num_pages_; a.page_size = page_;
+      }
       SPAN(1, attn_flops_, attn_prefill(stream_, a));
     } else {
       AttnDecodeArgs a{};
@@ -626,7 +633,6 @@ int Engine::submit(const int32_t* toks, int n, const hb_sampling* sp, uint64_t* 
   if (!toks || n <= 0 || !sp || !id) return fail(HB_ERR_INVALID, "null/empty argument");
   if (cuda_error_.load()) return fail(HB_ERR_CUDA, "engine is in a sticky CUDA error state");
   if (n >= cfg_.max_ctx) return fail(HB_ERR_INVALID, "prompt does not fit context_length");
-  if (n > t_cap_) return fail(HB_ERR_INVALID, "prompt longer than max_batched_tokens");
   for (int i = 0; i < n; ++i)
     if (toks[i] < 0 || toks[i] >= model_.d.vocab) return fail(HB_ERR_INVALID, "token id out of range");
   auto r = std::make_unique<Request>();
@@ -716,11 +722,12 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   const hb_model_desc& d = model_.d;
   const int B = (int)batch.size();
   int T = 0, max_len = 0;
-  bool want_all = false;
-  for (Request* r : batch) {
-    T += (int)r->prompt.size();
-    max_len = std::max(max_len, (int)r->prompt.size());
+  bool want_all = false, paged = false;
+  for (Request* r : batch) {  // this step covers prompt[prefilled, prefilled + chunk) of every request
+    T += r->chunk;
+    max_len = std::max(max_len, r->chunk);
     want_all |= (r->sp.capture & HB_CAPTURE_PROMPT_LOGITS) != 0;
+    paged |= r->prefilled > 0;
   }
   if (want_all) {
     if (T > 4096) return fail(HB_ERR_INVALID, "HB_CAPTURE_PROMPT_LOGITS limited to 4096 prompt tokens per step");
@@ -737,19 +744,26 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   int32_t* slot = (int32_t*)(h_step_ + L.slots);
   int32_t* cu = (int32_t*)(h_step_ + L.cu);
   int32_t* last = (int32_t*)(h_step_ + L.last);
+  int32_t* ctx = (int32_t*)(h_step_ + L.ctx);
+  int32_t* pt = (int32_t*)(h_step_ + L.pt);
   float* temp = (float*)(h_step_ + L.temp);
   uint64_t* seed = (uint64_t*)(h_step_ + L.seed);
   int t = 0;
   for (int i = 0; i < B; ++i) {
     Request* r = batch[i];
     cu[i] = t;
-    const int n = (int)r->prompt.size();
-    for (int j = 0; j < n; ++j, ++t) {
+    const int end = r->prefilled + r->chunk;
+    for (int j = r->prefilled; j < end; ++j, ++t) {
       tok[t] = r->prompt[j];
       pos[t] = j;
       slot[t] = r->pages[j / page_] * page_ + j % page_;
     }
     last[i] = t - 1;
+    ctx[i] = end;
+    if (paged) {
+      const int np = (end + page_ - 1) / page_;
+      for (int j = 0; j < np; ++j) pt[(size_t)i * max_pages_per_seq_ + j] = r->pages[j];
+    }
     temp[i] = r->sp.temperature;
     seed[i] = r->sp.seed * 0x9E3779B97F4A7C15ull + 0;
   }
@@ -757,11 +771,11 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
   attn_flops_ = 0;
   for (Request* r : batch) {
-    const double n = (double)r->prompt.size();
-    attn_flops_ += 4.0 * n * n * d.head_dim * d.heads * 0.5;  // causal half of QK^T + PV
+    const double n = (double)r->chunk, s = (double)r->prefilled;
+    attn_flops_ += 4.0 * (n * s + n * n * 0.5) * d.head_dim * d.heads;  // QK^T + PV over the causal trapezoid
   }
   CU(cudaEventRecord(fwd_a_, stream_));
-  int rc = forward_llama(T, B, true, max_len, L, want_all);
+  int rc = forward_llama(T, B, true, max_len, L, want_all, paged);
   if (rc != HB_OK) return rc;
   CU(cudaEventRecord(fwd_b_, stream_));
   CU(cudaMemcpyAsync(h_sampled_, sampled_, (size_t)B * 4, cudaMemcpyDeviceToHost, stream_));
@@ -777,12 +791,11 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   for (int i = 0; i < B; ++i) {
     Request* r = batch[i];
     if (r->sp.capture & HB_CAPTURE_PROMPT_LOGITS) {
-      const int n = (int)r->prompt.size();
-      r->prompt_logits.resize((size_t)n * d.vocab);
-      CU(cudaMemcpy(r->prompt_logits.data(), all_logits_ + (size_t)cu[i] * d.vocab, (size_t)n * d.vocab * 4,
-                    cudaMemcpyDeviceToHost));
+      r->prompt_logits.resize(r->prompt.size() * (size_t)d.vocab);
+      CU(cudaMemcpy(r->prompt_logits.data() + (size_t)r->prefilled * d.vocab, all_logits_ + (size_t)cu[i] * d.vocab,
+                    (size_t)r->chunk * d.vocab * 4, cudaMemcpyDeviceToHost));
     }
-    if (r->sp.capture & HB_CAPTURE_STEP_LOGITS) {
+    if ((r->sp.capture & HB_CAPTURE_STEP_LOGITS) && r->prefilled + r->chunk == (int)r->prompt.size()) {
       const size_t o = r->step_logits.size();
       r->step_logits.resize(o + d.vocab);
       CU(cudaMemcpy(r->step_logits.data() + o, logits_ + (size_t)i * d.vocab, (size_t)d.vocab * 4, cudaMemcpyDeviceToHost));
@@ -889,22 +902,35 @@ int Engine::step(int* did_work) {
         ++i;
       }
     }
-    // admission: FIFO, whole prompts, pages for prompt + max_tokens reserved up front (no preemption)
+    if (!waiting_.empty() && waiting_.front()->cancel_flag) {  // a partly prefilled prompt cancelled between its chunks
+      finish_request(waiting_.front(), ReqState::CANCELLED);
+      waiting_.pop_front();
+      cv_out_.notify_all();
+    }
+    // admission: FIFO; pages for prompt + max_tokens reserved up front (no preemption).  Prompts are packed whole into
+    // the step's token budget; only a prompt LONGER than the budget is split, and then runs as budget-sized chunks of
+    // its own (chunks after the first attend to the already cached prefix through the paged pool).
     int T = 0;
     while (!waiting_.empty()) {
       Request* r = waiting_.front();
       const int n = (int)r->prompt.size();
-      const int need = (n + r->sp.max_tokens + page_ - 1) / page_;
-      if ((int)(running_.size() + batch.size()) >= cfg_.max_seqs) break;
-      if ((int)free_pages_.size() < need) break;
-      if (T + n > t_cap_) break;
-      for (int i = 0; i < need; ++i) {
-        r->pages.push_back(free_pages_.back());
-        free_pages_.pop_back();
+      if (r->pages.empty()) {
+        const int need = (n + r->sp.max_tokens + page_ - 1) / page_;
+        if ((int)(running_.size() + batch.size()) >= cfg_.max_seqs) break;
+        if ((int)free_pages_.size() < need) break;
+        if (n <= t_cap_ && T + n > t_cap_) break;
+        if (n > t_cap_ && T > 0) break;
+        for (int i = 0; i < need; ++i) {
+          r->pages.push_back(free_pages_.back());
+          free_pages_.pop_back();
+        }
+        r->state = ReqState::RUNNING;  // owns cache pages from here on: cancellation goes through cancel_flag
       }
-      waiting_.pop_front();
+      r->chunk = std::min(n - r->prefilled, t_cap_ - T);
       batch.push_back(r);
-      T += n;
+      T += r->chunk;
+      if (r->prefilled + r->chunk < n) break;  // stays at the head of the queue until its last chunk
+      waiting_.pop_front();
     }
     if (!batch.empty()) {
       prefill = true;
@@ -919,6 +945,7 @@ int Engine::step(int* did_work) {
     if (rc != HB_OK) {
       for (Request* r : batch) {
         if (!prefill) running_.erase(std::remove(running_.begin(), running_.end(), r), running_.end());
+        waiting_.erase(std::remove(waiting_.begin(), waiting_.end(), r), waiting_.end());  // a partly prefilled prompt
         finish_request(r, ReqState::FAILED);
       }
       cv_out_.notify_all();
@@ -928,8 +955,9 @@ int Engine::step(int* did_work) {
       Request* r = batch[i];
       const int32_t t = h_sampled_[i];
       if (prefill) {
-        r->kv_len = (int)r->prompt.size();
-        r->state = ReqState::RUNNING;
+        r->prefilled += r->chunk;
+        r->kv_len = r->prefilled;
+        if (r->prefilled < (int)r->prompt.size()) continue;  // more chunks to go: nothing sampled yet
         running_.push_back(r);
       } else {
         r->kv_len += 1;

@@ -32,6 +32,8 @@ struct Request {
   bool cancel_flag = false;
   std::vector<int32_t> pages;
   int kv_len = 0;       // tokens whose K/V are in the cache
+  int prefilled = 0;    // prompt tokens already prefilled (chunked prefill of prompts longer than one step's budget)
+  int chunk = 0;        // prompt tokens scheduled in the current prefill step
   size_t polled = 0;    // tokens already handed to the caller
   std::vector<float> step_logits;    // rows of [vocab] (HB_CAPTURE_STEP_LOGITS)
   std::vector<float> prompt_logits;  // [n_prompt][vocab] (HB_CAPTURE_PROMPT_LOGITS)
@@ -78,7 +80,7 @@ class Engine {
   void loop();
   void finish_request(Request* r, ReqState st);
   StepLayout layout(int T, int B) const;
-  int forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits);
+  int forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits, bool paged = false);
   int forward_bert(int T, int B, int max_seqlen, const StepLayout& L, float* d_out);
   int run_prefill(std::vector<Request*>& batch);
   int run_decode(std::vector<Request*>& batch);

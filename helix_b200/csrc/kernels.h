@@ -87,6 +87,13 @@ struct AttnPrefillArgs {
   int Hq, Hkv, D;
   int causal;
   float scale;              // 1/sqrt(D)
+  // chunked prefill (optional; k_cache != nullptr selects it): the q rows are the last rows of kv_lens[b]-long sequences
+  // whose K/V are read from the paged pool instead of k/v
+  const bf16* k_cache = nullptr;   // [num_pages][Hkv][64][D] plane of one layer
+  const bf16* v_cache = nullptr;
+  const int32_t* page_table = nullptr;  // [B, max_pages]
+  const int32_t* kv_lens = nullptr;     // [B] kv length including this step's q rows
+  int max_pages = 0, num_pages = 0, page_size = 64;
 };
 cudaError_t attn_prefill(cudaStream_t stream, const AttnPrefillArgs& a);
 // test-only CUDA-core checker, fp32 output [T, ldo]

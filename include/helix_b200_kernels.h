@@ -36,6 +36,11 @@ int hbk_cls_pool_l2(const void* x, const int32_t* first_row, float* out, int B, 
 int hbk_attn_prefill(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
                      const int32_t* cu_seqlens, int B, int T, int max_seqlen, int Hq, int Hkv, int D, int causal,
                      float scale);
+/* chunked prefill: the cu_seqlens[b+1]-cu_seqlens[b] q rows of sequence b are the LAST positions of a kv_lens[b]-long
+ * sequence whose K/V (this chunk's included) are in the paged pool plane [num_pages][Hkv][64][D] (page size 64). */
+int hbk_attn_prefill_paged(const void* q, int ldq, const void* k_cache, const void* v_cache, const int32_t* page_table,
+                           int max_pages, const int32_t* kv_lens, void* out, int ldo, const int32_t* cu_seqlens, int B,
+                           int T, int max_q_len, int Hq, int Hkv, int D, int causal, float scale, int num_pages);
 int hbk_attn_naive(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, float* out_f32, int ldo,
                    const int32_t* cu_seqlens, int B, int T, int max_seqlen, int Hq, int Hkv, int D, int causal,
                    float scale);

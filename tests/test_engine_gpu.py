@@ -101,6 +101,49 @@ def test_continuous_batching_matches_solo_runs():
     assert st["kv_pages_free"] == st["kv_pages_total"]
 
 
+@pytest.mark.parametrize("head_dim,budget", [(64, 100), (128, 256)])
+def test_chunked_prefill_of_prompts_longer_than_the_step_budget(head_dim, budget):
+    """A prompt longer than max_batched_tokens is prefilled in budget-sized chunks (chunks after the first attend to the
+    cached prefix through the paged pool; budget 100 puts chunk starts off every tile/page boundary).  Every prompt
+    position's logits and the decoded tokens must match the fp32 oracle, and short prompts queued behind the long one
+    must still produce exactly their solo outputs."""
+    d = configs.tiny_llama(layers=2, head_dim=head_dim, vocab=1000)
+    sd = weights.llama_state_dict(d, 11, 0.05)
+    long_prompt = weights.random_tokens(900, 3 * budget + 57, d.vocab)
+    shorts = [weights.random_tokens(901 + i, n, d.vocab) for i, n in enumerate([5, 70, budget])]
+    cap = CAPTURE_PROMPT_LOGITS | CAPTURE_STEP_LOGITS
+    with hb.Engine(hb.EngineConfig(max_seqs=8, max_ctx=1024, max_batched_tokens=budget)) as e:
+        e.load_state_dict(d, sd)
+        solo = [e.generate([pr], hb.Sampling(max_tokens=6))[1][0] for pr in shorts]
+        before = e.stats()["steps_prefill"]
+        rid = e.submit(long_prompt, hb.Sampling(max_tokens=8, capture=cap))
+        rs = [e.submit(pr, hb.Sampling(max_tokens=6)) for pr in shorts]
+        outs = {r: [] for r in [rid] + rs}
+        done = set()
+        steps = 0
+        while len(done) < len(outs):
+            e.step()
+            steps += 1
+            for r in outs:
+                if r not in done:
+                    t, fin = e.poll(r)
+                    outs[r] += t
+                    if fin:
+                        done.add(r)
+            assert steps < 200
+        pl = e.captured_logits(rid, CAPTURE_PROMPT_LOGITS)
+        sl = e.captured_logits(rid, CAPTURE_STEP_LOGITS)
+        st = e.stats()
+    assert st["steps_prefill"] - before >= 4                      # 3 full chunks + the tail (+ the short prompts)
+    oracle = LlamaOracle(d, sd)
+    want = oracle.forward(long_prompt)
+    assert pl.shape == want.shape
+    assert np.abs(pl - want).max() <= tol(want)
+    check_tokens_against(oracle, long_prompt, outs[rid], sl)
+    assert [outs[r] for r in rs] == solo
+    assert st["kv_pages_free"] == st["kv_pages_total"]
+
+
 def test_step_loop_thread_eos_cancel_and_errors():
     d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000)
     sd = weights.llama_state_dict(d, 0, 0.02)

@@ -275,6 +275,49 @@ def test_attn_decode_paged(L, D, Hq, Hkv, splits):
         torch.testing.assert_close(out[b].float(), want, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("D,Hq,Hkv,causal", [(128, 8, 2, 1), (64, 4, 4, 1), (128, 4, 1, 0)])
+def test_attn_prefill_paged_chunks(L, D, Hq, Hkv, causal):
+    """Chunked prefill: the q rows are the last q_len positions of kv_len-long sequences living in the paged pool;
+    chunk starts are deliberately NOT multiples of the 128-position tile or the 64-position page."""
+    page = 64
+    qlen = [1, 130, 300, 256, 513, 77]
+    kvlen = [1, 130, 300 + 1000, 256 + 64, 513 + 37, 77 + 2048]   # first two: whole prompt in one chunk (q_off 0)
+    B = len(qlen)
+    max_pages = (max(kvlen) + page - 1) // page
+    npages = sum((c + page - 1) // page for c in kvlen) + 5
+    kc, vc = rnd(npages, Hkv, page, D, seed=70), rnd(npages, Hkv, page, D, seed=71)
+    perm = torch.randperm(npages).tolist()
+    pt = torch.zeros(B, max_pages, dtype=torch.int32)
+    it = iter(perm)
+    for b, c in enumerate(kvlen):
+        for j in range((c + page - 1) // page):
+            pt[b, j] = next(it)
+    T = sum(qlen)
+    cu = [0]
+    for n in qlen:
+        cu.append(cu[-1] + n)
+    q = rnd(T, Hq * D, seed=72)
+    out = torch.full((T, Hq * D), float("nan"), device="cuda", dtype=BF)
+    cu_t = torch.tensor(cu, device="cuda", dtype=torch.int32)
+    kv_t, pt_d = torch.tensor(kvlen, device="cuda", dtype=torch.int32), pt.cuda()
+    ck(L, L.hbk_attn_prefill_paged(p(q), Hq * D, p(kc), p(vc), p(pt_d), max_pages, p(kv_t), p(out), Hq * D, p(cu_t), B, T,
+                                   max(qlen), Hq, Hkv, D, causal, 1.0 / math.sqrt(D), npages))
+    torch.cuda.synchronize()
+    g = Hq // Hkv
+    for b in range(B):
+        c, n = kvlen[b], qlen[b]
+        pages = pt[b, :(c + page - 1) // page].long()
+        K = kc[pages].permute(1, 0, 2, 3).reshape(Hkv, -1, D)[:, :c].float().repeat_interleave(g, 0)
+        V = vc[pages].permute(1, 0, 2, 3).reshape(Hkv, -1, D)[:, :c].float().repeat_interleave(g, 0)
+        Q = q[cu[b]:cu[b + 1]].float().view(n, Hq, D).permute(1, 0, 2)
+        s = (Q @ K.transpose(1, 2)) / math.sqrt(D)
+        if causal:
+            qpos = torch.arange(c - n, c, device="cuda")[:, None]
+            s = s.masked_fill(torch.arange(c, device="cuda")[None, :] > qpos, float("-inf"))
+        want = (torch.softmax(s, -1) @ V).permute(1, 0, 2).reshape(n, Hq * D)
+        torch.testing.assert_close(out[cu[b]:cu[b + 1]].float(), want, rtol=2e-2, atol=2e-2)
+
+
 @pytest.mark.parametrize("M,N,K", [(32, 6144, 4096), (1, 4096, 4096), (7, 1000, 256), (64, 4096, 14336), (100, 28672, 4096),
                                    (256, 128256, 2048), (200, 512, 64), (33, 128, 4096)])
 def test_gemm_skinny_stream_k(L, M, N, K):
