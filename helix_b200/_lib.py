@@ -27,7 +27,7 @@ class ModelDescC(C.Structure):
 
 class SamplingC(C.Structure):
     _fields_ = [("temperature", C.c_float), ("seed", C.c_uint64), ("max_tokens", C.c_int32), ("eos_token", C.c_int32),
-                ("capture", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("capture", C.c_int32), ("top_k", C.c_int32), ("top_p", C.c_float), ("reserved", C.c_int32 * 1)]
 
 
 class StatsC(C.Structure):
@@ -79,6 +79,7 @@ SIGNATURES = {
     "hbk_layernorm": (I, [P, P, P, P, I, I, C.c_float]),
     "hbk_rope_kv_write": (I, [P, P, P, P, P, P, I, I, I, I, I]),
     "hbk_sample": (I, [P, I, P, P, P, I, I]),
+    "hbk_sample_filtered": (I, [P, I, P, P, P, P, P, I, I]),
     "hbk_cls_pool_l2": (I, [P, P, P, I, I]),
     "hbk_attn_prefill": (I, [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, I, C.c_float]),
     "hbk_attn_prefill_paged": (I, [P, I, P, P, P, I, P, P, I, P, I, I, I, I, I, I, I, C.c_float, I]),

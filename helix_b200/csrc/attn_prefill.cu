@@ -3,6 +3,7 @@
 // See the kernel comment for the warp roles and the two-q-tile ping-pong schedule.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -23,6 +24,48 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Packed fp32x2 arithmetic (FFMA2 / FADD2: two lanes per issue slot on sm_100).
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for two values on the FMA/ALU pipes only (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3
+// minimax polynomial for 2^f (relative error 7.6e-5, far below the bf16 rounding P gets), n added into the exponent
+// field.  The SFU does 16 ex2/clk/SM: at 128x128 scores per kv tile that is exactly as long as the tile's two MMAs, so
+// part of every row's exponentials is computed here instead (the split FlashAttention-4 uses).
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  x2 = f2_pack(fmaxf(x0, -126.f), fmaxf(x1, -126.f));  // masked scores are -inf: clamp so the exponent add cannot wrap
+  const uint64_t magic = f2_pack(12582912.f, 12582912.f);  // 1.5 * 2^23: the sum's low mantissa bits hold round(x)
+  const uint64_t t2 = f2_add(x2, magic);
+  const uint64_t n2 = f2_add(t2, f2_pack(-12582912.f, -12582912.f));
+  const uint64_t f2 = f2_fma(n2, f2_pack(-1.f, -1.f), x2);
+  uint64_t p2 = f2_fma(f2_pack(0.05520550534f, 0.05520550534f), f2, f2_pack(0.24261397123f, 0.24261397123f));
+  p2 = f2_fma(p2, f2, f2_pack(0.69325476885f, 0.69325476885f));
+  p2 = f2_fma(p2, f2, f2_pack(0.99992769957f, 0.99992769957f));
+  float t0, t1, p0, p1;
+  f2_unpack(t2, t0, t1);
+  f2_unpack(p2, p0, p1);
+  const uint32_t r0 = __float_as_uint(p0) + (__float_as_uint(t0) << 23);
+  const uint32_t r1 = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
+  return f2_pack(__uint_as_float(r0), __uint_as_float(r1));
 }
 
 template <int D>
@@ -49,7 +92,7 @@ struct ACfg {
 //                written by the RoPE/KV-write kernel just before) live in the paged pool: chunked prefill of prompts
 //                longer than one step's token budget.  A K/V tile is two 64-position pages, fetched by two TMA boxes
 //                into the two halves of the same swizzled smem tile the contiguous path uses.
-template <int D, bool PAGED>
+template <int D, bool PAGED, int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, bf16* __restrict__ out, int ldo,
@@ -73,7 +116,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint64_t* p_full = bars + 12;   // [2]
   uint64_t* pv_done = bars + 14;  // [2]
   uint64_t* o_free = bars + 16;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* p_half = bars + 18;   // [2] first 64 kv columns of P_t are in TMEM: the PV MMA starts on them
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = max_q_pairs * B * Hq;
@@ -118,6 +162,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
+      mbar_init(&p_half[i], 4);
       mbar_init(&pv_done[i], 1);
       mbar_init(&o_free[i], 4);
     }
@@ -199,10 +244,17 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         umma_commit(&s_full[t]);
       };
-      auto issue_pv = [&](int t, int slot, bool first) {  // O_t (+)= P_t · V
+      // O_t (+)= P_t · V, in two halves of 64 kv positions: the first starts while the softmax warps still produce the second
+      auto issue_pv = [&](int t, int slot, bool first, uint32_t parity) {
         const uint32_t v_addr = smem_u32(sV + slot * C::KV_BYTES);
+        mbar_wait(&p_half[t], parity);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
+          if (k == BKV / 32) {
+            mbar_wait(&p_full[t], parity);
+            tc_fence_after();
+          }
           const uint64_t bdesc = umma_desc_mnmajor_sw128(v_addr + k * (16 * 128), BKV * 128, 1024);
           umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * BKV + k * 8, bdesc, idesc_pv, (!first || k != 0) ? 1u : 0u);
         }
@@ -227,9 +279,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           mbar_wait(&v_full[s], ((kt + j) >> 1) & 1);
           if (j < n0) {
             if (j == 0) mbar_wait(&o_free[0], (oi[0] & 1) ^ 1);  // the previous item's O_0 has been read out
-            mbar_wait(&p_full[0], (jt[0] + j) & 1);
-            tc_fence_after();
-            issue_pv(0, s, j == 0);
+            issue_pv(0, s, j == 0, (jt[0] + j) & 1);
           }
           if (j + 1 < n) {
             mbar_wait(&k_full[s ^ 1], ((kt + j + 1) >> 1) & 1);
@@ -238,9 +288,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           if (j + 1 < n0) issue_s(0, s ^ 1);  // overwrites S0/P0 strictly after PV0(j): same-thread MMAs retire in order
           if (j < n1) {
             if (j == 0) mbar_wait(&o_free[1], (oi[1] & 1) ^ 1);
-            mbar_wait(&p_full[1], (jt[1] + j) & 1);
-            tc_fence_after();
-            issue_pv(1, s, j == 0);
+            issue_pv(1, s, j == 0, (jt[1] + j) & 1);
           }
           umma_commit(&v_empty[s]);
           if (j + 1 < n1) issue_s(1, s ^ 1);
@@ -294,9 +342,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 128; ++i) sv[i] = (kv0 + i <= lim) ? sv[i] : 0xff800000u;  // -inf
         }
-        float mx = -INFINITY;
+        float mx8[8];  // eight independent chains: a single running max is a 64-deep dependent FMNMX chain
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sv[i]);
+#pragma unroll
+        for (int i = 8; i < 128; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sv[i]));
+        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
         float m_new = (mx == -INFINITY) ? m_used : mx * scale_log2;
         if (j == 0) {
           m_used = m_new;
@@ -322,20 +373,42 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           }
         }
         // ---- p = exp2(s*scale - m) (masked entries are -inf -> 0), row sum, P (bf16x2) written over the S row
-        float sum = 0.f;
+        //      POLY of every 8 column pairs take the FMA-pipe exp2, the rest the SFU; scale/subtract and the sum are packed
+        const uint64_t scale2 = f2_pack(scale_log2, scale_log2), negm2 = f2_pack(-m_used, -m_used);
+        uint64_t sum2a = 0, sum2b = 0;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint32_t pk[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float p0 = fast_exp2(__uint_as_float(sv[c * 16 + 2 * i]) * scale_log2 - m_used);
-            const float p1 = fast_exp2(__uint_as_float(sv[c * 16 + 2 * i + 1]) * scale_log2 - m_used);
-            sum += p0 + p1;
+            const uint64_t x2 = f2_fma(f2_pack(__uint_as_float(sv[c * 16 + 2 * i]), __uint_as_float(sv[c * 16 + 2 * i + 1])),
+                                       scale2, negm2);
+            uint64_t p2;
+            if ((i * POLY) % 8 < POLY) {  // POLY of the 8 pairs, evenly interleaved with the SFU ones
+              p2 = exp2_poly2(x2);
+            } else {
+              float x0, x1;
+              f2_unpack(x2, x0, x1);
+              p2 = f2_pack(fast_exp2(x0), fast_exp2(x1));
+            }
+            if (i & 1) sum2b = f2_add(sum2b, p2); else sum2a = f2_add(sum2a, p2);
+            float p0, p1;
+            f2_unpack(p2, p0, p1);
             pk[i] = pack_bf16x2(p0, p1);
           }
           tmem_st_32x32b_x8(tS + c * 8, pk);
+          if (c == 3) {  // P columns 0..63 are stored: let the issuer start the first half of PV
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_half[t]);
+          }
         }
-        l += sum;
+        {
+          float s0, s1;
+          f2_unpack(f2_add(sum2a, sum2b), s0, s1);
+          l += s0 + s1;
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -378,8 +451,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
 }
 
-template <int D, bool PAGED>
-cudaError_t launch(cudaStream_t stream, const AttnPrefillArgs& a) {
+template <int D, bool PAGED, int POLY>
+cudaError_t launch_p(cudaStream_t stream, const AttnPrefillArgs& a) {
   using C = ACfg<D>;
   CUtensorMap mq, mk, mv;
   if (!make_tmap_2d(&mq, a.q, TM_BF16, (uint64_t)a.Hq * D, (uint64_t)a.T, (uint64_t)a.ldq * 2, 64, BQ)) return cudaErrorInvalidValue;
@@ -392,7 +465,7 @@ cudaError_t launch(cudaStream_t stream, const AttnPrefillArgs& a) {
     if (!make_tmap_2d(&mk, a.k, TM_BF16, (uint64_t)a.Hkv * D, (uint64_t)a.T, (uint64_t)a.ldk * 2, 64, BKV)) return cudaErrorInvalidValue;
     if (!make_tmap_2d(&mv, a.v, TM_BF16, (uint64_t)a.Hkv * D, (uint64_t)a.T, (uint64_t)a.ldv * 2, 64, BKV)) return cudaErrorInvalidValue;
   }
-  auto kern = attn_prefill_kernel<D, PAGED>;
+  auto kern = attn_prefill_kernel<D, PAGED, POLY>;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -438,14 +511,36 @@ __global__ void attn_naive_kernel(const bf16* q, int ldq, const bf16* k, int ldk
 
 }  // namespace
 
+// pairs (of every 8) whose exp2 runs on the FMA pipe; HB_ATTN_POLY overrides (tuning / A-B runs)
+int poly_pairs(int D) {
+  static int env = -2;
+  if (env == -2) {
+    const char* s = getenv("HB_ATTN_POLY");
+    env = s ? atoi(s) : -1;
+  }
+  if (env >= 0) return env;
+  (void)D;
+  return 2;  // measured on B200: 2 of 8 is +2-4 %, 4 of 8 already costs more issue slots than the SFU relief is worth
+}
+template <int D, bool PAGED>
+cudaError_t launch(cudaStream_t stream, const AttnPrefillArgs& a) {
+  switch (poly_pairs(D)) {
+    case 0: return launch_p<D, PAGED, 0>(stream, a);
+    case 4: return launch_p<D, PAGED, 4>(stream, a);
+    default: return launch_p<D, PAGED, 2>(stream, a);
+  }
+}
+
 cudaError_t attn_prefill_init() {
   cudaError_t e;
-#define HB_ATTR(D_, P_)                                                                                              \
-  if ((e = cudaFuncSetAttribute(attn_prefill_kernel<D_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+#define HB_ATTR1(D_, P_, Y_)                                                                                         \
+  if ((e = cudaFuncSetAttribute(attn_prefill_kernel<D_, P_, Y_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                 ACfg<D_>::SMEM)) != cudaSuccess)                                                     \
     return e;
+#define HB_ATTR(D_, P_) HB_ATTR1(D_, P_, 0) HB_ATTR1(D_, P_, 2) HB_ATTR1(D_, P_, 4)
   HB_ATTR(128, false) HB_ATTR(128, true) HB_ATTR(64, false) HB_ATTR(64, true)
 #undef HB_ATTR
+#undef HB_ATTR1
   return cudaSuccess;
 }
 

@@ -130,14 +130,22 @@ int hbk_rope_kv_write(void* qkv, const int32_t* positions, const int32_t* slot_m
   return kret(hb::rope_kv_write(0, (hb::bf16*)qkv, positions, slot_mapping, inv_freq, (hb::bf16*)k_cache,
                                 (hb::bf16*)v_cache, T, Hq, Hkv, D, page_size));
 }
-int hbk_sample(const float* logits, int ldl, const float* temperature, const uint64_t* seed, int32_t* out, int B, int V) {
+static int sample_impl(const float* logits, int ldl, const float* temperature, const uint64_t* seed, const int32_t* top_k,
+                       const float* top_p, int32_t* out, int B, int V) {
   void* scratch = nullptr;
   cudaError_t e = cudaMalloc(&scratch, hb::sample_scratch_bytes(B, V));
   if (e != cudaSuccess) return kret(e);
-  e = hb::sample_tokens(0, logits, ldl, temperature, seed, out, B, V, scratch);
+  e = hb::sample_tokens(0, logits, ldl, temperature, seed, out, B, V, scratch, top_k, top_p);
   cudaError_t e2 = cudaDeviceSynchronize();
   cudaFree(scratch);
   return kret(e != cudaSuccess ? e : e2);
+}
+int hbk_sample(const float* logits, int ldl, const float* temperature, const uint64_t* seed, int32_t* out, int B, int V) {
+  return sample_impl(logits, ldl, temperature, seed, nullptr, nullptr, out, B, V);
+}
+int hbk_sample_filtered(const float* logits, int ldl, const float* temperature, const uint64_t* seed, const int32_t* top_k,
+                        const float* top_p, int32_t* out, int B, int V) {
+  return sample_impl(logits, ldl, temperature, seed, top_k, top_p, out, B, V);
 }
 int hbk_cls_pool_l2(const void* x, const int32_t* first_row, float* out, int B, int H) {
   return kret(hb::cls_pool_l2(0, (const hb::bf16*)x, first_row, out, B, H));

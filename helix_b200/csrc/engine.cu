@@ -196,6 +196,8 @@ StepLayout Engine::layout(int T, int B) const {
   L.pt = o; o = al16(o + 4 * (size_t)B * max_pages_per_seq_);
   L.temp = o; o = al16(o + 4 * (size_t)B);
   L.seed = o; o = al16(o + 8 * (size_t)B);
+  L.topk = o; o = al16(o + 4 * (size_t)B);
+  L.topp = o; o = al16(o + 4 * (size_t)B);
   L.total = o;
   return L;
 }
@@ -441,6 +443,8 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
   const int32_t* pt = (const int32_t*)(d_step_ + L.pt);
   const float* temp = (const float*)(d_step_ + L.temp);
   const uint64_t* seed = (const uint64_t*)(d_step_ + L.seed);
+  const int32_t* topk = (const int32_t*)(d_step_ + L.topk);
+  const float* topp = (const float*)(d_step_ + L.topp);
   const size_t layer_kv = (size_t)num_pages_ * d.kv_heads * page_ * D;  // elements per K (or V) plane
 
   const int gcat = prefill ? 0 : 4;  // GEMM family: FLOPs in prefill steps, weight bytes in decode steps
@@ -515,7 +519,8 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
     GemmArgs g{h_, H, model_.lm_head, H, logits_, d.vocab, nullptr, 0, nullptr, B, d.vocab, H, EPI_F32, 0};
     SPAN(gcat, gwork(B, d.vocab, H), gemm_bf16_tn(stream_, g));
   }
-  LAUNCH(sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab, sample_ws_));
+  LAUNCH(sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab, sample_ws_,
+                       step_filtered_ ? topk : nullptr, step_filtered_ ? topp : nullptr));
   return HB_OK;
 }
 
@@ -531,6 +536,8 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
   const int32_t* pt = (const int32_t*)(d_step_ + L.pt);
   const float* temp = (const float*)(d_step_ + L.temp);
   const uint64_t* seed = (const uint64_t*)(d_step_ + L.seed);
+  const int32_t* topk = (const int32_t*)(d_step_ + L.topk);
+  const float* topp = (const float*)(d_step_ + L.topp);
   const size_t layer_kv = (size_t)num_pages_ * d.kv_heads * page_ * D;
   auto wbytes = [&](double N, double K) { return 2.0 * N * K + 2.0 * B * K + 4.0 * B * N; };
   const double rowb = 4.0 * B * H;
@@ -569,7 +576,8 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
   }
   SPAN(4, wbytes(d.vocab, H), gemm_skinny(stream_, plan_head_, xn_, H, model_.lm_head, H, skinny_ws_, B, d.vocab, H));
   SPAN(3, 8.0 * B * d.vocab, dec_sum_slabs(stream_, skinny_ws_, plan_head_, logits_, d.vocab, B, d.vocab));
-  SPAN(3, 4.0 * B * d.vocab, sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab, sample_ws_));
+  SPAN(3, 4.0 * B * d.vocab, sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab, sample_ws_,
+                                           step_filtered_ ? topk : nullptr, step_filtered_ ? topp : nullptr));
   return HB_OK;
 }
 
@@ -620,6 +628,9 @@ int Engine::forward_bert(int T, int B, int max_seqlen, const StepLayout& L, floa
 }
 
 // ------------------------------------------------------------------ scheduling
+static bool wants_filter(const hb_sampling& sp, int vocab) {
+  return sp.temperature > 0.f && ((sp.top_k > 0 && sp.top_k < vocab) || (sp.top_p > 0.f && sp.top_p < 1.f));
+}
 void Engine::finish_request(Request* r, ReqState st) {
   // mu_ held
   for (int32_t pg : r->pages) free_pages_.push_back(pg);
@@ -748,6 +759,9 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   int32_t* pt = (int32_t*)(h_step_ + L.pt);
   float* temp = (float*)(h_step_ + L.temp);
   uint64_t* seed = (uint64_t*)(h_step_ + L.seed);
+  int32_t* topk = (int32_t*)(h_step_ + L.topk);
+  float* topp = (float*)(h_step_ + L.topp);
+  step_filtered_ = false;
   int t = 0;
   for (int i = 0; i < B; ++i) {
     Request* r = batch[i];
@@ -766,6 +780,9 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
     }
     temp[i] = r->sp.temperature;
     seed[i] = r->sp.seed * 0x9E3779B97F4A7C15ull + 0;
+    topk[i] = r->sp.top_k;
+    topp[i] = r->sp.top_p;
+    step_filtered_ |= wants_filter(r->sp, d.vocab);
   }
   cu[B] = t;
   CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
@@ -817,6 +834,9 @@ int Engine::run_decode(std::vector<Request*>& batch) {
   int32_t* pt = (int32_t*)(h_step_ + L.pt);
   float* temp = (float*)(h_step_ + L.temp);
   uint64_t* seed = (uint64_t*)(h_step_ + L.seed);
+  int32_t* topk = (int32_t*)(h_step_ + L.topk);
+  float* topp = (float*)(h_step_ + L.topp);
+  step_filtered_ = false;
   for (int i = 0; i < B; ++i) {
     Request* r = batch[i];
     const int p = r->kv_len;
@@ -830,6 +850,9 @@ int Engine::run_decode(std::vector<Request*>& batch) {
     for (int j = 0; j < np; ++j) pt[(size_t)i * max_pages_per_seq_ + j] = r->pages[j];
     temp[i] = r->sp.temperature;
     seed[i] = r->sp.seed * 0x9E3779B97F4A7C15ull + (uint64_t)r->out.size();
+    topk[i] = r->sp.top_k;
+    topp[i] = r->sp.top_p;
+    step_filtered_ |= wants_filter(r->sp, d.vocab);
   }
   cu[B] = B;
   CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
@@ -837,25 +860,26 @@ int Engine::run_decode(std::vector<Request*>& batch) {
   for (Request* r : batch) attn_bytes_ += (double)(r->kv_len + 1) * 2.0 * d.kv_heads * d.head_dim * 2.0;
   CU(cudaEventRecord(fwd_a_, stream_));
   if (cfg_.use_cuda_graphs && !profile_) {
-    auto it = graphs_.find(B);
+    const int gkey = B | (step_filtered_ ? 1 << 20 : 0);  // the filtered sampler is a different kernel sequence
+    auto it = graphs_.find(gkey);
     if (it == graphs_.end()) {
       cudaGraph_t graph = nullptr;
       const uint64_t l0 = launches_.load();
       CU(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
       int rc = forward_llama(B, B, false, 1, L, false);
       cudaError_t ce = cudaStreamEndCapture(stream_, &graph);
-      graph_kernels_[B] = launches_.load() - l0;
+      graph_kernels_[gkey] = launches_.load() - l0;
       launches_.store(l0);  // captured, not executed
       if (rc != HB_OK) return rc;
       if (ce != cudaSuccess) return fail_cuda(ce, "cudaStreamEndCapture");
       cudaGraphExec_t exec = nullptr;
       CU(cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
-      it = graphs_.emplace(B, exec).first;
+      it = graphs_.emplace(gkey, exec).first;
     }
     CU(cudaGraphLaunch(it->second, stream_));
     graph_launches_++;
-    launches_.fetch_add(graph_kernels_[B]);
+    launches_.fetch_add(graph_kernels_[gkey]);
   } else {
     int rc = forward_llama(B, B, false, 1, L, false);
     if (rc != HB_OK) return rc;

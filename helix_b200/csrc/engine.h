@@ -40,7 +40,7 @@ struct Request {
 };
 
 struct StepLayout {
-  size_t tokens, positions, slots, cu, last, ctx, pt, temp, seed, total;
+  size_t tokens, positions, slots, cu, last, ctx, pt, temp, seed, topk, topp, total;
 };
 
 class Engine {
@@ -126,6 +126,7 @@ class Engine {
   int skinny_max_b_ = 0;
   int32_t* sampled_ = nullptr;
   void* sample_ws_ = nullptr;
+  bool step_filtered_ = false;  // some sequence of the current step samples with top-k / top-p
   uint8_t* d_step_ = nullptr;  // per-step int/float inputs (layout())
   uint8_t* h_step_ = nullptr;  // pinned mirror
   int32_t* h_sampled_ = nullptr;

@@ -70,7 +70,8 @@ cudaError_t rope_kv_write(cudaStream_t s, bf16* qkv, const int32_t* positions, c
 // Greedy / Gumbel-max sampling over fp32 logits[B,V]: out[b] = argmax_v(logits[b,v]/temp[b] + g(seed[b],v)),
 // temp[b] <= 0 -> pure argmax (lowest index wins ties).
 cudaError_t sample_tokens(cudaStream_t s, const float* logits, int ldl, const float* temperature, const uint64_t* seed,
-                          int32_t* out, int B, int V, void* scratch);
+                          int32_t* out, int B, int V, void* scratch, const int32_t* top_k = nullptr,
+                          const float* top_p = nullptr);  // per-row top-k (<=0 off) / top-p (outside (0,1) off), sampled rows only
 size_t sample_scratch_bytes(int B, int V);  // two-stage argmax partials
 // out[b,:] = l2normalize(x[first_row[b], :]) as fp32 (CLS pooling for bge-style encoders)
 cudaError_t cls_pool_l2(cudaStream_t s, const bf16* x, const int32_t* first_row, float* out, int B, int H);

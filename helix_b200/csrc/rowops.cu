@@ -305,10 +305,112 @@ __device__ __forceinline__ void block_argmax(float& best, int& bi, float* sval, 
   }
 }
 
+// ---- top-k / top-p (nucleus) filtering: stage 0 finds, per row, the logit threshold below which tokens are dropped ----
+// float -> unsigned key that orders like the float (and back)
+__device__ __forceinline__ uint32_t fkey(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+constexpr int kThrThreads = 1024;
+// block-wide sum of a (count, mass) pair; every thread gets the result; fixed summation tree -> deterministic
+__device__ __forceinline__ void block_sum2(unsigned long long& cnt, unsigned long long& mass, unsigned long long* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    mass += __shfl_xor_sync(0xffffffffu, mass, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // sh reuse across calls
+  if (l == 0) { sh[2 * w] = cnt; sh[2 * w + 1] = mass; }
+  __syncthreads();
+  cnt = sh[2 * l];
+  mass = sh[2 * l + 1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    mass += __shfl_xor_sync(0xffffffffu, mass, o);
+  }
+}
+// One block per row. Result thr[b]: tokens with logit < thr[b] are excluded from sampling (-inf: keep all).
+//   top-k : the largest threshold that keeps >= k tokens (ties at the k-th value are all kept)
+//   top-p : applied to the top-k survivors: the smallest set of most-probable tokens whose softmax(logits/T) mass
+//           reaches p of the survivors' mass
+// Both are bisections over the ordered 32-bit key space (at most 32 passes over an L2-resident row each, usually ~18:
+// the search stops as soon as one more step cannot change the kept set).  Probability mass is accumulated in 2^-32 fixed
+// point so the result does not depend on summation order.
+__global__ void __launch_bounds__(kThrThreads)
+sample_threshold_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ temperature,
+                        const int32_t* __restrict__ top_k, const float* __restrict__ top_p, float* __restrict__ thr, int V) {
+  __shared__ unsigned long long sh[64];
+  __shared__ float smax[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const float temp = temperature ? temperature[b] : 0.f;
+  const int k = top_k ? top_k[b] : 0;
+  const float p = top_p ? top_p[b] : 1.f;
+  const bool use_k = k > 0 && k < V, use_p = p > 0.f && p < 1.f;
+  if (!(temp > 0.f) || (!use_k && !use_p)) {  // greedy rows and unfiltered rows
+    if (threadIdx.x == 0) thr[b] = -INFINITY;
+    return;
+  }
+  const float* row = logits + (size_t)b * ldl;
+  // row max (for the softmax weights)
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += kThrThreads) mx = fmaxf(mx, row[v]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = smax[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float inv_t = 1.f / temp;
+  // (count, mass) of the tokens whose key is >= `key`
+  auto tally = [&](uint32_t key, unsigned long long& cnt, unsigned long long& mass) {
+    cnt = 0;
+    mass = 0;
+    for (int v = threadIdx.x; v < V; v += kThrThreads) {
+      const float x = row[v];
+      if (fkey(x) >= key) {
+        cnt += 1;
+        mass += (unsigned long long)(__expf((x - mx) * inv_t) * 4294967296.0f);
+      }
+    }
+    block_sum2(cnt, mass, sh);
+  };
+  unsigned long long lo = 0, hi = 1ull << 32;  // keys; invariant: keeping [lo, ..) is enough, keeping [hi, ..) is not
+  unsigned long long c_lo = V, c_hi = 0, m_lo = 0, c, m;
+  if (use_k) {
+    while (hi - lo > 1 && c_lo != (unsigned long long)k) {
+      const unsigned long long mid = (lo + hi) >> 1;
+      tally((uint32_t)mid, c, m);
+      if (c >= (unsigned long long)k) { lo = mid; c_lo = c; } else { hi = mid; c_hi = c; }
+    }
+  }
+  if (use_p) {
+    tally((uint32_t)lo, c_lo, m_lo);  // mass of the top-k survivors (of the whole row without top-k)
+    unsigned long long target = (unsigned long long)((double)p * (double)m_lo);
+    if (target < 1) target = 1;
+    hi = 1ull << 32;
+    c_hi = 0;
+    while (hi - lo > 1 && c_lo - c_hi > 1) {
+      const unsigned long long mid = (lo + hi) >> 1;
+      tally((uint32_t)mid, c, m);
+      if (m >= target) { lo = mid; c_lo = c; } else { hi = mid; c_hi = c; }
+    }
+  }
+  if (threadIdx.x == 0) thr[b] = lo == 0 ? -INFINITY : fkey_inv((uint32_t)lo);
+}
+
 // stage 1: grid (chunks, B): per-chunk argmax of logits/T + Gumbel noise -> part[b][chunk]
 __global__ void __launch_bounds__(256)
 sample_stage1_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ temperature,
-                     const uint64_t* __restrict__ seed, float* __restrict__ part_val, int* __restrict__ part_idx, int V) {
+                     const uint64_t* __restrict__ seed, const float* __restrict__ thr, float* __restrict__ part_val,
+                     int* __restrict__ part_idx, int V) {
   __shared__ float sval[8];
   __shared__ int sidx[8];
   pdl_launch_dependents();
@@ -319,11 +421,14 @@ sample_stage1_kernel(const float* __restrict__ logits, int ldl, const float* __r
   const bool greedy = !(temp > 0.f);
   const float inv_t = greedy ? 1.f : 1.f / temp;
   const uint64_t sd = seed ? seed[b] : 0;
+  const float floor_logit = (thr && !greedy) ? thr[b] : -INFINITY;  // top-k / top-p survivors only
   float best = -INFINITY;
   int bi = 0x7fffffff;
   const int v_end = min(V, (chunk + 1) * kSampleChunk);
   for (int v = chunk * kSampleChunk + threadIdx.x; v < v_end; v += 256) {
-    float x = row[v] * inv_t;
+    const float raw = row[v];
+    if (raw < floor_logit) continue;
+    float x = raw * inv_t;
     if (!greedy) {
       const uint64_t h = mix64(sd ^ (0xD1B54A32D192ED03ull * (uint64_t)(v + 1)));
       const float u = ((float)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0,1]
@@ -415,16 +520,24 @@ cudaError_t rope_kv_write(cudaStream_t s, bf16* qkv, const int32_t* positions, c
                                                          Hkv, D, page_size);
   return cudaGetLastError();
 }
-size_t sample_scratch_bytes(int B, int V) { return (size_t)B * ((V + kSampleChunk - 1) / kSampleChunk) * 8; }
+size_t sample_scratch_bytes(int B, int V) { return (size_t)B * ((V + kSampleChunk - 1) / kSampleChunk) * 8 + (size_t)B * 4; }
 
 cudaError_t sample_tokens(cudaStream_t s, const float* logits, int ldl, const float* temperature, const uint64_t* seed,
-                          int32_t* out, int B, int V, void* scratch) {
+                          int32_t* out, int B, int V, void* scratch, const int32_t* top_k, const float* top_p) {
   if (B <= 0) return cudaSuccess;
   const int chunks = (V + kSampleChunk - 1) / kSampleChunk;
   float* pv = static_cast<float*>(scratch);
   int* pi = reinterpret_cast<int*>(pv + (size_t)B * chunks);
-  cudaError_t e = launch_k(sample_stage1_kernel, dim3(chunks, B), dim3(256), 0, s, true, logits, ldl, temperature, seed, pv,
-                           pi, V);
+  float* thr = nullptr;
+  cudaError_t e;
+  if (temperature && (top_k || top_p)) {  // rows that ask for neither leave the kernel at once
+    thr = reinterpret_cast<float*>(pi + (size_t)B * chunks);
+    e = launch_k(sample_threshold_kernel, dim3(B), dim3(kThrThreads), 0, s, true, logits, ldl, temperature, top_k, top_p,
+                 thr, V);
+    if (e != cudaSuccess) return e;
+  }
+  e = launch_k(sample_stage1_kernel, dim3(chunks, B), dim3(256), 0, s, true, logits, ldl, temperature, seed,
+               (const float*)thr, pv, pi, V);
   if (e != cudaSuccess) return e;
   return launch_k(sample_stage2_kernel, dim3(B), dim3(32), 0, s, true, (const float*)pv, (const int*)pi, out, chunks);
 }

@@ -71,9 +71,11 @@ class Sampling:
     max_tokens: int = 16
     eos_token: int = -1
     capture: int = 0
+    top_k: int = 0      # <= 0: off
+    top_p: float = 1.0  # outside (0, 1): off
 
     def to_c(self):
-        return SamplingC(self.temperature, self.seed, self.max_tokens, self.eos_token, self.capture)
+        return SamplingC(self.temperature, self.seed, self.max_tokens, self.eos_token, self.capture, self.top_k, self.top_p)
 
 
 def bf16_bits(a):

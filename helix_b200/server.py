@@ -159,7 +159,9 @@ class OpenAIServer:
         temp = body.get("temperature", 0.0) or 0.0   # the runner already rewrote 0 -> 0.1 (openai_chat_handlers.go:52-58)
         sp = Sampling(temperature=float(temp), seed=int(body.get("seed", 0) or 0),
                       max_tokens=int(body.get("max_tokens") or body.get("max_completion_tokens") or 256),
-                      eos_token=getattr(self.tok, "EOS", -1))
+                      eos_token=getattr(self.tok, "EOS", -1),
+                      top_p=float(body.get("top_p") or 1.0),      # openai.ChatCompletionRequest.TopP (nucleus)
+                      top_k=int(body.get("top_k") or 0))          # vLLM extension the reference's backend accepts
         return self.rt.engine.submit(ids, sp), len(ids), sp
 
     def chat_stream(self, body):

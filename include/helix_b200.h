@@ -83,7 +83,10 @@ typedef struct hb_sampling {
   int32_t max_tokens;  /* generated tokens, >= 1 */
   int32_t eos_token;   /* < 0: none */
   int32_t capture;     /* HB_CAPTURE_* bit mask (parity tap) */
-  int32_t reserved[3];
+  int32_t top_k;       /* sampled rows only: keep the k most likely tokens (ties at the k-th logit kept); <= 0: off */
+  float top_p;         /* nucleus: smallest set of most likely tokens (after top_k) with softmax(logits/T) mass >= top_p;
+                          values outside (0,1) (so also a zero-initialised struct): off */
+  int32_t reserved[1];
 } hb_sampling;
 
 #define HB_CAPTURE_NONE 0

@@ -31,6 +31,9 @@ int hbk_layernorm(const void* x, const void* gamma, const void* beta, void* out,
 int hbk_rope_kv_write(void* qkv, const int32_t* positions, const int32_t* slot_mapping, const float* inv_freq,
                       void* k_cache, void* v_cache, int T, int Hq, int Hkv, int D, int page_size);
 int hbk_sample(const float* logits, int ldl, const float* temperature, const uint64_t* seed, int32_t* out, int B, int V);
+/* as hbk_sample, restricted per row to the top_k / top_p survivors (either pointer may be NULL) */
+int hbk_sample_filtered(const float* logits, int ldl, const float* temperature, const uint64_t* seed, const int32_t* top_k,
+                        const float* top_p, int32_t* out, int B, int V);
 int hbk_cls_pool_l2(const void* x, const int32_t* first_row, float* out, int B, int H);
 
 int hbk_attn_prefill(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,

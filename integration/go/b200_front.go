@@ -86,7 +86,7 @@ func (f *openAIFront) chat(w http.ResponseWriter, r *http.Request) {
 		flusher, _ = w.(http.Flusher)
 		writeSSE(w, flusher, chunk(openai.ChatCompletionStreamChoiceDelta{Role: "assistant"}, ""))
 	}
-	fin, err := f.rt.Generate(r.Context(), prompt, maxTokens, req.Temperature, uint64(derefInt(req.Seed)), func(ids []int32) error {
+	fin, err := f.rt.Generate(r.Context(), prompt, maxTokens, req.Temperature, req.TopP, uint64(derefInt(req.Seed)), func(ids []int32) error {
 		n += len(ids)
 		text := f.tok.Decode(dropToken(ids, f.tok.EOS()))
 		full += text

@@ -150,8 +150,9 @@ func (r *B200Runtime) Status(context.Context) string {
 }
 
 // Generate streams token ids of one request; emit is called once per poll (one SSE chunk each).
-func (r *B200Runtime) Generate(ctx context.Context, prompt []int32, maxTokens int, temperature float32, seed uint64, emit func([]int32) error) (finished int, err error) {
-	sp := C.hb_sampling{temperature: C.float(temperature), seed: C.uint64_t(seed), max_tokens: C.int32_t(maxTokens), eos_token: -1}
+func (r *B200Runtime) Generate(ctx context.Context, prompt []int32, maxTokens int, temperature, topP float32, seed uint64, emit func([]int32) error) (finished int, err error) {
+	sp := C.hb_sampling{temperature: C.float(temperature), seed: C.uint64_t(seed), max_tokens: C.int32_t(maxTokens), eos_token: -1,
+		top_p: C.float(topP)} // 0 (absent from the request) = nucleus filtering off
 	var id C.uint64_t
 	if rc := C.hb_submit(r.eng, (*C.int32_t)(unsafe.Pointer(&prompt[0])), C.int32_t(len(prompt)), &sp, &id); rc != C.HB_OK {
 		return 0, r.lastError()

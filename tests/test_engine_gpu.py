@@ -144,6 +144,36 @@ def test_chunked_prefill_of_prompts_longer_than_the_step_budget(head_dim, budget
     assert st["kv_pages_free"] == st["kv_pages_total"]
 
 
+def test_top_k_top_p_through_the_engine():
+    """hb_sampling.top_k / top_p reach the sampler in prefill steps and in (graph-captured) decode steps: top_k=1 at any
+    temperature is greedy decoding; a mixed batch leaves the unfiltered request's tokens unchanged; seeded runs repeat."""
+    d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000)
+    sd = weights.llama_state_dict(d, 3, 0.05)
+    pr = [weights.random_tokens(40 + i, 20 + 7 * i, d.vocab) for i in range(3)]
+    with hb.Engine(hb.EngineConfig(max_seqs=4, max_ctx=256, max_batched_tokens=256, use_cuda_graphs=1)) as e:
+        e.load_state_dict(d, sd)
+        greedy = e.generate(pr, hb.Sampling(max_tokens=12))[1]
+        k1 = e.generate(pr, hb.Sampling(max_tokens=12, temperature=1.5, seed=9, top_k=1))[1]
+        assert k1 == greedy
+        plain = e.generate([pr[0]], hb.Sampling(max_tokens=12, temperature=0.9, seed=4))[1][0]
+        ra = e.submit(pr[0], hb.Sampling(max_tokens=12, temperature=0.9, seed=4))
+        rb = e.submit(pr[1], hb.Sampling(max_tokens=12, temperature=0.9, seed=5, top_p=0.3, top_k=20))
+        outs = {ra: [], rb: []}
+        done = set()
+        while len(done) < 2:
+            e.step()
+            for r in outs:
+                t, fin = e.poll(r)
+                outs[r] += t
+                if fin:
+                    done.add(r)
+        assert outs[ra] == plain
+        again = e.generate([pr[1]], hb.Sampling(max_tokens=12, temperature=0.9, seed=5, top_p=0.3, top_k=20))[1][0]
+        assert again == outs[rb] and len(again) == 12
+        tiny_p = e.generate(pr, hb.Sampling(max_tokens=12, temperature=2.0, seed=1, top_p=1e-6))[1]
+        assert tiny_p == greedy                      # a vanishing nucleus keeps only the most likely token
+
+
 def test_step_loop_thread_eos_cancel_and_errors():
     d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000)
     sd = weights.llama_state_dict(d, 0, 0.02)

@@ -184,6 +184,61 @@ def test_sampling_argmax_and_gumbel(L):
     torch.testing.assert_close(freq, torch.softmax(lg[0] / 0.7, -1), atol=0.03, rtol=0)
 
 
+def test_sampling_top_k_top_p(L):
+    """Top-k / nucleus filtering in front of the Gumbel-max sampler: exact set membership against a float64 restatement
+    (vLLM semantics: top-k first, then top-p over the survivors), untouched rows identical to the unfiltered sampler."""
+    torch.manual_seed(5)
+    B, V = 64, 128256
+    logits = (torch.randn(1, V, device="cuda") * 2.5).repeat(B, 1).contiguous()
+    temp = torch.full((B,), 0.8, device="cuda")
+    seeds = torch.arange(B, device="cuda", dtype=torch.int64) * 104729 + 7
+    topk = torch.zeros(B, device="cuda", dtype=torch.int32)
+    topp = torch.ones(B, device="cuda")
+    topk[0:16] = 1                    # == argmax whatever the noise
+    topk[16:32] = 40
+    topp[32:48] = 0.9
+    topk[48:56], topp[48:56] = 50, 0.5
+    temp[60:] = 0.0                   # greedy rows ignore the filters
+    topk[60:] = 3
+    out, base = torch.empty(B, device="cuda", dtype=torch.int32), torch.empty(B, device="cuda", dtype=torch.int32)
+    ck(L, L.hbk_sample_filtered(p(logits), V, p(temp), p(seeds), p(topk), p(topp), p(out), B, V))
+    ck(L, L.hbk_sample(p(logits), V, p(temp), p(seeds), p(base), B, V))
+    out2 = torch.empty_like(out)
+    ck(L, L.hbk_sample_filtered(p(logits), V, p(temp), p(seeds), p(topk), p(topp), p(out2), B, V))
+    assert torch.equal(out, out2)
+    row = logits[0].double().cpu().numpy()
+    order = np.argsort(-row, kind="stable")
+    o = out.cpu().numpy()
+
+    def nucleus(cands, pth):
+        pr = np.exp((row[cands] - row[cands].max()) / 0.8)
+        cum = np.cumsum(pr / pr.sum())
+        return set(cands[: int(np.searchsorted(cum, pth) + 1)].tolist())
+
+    assert (o[0:16] == order[0]).all()
+    assert set(o[16:32].tolist()) <= set(order[:40].tolist()) and len(set(o[16:32].tolist())) > 3
+    lo, hi = nucleus(order, 0.9 - 1e-4), nucleus(order, 0.9 + 1e-4)
+    assert set(o[32:48].tolist()) <= hi and len(hi) < V // 2 and len(lo) > 10
+    assert set(o[48:56].tolist()) <= nucleus(order[:50], 0.5 + 1e-4)
+    assert (o[56:60] == base.cpu().numpy()[56:60]).all()      # unfiltered sampled rows: same token as the plain sampler
+    assert (o[60:] == order[0]).all()
+    # distribution over a small vocabulary: p = [.4 .3 .2 .1], top_p = 0.75 keeps {0,1,2} (0.4+0.3 < 0.75), renormalised
+    n = 6000
+    lg = torch.log(torch.tensor([[0.4, 0.3, 0.2, 0.1]], device="cuda")).repeat(n, 1).contiguous()
+    o3 = torch.empty(n, device="cuda", dtype=torch.int32)
+    sd = torch.arange(n, device="cuda", dtype=torch.int64) * 31 + 1
+    t1, p75 = torch.ones(n, device="cuda"), torch.full((n,), 0.75, device="cuda")   # keep alive across the call
+    ck(L, L.hbk_sample_filtered(p(lg), 4, p(t1), p(sd), None, p(p75), p(o3), n, 4))
+    freq = torch.bincount(o3.long(), minlength=4).float().cpu() / n
+    torch.testing.assert_close(freq, torch.tensor([0.4, 0.3, 0.2, 0.0]) / 0.9, atol=0.03, rtol=0)
+    # ties at the k-th logit are all kept
+    tie = torch.tensor([[5.0, 1.0, 5.0, 5.0, 0.0, 5.0, -2.0, 1.0]], device="cuda").repeat(2000, 1).contiguous()
+    o4 = torch.empty(2000, device="cuda", dtype=torch.int32)
+    sd4, k2 = sd[:2000].contiguous(), torch.full((2000,), 2, device="cuda", dtype=torch.int32)
+    ck(L, L.hbk_sample_filtered(p(tie), 8, p(t1), p(sd4), p(k2), None, p(o4), 2000, 8))
+    assert set(o4.cpu().tolist()) == {0, 2, 3, 5}
+
+
 def test_cls_pool(L):
     x = rnd(50, 768, seed=30)
     first = torch.tensor([0, 7, 49], device="cuda", dtype=torch.int32)
