@@ -13,7 +13,7 @@ class LibraryMissing(RuntimeError):
 class EngineCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("memory_budget_bytes", C.c_uint64), ("max_seqs", C.c_int32),
                 ("max_ctx", C.c_int32), ("max_batched_tokens", C.c_int32), ("kv_page_size", C.c_int32),
-                ("use_cuda_graphs", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("use_cuda_graphs", C.c_int32), ("enable_prefix_cache", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class ModelDescC(C.Structure):
@@ -36,7 +36,8 @@ class StatsC(C.Structure):
                 ("running", C.c_int32), ("waiting", C.c_int32), ("steps_prefill", C.c_uint64),
                 ("steps_decode", C.c_uint64), ("tokens_prefill", C.c_uint64), ("tokens_decode", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("graph_launches", C.c_uint64), ("cuda_error", C.c_int32),
-                ("reserved", C.c_int32 * 7), ("gpu_ms_prefill", C.c_double), ("gpu_ms_decode", C.c_double),
+                ("kv_pages_cached", C.c_int32), ("reserved0", C.c_int32), ("prefix_hit_tokens", C.c_uint64),
+                ("reserved", C.c_int32 * 3), ("gpu_ms_prefill", C.c_double), ("gpu_ms_decode", C.c_double),
                 ("prof_ms", C.c_double * 8), ("prof_work", C.c_double * 8), ("prof_launches", C.c_uint64 * 8)]
 
 

@@ -313,6 +313,9 @@ int Engine::alloc_runtime() {
     // NaN/Inf bit patterns left behind by a previous owner of the memory
     CU(cudaMemsetAsync(kv_, 0, kv_bytes_, stream_));
     CU(cudaStreamSynchronize(stream_));
+    pmeta_.assign(num_pages_, PageMeta{});
+    cache_.clear();
+    lru_.clear();
     free_pages_.resize(num_pages_);
     for (int i = 0; i < num_pages_; ++i) free_pages_[i] = num_pages_ - 1 - i;  // pop_back hands out page 0 first
   } else {
@@ -627,13 +630,72 @@ int Engine::forward_bert(int T, int B, int max_seqlen, const StepLayout& L, floa
   return HB_OK;
 }
 
+// ------------------------------------------------------------------ prefix cache (all under mu_)
+static uint64_t page_key(uint64_t parent, const int32_t* toks, int n) {
+  uint64_t h = parent ^ 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < n; ++i) {
+    h ^= (uint64_t)(uint32_t)toks[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 31;
+  }
+  return h;
+}
+int32_t Engine::take_page() {
+  int32_t pg;
+  if (!free_pages_.empty()) {
+    pg = free_pages_.back();
+    free_pages_.pop_back();
+  } else {
+    auto it = lru_.begin();  // oldest unreferenced cached page
+    pg = it->second;
+    lru_.erase(it);
+    cache_.erase(pmeta_[pg].key);
+    pmeta_[pg].cached = false;
+  }
+  pmeta_[pg].ref = 1;
+  return pg;
+}
+void Engine::drop_page(int32_t pg) {
+  PageMeta& m = pmeta_[pg];
+  if (--m.ref > 0) return;
+  if (m.cached) {
+    m.tick = ++tick_;
+    lru_[m.tick] = pg;
+  } else {
+    free_pages_.push_back(pg);
+  }
+}
+// Every page the sequence has completely filled (prompt or generated tokens, K/V resident) becomes addressable by content.
+void Engine::register_full_pages(Request* r) {
+  if (!cfg_.enable_prefix_cache) return;
+  const int full = r->kv_len / page_;
+  std::vector<int32_t> toks(page_);
+  for (int i = r->registered; i < full; ++i) {
+    for (int j = 0; j < page_; ++j) toks[j] = token_at(r, i * page_ + j);
+    const uint64_t parent = r->chain_key;
+    const uint64_t key = page_key(parent, toks.data(), page_);
+    const int32_t pg = r->pages[i];
+    PageMeta& m = pmeta_[pg];
+    if (!m.cached && !cache_.count(key)) {  // same content already cached on another page: keep that one
+      m.cached = true;
+      m.key = key;
+      m.parent = parent;
+      m.toks = toks;
+      cache_[key] = pg;
+    }
+    r->chain_key = key;
+    r->registered = i + 1;
+  }
+}
+
 // ------------------------------------------------------------------ scheduling
 static bool wants_filter(const hb_sampling& sp, int vocab) {
   return sp.temperature > 0.f && ((sp.top_k > 0 && sp.top_k < vocab) || (sp.top_p > 0.f && sp.top_p < 1.f));
 }
 void Engine::finish_request(Request* r, ReqState st) {
   // mu_ held
-  for (int32_t pg : r->pages) free_pages_.push_back(pg);
+  // last page first: the LRU then evicts a chain from its tail and the shared root (system prompt) survives longest
+  for (auto it = r->pages.rbegin(); it != r->pages.rend(); ++it) drop_page(*it);
   r->pages.clear();
   r->state = st;
 }
@@ -939,15 +1001,39 @@ int Engine::step(int* did_work) {
       Request* r = waiting_.front();
       const int n = (int)r->prompt.size();
       if (r->pages.empty()) {
-        const int need = (n + r->sp.max_tokens + page_ - 1) / page_;
+        const int total = (n + r->sp.max_tokens + page_ - 1) / page_;
         if ((int)(running_.size() + batch.size()) >= cfg_.max_seqs) break;
-        if ((int)free_pages_.size() < need) break;
-        if (n <= t_cap_ && T + n > t_cap_) break;
-        if (n > t_cap_ && T > 0) break;
-        for (int i = 0; i < need; ++i) {
-          r->pages.push_back(free_pages_.back());
-          free_pages_.pop_back();
+        // leading full pages already in the pool (always leave >= 1 prompt token to run: its logits seed the decode)
+        std::vector<int32_t> hit;
+        uint64_t key = 0;
+        int idle_hits = 0;
+        if (cfg_.enable_prefix_cache) {
+          for (int i = 0; (i + 1) * page_ <= n - 1; ++i) {
+            const uint64_t k2 = page_key(key, r->prompt.data() + (size_t)i * page_, page_);
+            auto it = cache_.find(k2);
+            if (it == cache_.end()) break;
+            const PageMeta& m = pmeta_[it->second];
+            if (m.parent != key || !std::equal(m.toks.begin(), m.toks.end(), r->prompt.begin() + (size_t)i * page_)) break;
+            hit.push_back(it->second);
+            idle_hits += m.ref == 0;
+            key = k2;
+          }
         }
+        const int need = total - (int)hit.size();
+        const int rest = n - (int)hit.size() * page_;  // prompt tokens still to prefill
+        if (pages_available() - idle_hits < need) break;
+        if (rest <= t_cap_ && T + rest > t_cap_) break;
+        if (rest > t_cap_ && T > 0) break;
+        for (int32_t pg : hit) {
+          PageMeta& m = pmeta_[pg];
+          if (m.ref++ == 0) lru_.erase(m.tick);
+          r->pages.push_back(pg);
+        }
+        for (int i = 0; i < need; ++i) r->pages.push_back(take_page());
+        r->prefilled = r->kv_len = (int)hit.size() * page_;
+        r->registered = (int)hit.size();
+        r->chain_key = key;
+        prefix_hit_tokens_ += (uint64_t)r->prefilled;
         r->state = ReqState::RUNNING;  // owns cache pages from here on: cancellation goes through cancel_flag
       }
       r->chunk = std::min(n - r->prefilled, t_cap_ - T);
@@ -981,10 +1067,12 @@ int Engine::step(int* did_work) {
       if (prefill) {
         r->prefilled += r->chunk;
         r->kv_len = r->prefilled;
+        register_full_pages(r);
         if (r->prefilled < (int)r->prompt.size()) continue;  // more chunks to go: nothing sampled yet
         running_.push_back(r);
       } else {
         r->kv_len += 1;
+        register_full_pages(r);
       }
       r->out.push_back(t);
       const bool done = (int)r->out.size() >= r->sp.max_tokens || (r->sp.eos_token >= 0 && t == r->sp.eos_token) ||
@@ -1116,7 +1204,9 @@ int Engine::stats(hb_stats* s) {
   s->workspace_bytes = ws_bytes_ + step_bytes_;
   s->budget_bytes = budget_;
   s->kv_pages_total = num_pages_;
-  s->kv_pages_free = (int)free_pages_.size();
+  s->kv_pages_free = pages_available();
+  s->kv_pages_cached = (int)lru_.size();
+  s->prefix_hit_tokens = prefix_hit_tokens_;
   s->running = (int)running_.size();
   s->waiting = (int)waiting_.size();
   s->steps_prefill = steps_prefill_;

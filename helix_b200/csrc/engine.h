@@ -12,6 +12,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <map>
 #include <unordered_map>
 #include <vector>
 
@@ -34,6 +35,8 @@ struct Request {
   int kv_len = 0;       // tokens whose K/V are in the cache
   int prefilled = 0;    // prompt tokens already prefilled (chunked prefill of prompts longer than one step's budget)
   int chunk = 0;        // prompt tokens scheduled in the current prefill step
+  int registered = 0;   // leading pages already content-addressed (prefix cache)
+  uint64_t chain_key = 0;  // content key of page `registered - 1`
   size_t polled = 0;    // tokens already handed to the caller
   std::vector<float> step_logits;    // rows of [vocab] (HB_CAPTURE_STEP_LOGITS)
   std::vector<float> prompt_logits;  // [n_prompt][vocab] (HB_CAPTURE_PROMPT_LOGITS)
@@ -116,6 +119,25 @@ class Engine {
   size_t kv_bytes_ = 0;
   int num_pages_ = 0;
   std::vector<int32_t> free_pages_;
+  // ---- prefix cache (mu_ held): full pages are content-addressed by the hash chain of their tokens
+  struct PageMeta {
+    int ref = 0;            // sequences holding the page
+    bool cached = false;    // registered in cache_
+    uint64_t key = 0, parent = 0;
+    uint64_t tick = 0;      // LRU stamp while unreferenced
+    std::vector<int32_t> toks;  // the page's 64 tokens (hits are verified, not trusted to the hash)
+  };
+  std::vector<PageMeta> pmeta_;
+  std::unordered_map<uint64_t, int32_t> cache_;   // content key -> page
+  std::map<uint64_t, int32_t> lru_;               // tick -> unreferenced cached page (oldest first)
+  uint64_t tick_ = 0, prefix_hit_tokens_ = 0;
+  int32_t take_page();                 // free list first, then evict the oldest unreferenced cached page
+  void drop_page(int32_t pg);          // a sequence lets go of a page
+  int pages_available() const { return (int)(free_pages_.size() + lru_.size()); }
+  void register_full_pages(Request* r);
+  int32_t token_at(const Request* r, int pos) const {
+    return pos < (int)r->prompt.size() ? r->prompt[pos] : r->out[pos - (int)r->prompt.size()];
+  }
   uint8_t* ws_ = nullptr;
   size_t ws_bytes_ = 0;
   bf16 *x_ = nullptr, *xn_ = nullptr, *qkv_ = nullptr, *attn_ = nullptr, *h_ = nullptr;

@@ -31,10 +31,11 @@ class EngineConfig:
     max_batched_tokens: int = 16384
     kv_page_size: int = 64
     use_cuda_graphs: int = 0
+    enable_prefix_cache: int = 0
 
     def to_c(self):
         return EngineCfg(self.device, self.memory_budget_bytes, self.max_seqs, self.max_ctx, self.max_batched_tokens,
-                         self.kv_page_size, self.use_cuda_graphs)
+                         self.kv_page_size, self.use_cuda_graphs, self.enable_prefix_cache)
 
 
 @dataclass
@@ -217,7 +218,7 @@ class Engine:
         self._ck(self._l.hb_get_stats(self._h, C.byref(s)))
         out = {}
         for k, _ in StatsC._fields_:
-            if k == "reserved":
+            if k.startswith("reserved"):
                 continue
             v = getattr(s, k)
             out[k] = list(v) if hasattr(v, "__len__") else v

@@ -21,6 +21,8 @@ class ParsedArgs:
     max_num_seqs: int = DEFAULT_MAX_NUM_SEQS
     max_model_len: Optional[int] = None
     task_embed: bool = False
+    enable_prefix_caching: bool = True       # vLLM V1's default; multi-turn Helix sessions resend the whole conversation
+    max_num_batched_tokens: Optional[int] = None
     unknown: List[str] = field(default_factory=list)
 
 
@@ -39,6 +41,10 @@ def parse_vllm_args(args: List[str]) -> ParsedArgs:
             out.max_model_len = int(nxt); i += 2
         elif a == "--task" and nxt is not None:
             out.task_embed = (nxt == "embed"); i += 2
+        elif a == "--max-num-batched-tokens" and nxt is not None:
+            out.max_num_batched_tokens = int(nxt); i += 2
+        elif a in ("--enable-prefix-caching", "--no-enable-prefix-caching"):
+            out.enable_prefix_caching = not a.startswith("--no-"); i += 1
         elif a.startswith("--") and nxt is not None and not nxt.startswith("--"):
             out.unknown += [a, nxt]; i += 2
         else:
@@ -107,7 +113,9 @@ class B200Runtime:
         cfg = EngineConfig(device=self.p.gpu_index,
                            memory_budget_bytes=memory_budget(self.p.model_memory_requirement, self.p.per_gpu_memory,
                                                              self.parsed.gpu_memory_utilization),
-                           max_seqs=self.parsed.max_num_seqs, max_ctx=max_ctx, use_cuda_graphs=1)
+                           max_seqs=self.parsed.max_num_seqs, max_ctx=max_ctx, use_cuda_graphs=1,
+                           max_batched_tokens=self.parsed.max_num_batched_tokens or 16384,
+                           enable_prefix_cache=int(self.parsed.enable_prefix_caching and not embed))
         eng = Engine(cfg)
         try:
             if self.p.state_dict is not None:

@@ -59,7 +59,10 @@ typedef struct hb_engine_cfg {
   int32_t max_batched_tokens;   /* prompt tokens processed per prefill step (default 16384) */
   int32_t kv_page_size;         /* tokens per KV page; must be 64 */
   int32_t use_cuda_graphs;      /* capture the decode step per batch size */
-  int32_t reserved[7];
+  int32_t enable_prefix_cache;  /* --enable-prefix-caching: full KV pages (64 tokens) are content-addressed; a new prompt
+                                   whose leading pages are already in the pool (an earlier turn of the same chat, a
+                                   shared system prompt) only prefills the rest */
+  int32_t reserved[6];
 } hb_engine_cfg;
 
 typedef struct hb_model_desc {
@@ -102,7 +105,10 @@ typedef struct hb_stats {
   uint64_t kernel_launches;   /* launches of this library's kernels since creation */
   uint64_t graph_launches;
   int32_t cuda_error;         /* sticky cudaError_t, 0 = healthy */
-  int32_t reserved[7];
+  int32_t kv_pages_cached;    /* unreferenced pages kept for prefix reuse (counted in kv_pages_free: evictable) */
+  int32_t reserved0;
+  uint64_t prefix_hit_tokens; /* prompt tokens served from cached pages instead of being prefilled */
+  int32_t reserved[3];
   /* device time of the forward passes (CUDA events on the engine stream: after the step's inputs are
      resident, before the sampled ids are copied back) */
   double gpu_ms_prefill, gpu_ms_decode;

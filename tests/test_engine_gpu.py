@@ -40,6 +40,16 @@ def check_tokens_against(oracle, prompt, toks, rows):
         logits = oracle.forward([t])[-1]
 
 
+def check_greedy(oracle, prompt, toks):
+    """Tokens only: every generated token is the oracle's argmax, or within the near-tie margin of it."""
+    oracle.reset()
+    logits = oracle.forward(prompt)[-1]
+    for i, t in enumerate(toks):
+        best = int(np.argmax(logits))
+        assert t == best or logits[best] - logits[t] <= 2 * tol(logits), f"step {i}: token {t} vs oracle {best}"
+        logits = oracle.forward([t])[-1]
+
+
 @pytest.mark.parametrize("name", sorted(LLAMA_CASES))
 @pytest.mark.parametrize("graphs", [0, 1])
 def test_llama_matches_golden_and_oracle(name, graphs, golden_dir):
@@ -172,6 +182,70 @@ def test_top_k_top_p_through_the_engine():
         assert again == outs[rb] and len(again) == 12
         tiny_p = e.generate(pr, hb.Sampling(max_tokens=12, temperature=2.0, seed=1, top_p=1e-6))[1]
         assert tiny_p == greedy                      # a vanishing nucleus keeps only the most likely token
+
+
+def test_prefix_cache_reuses_pages_across_requests_and_turns():
+    """enable_prefix_cache: leading full pages (64 tokens) of a prompt that are already in the pool are not prefilled
+    again — a shared system prompt, and the next turn of a chat (which resends prompt + generated tokens).  The rest of
+    the prompt runs through the paged chunk path; logits/tokens still match the fp32 oracle; nothing leaks; an
+    over-committed pool evicts unreferenced cached pages instead of refusing work."""
+    d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000)
+    sd = weights.llama_state_dict(d, 21, 0.05)
+    oracle = LlamaOracle(d, sd)
+    sys_p = weights.random_tokens(300, 200, d.vocab)
+    p1 = np.concatenate([sys_p, weights.random_tokens(301, 50, d.vocab)])
+    p2 = np.concatenate([sys_p, weights.random_tokens(302, 70, d.vocab)])
+    cap = CAPTURE_STEP_LOGITS
+    with hb.Engine(hb.EngineConfig(max_seqs=4, max_ctx=512, max_batched_tokens=512, enable_prefix_cache=1)) as e:
+        e.load_state_dict(d, sd)
+        r1, o1 = e.generate([p1], hb.Sampling(max_tokens=20, capture=cap))
+        s1 = e.stats()
+        assert s1["prefix_hit_tokens"] == 0 and s1["kv_pages_cached"] == (250 + 19) // 64
+        r2, o2 = e.generate([p2], hb.Sampling(max_tokens=8, capture=cap))
+        s2 = e.stats()
+        assert s2["prefix_hit_tokens"] == 192                      # the 3 full pages of the shared system prompt
+        assert s2["tokens_prefill"] - s1["tokens_prefill"] == len(p2) - 192
+        check_tokens_against(oracle, p2, o2[0], e.captured_logits(r2[0], cap))
+        # next turn of chat 1: prompt + assistant reply + new user text; the reply's pages were cached as they filled
+        p3 = np.concatenate([p1, np.array(o1[0], np.int32), weights.random_tokens(303, 30, d.vocab)])
+        r3, o3 = e.generate([p3], hb.Sampling(max_tokens=6, capture=cap))
+        s3 = e.stats()
+        assert s3["prefix_hit_tokens"] - s2["prefix_hit_tokens"] == 256
+        check_tokens_against(oracle, p3, o3[0], e.captured_logits(r3[0], cap))
+        # an exact repeat leaves one page to compute (the last prompt token's logits are needed)
+        r4, o4 = e.generate([p1], hb.Sampling(max_tokens=20))
+        assert e.stats()["prefix_hit_tokens"] - s3["prefix_hit_tokens"] == 192 and len(o4[0]) == 20
+        check_greedy(oracle, p1, o4[0])
+        # two requests sharing the prefix in one step, while both hold references
+        ra = e.submit(p1, hb.Sampling(max_tokens=5))
+        rb = e.submit(p2, hb.Sampling(max_tokens=5))
+        outs = {ra: [], rb: []}
+        done = set()
+        while len(done) < 2:
+            e.step()
+            for r in outs:
+                t, fin = e.poll(r)
+                outs[r] += t
+                if fin:
+                    done.add(r)
+        check_greedy(oracle, p1, outs[ra])
+        check_greedy(oracle, p2, outs[rb])
+        st = e.stats()
+        assert st["kv_pages_free"] == st["kv_pages_total"] and 0 < st["kv_pages_cached"] <= st["kv_pages_total"]
+    # eviction: a 16-page pool, every request needs 6-7 pages and leaves cached pages behind
+    with hb.Engine(hb.EngineConfig(max_seqs=2, max_ctx=512, max_batched_tokens=512, enable_prefix_cache=1)) as e:
+        e.load_state_dict(d, sd)
+        total = e.stats()["kv_pages_total"]
+        assert total == 16
+        for i in range(8):
+            pr = weights.random_tokens(400 + i, 330 + i, d.vocab)
+            _, o = e.generate([pr, pr[:100]], hb.Sampling(max_tokens=40))
+            assert len(o[0]) == 40 and len(o[1]) == 40
+            st = e.stats()
+            assert st["kv_pages_free"] == total and st["running"] == 0
+        assert e.stats()["prefix_hit_tokens"] == 0
+        _, o = e.generate([pr], hb.Sampling(max_tokens=4))      # the most recent prompt is still cached
+        assert e.stats()["prefix_hit_tokens"] == 320
 
 
 def test_step_loop_thread_eos_cancel_and_errors():

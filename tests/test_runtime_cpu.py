@@ -17,6 +17,8 @@ def test_args_from_the_scheduler_round_trip():
     assert p.gpu_memory_utilization == 0.10 and p.max_num_seqs == 64 and p.max_model_len == 8192 and not p.task_embed
     assert R.parse_vllm_args(["--task", "embed", "--trust-remote-code"]).task_embed
     assert R.parse_vllm_args([]).max_num_seqs == 256  # types/memory.go:11
+    assert R.parse_vllm_args([]).enable_prefix_caching and not R.parse_vllm_args(["--no-enable-prefix-caching"]).enable_prefix_caching
+    assert R.parse_vllm_args(["--max-num-batched-tokens", "8192", "--enable-prefix-caching"]).max_num_batched_tokens == 8192
     # ... and the budget the engine derives: exact bytes when the slot carries them, ratio*perGPU otherwise
     assert R.memory_budget(8 * GB, 80 * GB, 0.10) == 8 * GB
     assert R.memory_budget(0, 80 * GB, 0.10) == 8 * GB
