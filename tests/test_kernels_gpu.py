@@ -7,6 +7,7 @@ import pytest
 import torch
 
 import helix_b200 as hb
+from oracle import sampling_ref
 
 pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
@@ -210,16 +211,14 @@ def test_sampling_top_k_top_p(L):
     order = np.argsort(-row, kind="stable")
     o = out.cpu().numpy()
 
-    def nucleus(cands, pth):
-        pr = np.exp((row[cands] - row[cands].max()) / 0.8)
-        cum = np.cumsum(pr / pr.sum())
-        return set(cands[: int(np.searchsorted(cum, pth) + 1)].tolist())
+    def kept(top_k, top_p):  # the oracle's survivor set (a hair more inclusive: the kernel sums masses in fp32 fixed point)
+        return set(np.flatnonzero(sampling_ref.keep_mask(row, 0.8, top_k, min(top_p + 1e-4, 1.0))).tolist())
 
     assert (o[0:16] == order[0]).all()
-    assert set(o[16:32].tolist()) <= set(order[:40].tolist()) and len(set(o[16:32].tolist())) > 3
-    lo, hi = nucleus(order, 0.9 - 1e-4), nucleus(order, 0.9 + 1e-4)
-    assert set(o[32:48].tolist()) <= hi and len(hi) < V // 2 and len(lo) > 10
-    assert set(o[48:56].tolist()) <= nucleus(order[:50], 0.5 + 1e-4)
+    assert set(o[16:32].tolist()) <= kept(40, 1.0) == set(order[:40].tolist()) and len(set(o[16:32].tolist())) > 3
+    hi = kept(0, 0.9)
+    assert set(o[32:48].tolist()) <= hi and 10 < len(hi) < V // 2
+    assert set(o[48:56].tolist()) <= kept(50, 0.5) and len(kept(50, 0.5)) < 50
     assert (o[56:60] == base.cpu().numpy()[56:60]).all()      # unfiltered sampled rows: same token as the plain sampler
     assert (o[60:] == order[0]).all()
     # distribution over a small vocabulary: p = [.4 .3 .2 .1], top_p = 0.75 keeps {0,1,2} (0.4+0.3 < 0.75), renormalised
