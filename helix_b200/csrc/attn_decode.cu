@@ -115,12 +115,15 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);  // warp-uniform for the compiler too
   const uint32_t tmem_S = tmem_base;       // 2 x 16 columns
   const uint32_t tmem_O = tmem_base + 32;  // 16 columns
 
+  // Single-thread roles: whole warp converged through loops and waits, TMA / tcgen05 instructions predicated on an
+  // elect.sync leader (under `if (lane == 0)` ptxas wraps each of them in a waterfall loop; see gemm.cu).
   if (warp == 0) {
-    if (lane == 0) {
+    const bool elected = elect_one_sync();
+    {
       for (int j = 0; j < n_tiles; ++j) {
         const int pg0 = (t_begin + j) * 2;
         // a tile's second page may not exist yet: re-load the first one (finite data, masked by the softmax)
@@ -130,19 +133,22 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
           const int item = 2 * j + kv;
           const int s = item % STAGES;
           mbar_wait(&r_empty[s], ((item / STAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(&r_full[s], C::KV_BYTES);
           const CUtensorMap* mp = kv ? &map_v : &map_k;
           uint8_t* dst = ring + s * C::KV_BYTES;
+          if (elected) {
+            mbar_arrive_expect_tx(&r_full[s], C::KV_BYTES);
 #pragma unroll
-          for (int c = 0; c < C::SUB; ++c) {
-            tma_load_3d(dst + c * (BKV * 128), mp, &r_full[s], c * 64, 0, page_a * Hkv + kvh, kEvictFirst);
-            tma_load_3d(dst + c * (BKV * 128) + PAGE * 128, mp, &r_full[s], c * 64, 0, page_b * Hkv + kvh, kEvictFirst);
+            for (int c = 0; c < C::SUB; ++c) {
+              tma_load_3d(dst + c * (BKV * 128), mp, &r_full[s], c * 64, 0, page_a * Hkv + kvh, kEvictFirst);
+              tma_load_3d(dst + c * (BKV * 128) + PAGE * 128, mp, &r_full[s], c * 64, 0, page_b * Hkv + kvh, kEvictFirst);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool elected = elect_one_sync();
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(BKV, NQ, 0, 0);   // A = K tile (K-major), B = Q (K-major)
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, NQ, 1, 0);   // A = V tile (MN-major: d contiguous), B = P^T
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
@@ -152,14 +158,16 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
         mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(ring + s * C::KV_BYTES);
+        if (elected) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint64_t adesc = umma_desc_kmajor_sw128(k_addr + (k >> 2) * (BKV * 128) + (k & 3) * 32);
-          const uint64_t bdesc = umma_desc_kmajor_sw128(q_addr + (k >> 2) * (NQ * 128) + (k & 3) * 32);
-          umma_f16_ss(tmem_S + (j & 1) * NQ, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < D / 16; ++k) {
+            const uint64_t adesc = umma_desc_kmajor_sw128(k_addr + (k >> 2) * (BKV * 128) + (k & 3) * 32);
+            const uint64_t bdesc = umma_desc_kmajor_sw128(q_addr + (k >> 2) * (NQ * 128) + (k & 3) * 32);
+            umma_f16_ss(tmem_S + (j & 1) * NQ, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+          }
+          umma_commit(&r_empty[s]);
+          umma_commit(&s_full[j & 1]);
         }
-        umma_commit(&r_empty[s]);
-        umma_commit(&s_full[j & 1]);
       };
       mbar_wait(q_ready, 0);
       issue_s(0);
@@ -170,14 +178,16 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
         mbar_wait(&r_full[s], (item / STAGES) & 1);
         tc_fence_after();
         const uint32_t v_addr = smem_u32(ring + s * C::KV_BYTES);
+        if (elected) {
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t adesc = umma_desc_mnmajor_sw128(v_addr + k * (16 * 128), BKV * 128, 1024);
-          const uint64_t bdesc = umma_desc_kmajor_sw128(p_addr + (k >> 2) * (NQ * 128) + (k & 3) * 32);
-          umma_f16_ss(tmem_O, adesc, bdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BKV / 16; ++k) {
+            const uint64_t adesc = umma_desc_mnmajor_sw128(v_addr + k * (16 * 128), BKV * 128, 1024);
+            const uint64_t bdesc = umma_desc_kmajor_sw128(p_addr + (k >> 2) * (NQ * 128) + (k & 3) * 32);
+            umma_f16_ss(tmem_O, adesc, bdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&r_empty[s]);
+          umma_commit(pv_done);
         }
-        umma_commit(&r_empty[s]);
-        umma_commit(pv_done);
       }
     }
   } else {

@@ -16,7 +16,7 @@ namespace {
 
 constexpr int BQ = 128;     // q rows per softmax warpgroup
 constexpr int QPAIR = 256;  // q rows per CTA: two q tiles ping-pong on the tensor pipe
-constexpr int BKV = 128;    // kv positions per tile
+constexpr int BKV = 64;     // kv positions per tile (= one KV page)
 constexpr int kThreads = 320;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
@@ -72,26 +72,32 @@ template <int D>
 struct ACfg {
   static constexpr int Q_BYTES = BQ * D * 2;    // one q tile
   static constexpr int KV_BYTES = BKV * D * 2;
-  static constexpr int SMEM = 2 * Q_BYTES + 4 * KV_BYTES + 1024 + 256;
+  static constexpr int STAGES = 4;              // K ring and V ring depth (16 KB tiles at D = 128)
+  static constexpr int SMEM = 2 * Q_BYTES + 2 * STAGES * KV_BYTES + 1024 + 512;
   static constexpr int SUB = D / 64;  // 64-column swizzle sub-tiles per row
 };
 
 // PERSISTENT kernel: one CTA per SM walks a static list of (256-row q pair, sequence, q-head) items, heaviest
-// (latest, most kv tiles under the causal mask) first, so the TMEM allocation, barrier setup and — above all — the
-// latency of an item's first loads and of its output write-back overlap with the neighbouring items' work.
-// TMEM: S0 | S1 (128 fp32 columns each; P_t, packed bf16x2, aliases the first 64 columns of S_t) | O0 | O1.
+// (latest, most kv tiles under the causal mask) first, so the TMEM allocation, barrier setup and the latency of an
+// item's first loads and of its output write-back overlap with the neighbouring items' work.
+//
+// kv tiles are 64 positions (= one KV page) and every q tile owns TWO S buffers in TMEM:
+//   TMEM columns: [S0a S0b S1a S1b] 4 x 64 fp32 | O0 | O1 (D fp32 each, at 256 + t*128).  P_t(j), packed bf16x2,
+//   overwrites the first 32 columns of the buffer S_t(j) was read from.
+// S_t(j+1) = Q_t·K(j+1)ᵀ is therefore issued BEFORE the softmax of tile j has produced P_t(j): the softmax warps find
+// their next S tile waiting when they finish one, and the tensor pipe always has the other buffer's / other q tile's
+// work queued.  (With one S buffer per q tile — the previous version — S(j+1) had to wait for PV(j), i.e. for the
+// softmax: ncu showed the softmax warps waiting for S 56 % of the time and the tensor pipe 41 % busy.)
 //   warp 0 lane 0 : TMA producer (Q pair of the next item as soon as the last S MMA of the current one retired;
-//                   K_j / V_j through 2-stage rings that keep running across items)
-//   warp 1 lane 0 : MMA issuer, ping-pong order  PV0(j) S0(j+1) PV1(j) S1(j+1):  while one warpgroup runs its
-//                   softmax the tensor pipe works for the other one.  P is consumed straight from TMEM
-//                   (tcgen05.mma A-from-TMEM), V straight from its [kv][d] layout (MN-major B): no smem round trip.
+//                   K_j / V_j through KST-stage rings that keep running across items)
+//   warp 1 lane 0 : MMA issuer, program order  S_t(0) S_t(1) | PV0(j) S0(j+2) PV1(j) S1(j+2) ...  P is consumed straight
+//                   from TMEM (tcgen05.mma A-from-TMEM), V straight from its [kv][d] layout (MN-major B).
 //   warps 2..5 / 6..9 : softmax warpgroup of q tile 0 / 1, one thread per q row; lazy O rescale; O/l -> global.
 //
 // PAGED = false: K/V rows come from the same packed [T, ...] activation as Q (whole-prompt prefill, encoder), kv_len == q_len.
 // PAGED = true : the q rows are the LAST q_len positions of a kv_len-long sequence whose K/V (including the chunk's own,
-//                written by the RoPE/KV-write kernel just before) live in the paged pool: chunked prefill of prompts
-//                longer than one step's token budget.  A K/V tile is two 64-position pages, fetched by two TMA boxes
-//                into the two halves of the same swizzled smem tile the contiguous path uses.
+//                written by the RoPE/KV-write kernel just before) live in the paged pool (chunked prefill, prefix-cache
+//                hits): tile j is page_table[b][j].
 template <int D, bool PAGED, int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -100,24 +106,25 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     int max_q_pairs, const int32_t* __restrict__ kv_lens, const int32_t* __restrict__ page_table,
                     int max_pages, int Hkv) {
   using C = ACfg<D>;
+  constexpr int KST = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                        // [2][Q_BYTES]
-  uint8_t* sK = sQ + 2 * C::Q_BYTES;         // [2][KV_BYTES]
-  uint8_t* sV = sK + 2 * C::KV_BYTES;        // [2][KV_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * C::KV_BYTES);
+  uint8_t* sQ = smem;                          // [2][Q_BYTES]
+  uint8_t* sK = sQ + 2 * C::Q_BYTES;           // [KST][KV_BYTES]
+  uint8_t* sV = sK + KST * C::KV_BYTES;        // [KST][KV_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KST * C::KV_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;    // [2]
-  uint64_t* k_empty = bars + 4;   // [2]
-  uint64_t* v_full = bars + 6;    // [2]
-  uint64_t* v_empty = bars + 8;   // [2]
-  uint64_t* s_full = bars + 10;   // [2] per q tile
-  uint64_t* p_full = bars + 12;   // [2]
-  uint64_t* pv_done = bars + 14;  // [2]
-  uint64_t* o_free = bars + 16;   // [2]
-  uint64_t* p_half = bars + 18;   // [2] first 64 kv columns of P_t are in TMEM: the PV MMA starts on them
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* s_full = bars + 2;    // [q tile][S buffer]
+  uint64_t* p_full = bars + 6;    // [q tile][S buffer]
+  uint64_t* pv_done = bars + 10;  // [q tile][tile parity]: two per q tile, so that a waiter can never be a whole
+                                  // phase behind (PV(x-2) is known complete whenever PV(x) is waited for, PV(x-1) is not)
+  uint64_t* o_free = bars + 14;   // [2]
+  uint64_t* k_full = bars + 16;   // [KST]
+  uint64_t* k_empty = k_full + KST;
+  uint64_t* v_full = k_empty + KST;
+  uint64_t* v_empty = v_full + KST;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(v_empty + KST);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = max_q_pairs * B * Hq;
@@ -155,16 +162,17 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     tma_prefetch_desc(&map_v);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) mbar_init(&o_free[i], 4);
+    for (int i = 0; i < KST; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&p_half[i], 4);
-      mbar_init(&pv_done[i], 1);
-      mbar_init(&o_free[i], 4);
     }
     fence_barrier_init();
   }
@@ -175,126 +183,132 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);  // warp-uniform for the compiler too
 
+  // The two single-thread roles run their loops and barrier waits with the WHOLE warp converged and only predicate the
+  // TMA / tcgen05 instructions on an elect.sync leader: ptxas then keeps descriptors and addresses in uniform registers.
+  // Under `if (lane == 0)` it wraps every UTCHMMA / UTMALDG in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop —
+  // ~140 cycles per MMA issued, more than a 128x64x16 MMA takes to execute (ncu: tensor pipe 33-41 % busy, issuer never
+  // waiting for its inputs).
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one_sync();
+    {
       int kt = 0, qi = 0;  // running kv-tile / item counters: barrier phases continue across items
       for (int idx = blockIdx.x; idx < num_items; idx += gridDim.x) {
         const Item it = get_item(idx);
         if (!it.valid) continue;
         mbar_wait(q_empty, (qi & 1) ^ 1);  // every S MMA of the previous item has retired: the Q pair buffer is free
-        mbar_arrive_expect_tx(q_full, (it.act1 ? 2 : 1) * C::Q_BYTES);
-        for (int t = 0; t < (it.act1 ? 2 : 1); ++t)
+        if (leader) {
+          mbar_arrive_expect_tx(q_full, (it.act1 ? 2 : 1) * C::Q_BYTES);
+          for (int t = 0; t < (it.act1 ? 2 : 1); ++t)
 #pragma unroll
-          for (int c = 0; c < C::SUB; ++c)
-            tma_load_2d(sQ + t * C::Q_BYTES + c * (BQ * 128), &map_q, q_full, it.h * D + c * 64, it.seq0 + it.q0 + t * BQ,
-                        kEvictFirst);
+            for (int c = 0; c < C::SUB; ++c)
+              tma_load_2d(sQ + t * C::Q_BYTES + c * (BQ * 128), &map_q, q_full, it.h * D + c * 64,
+                          it.seq0 + it.q0 + t * BQ, kEvictFirst);
+        }
         ++qi;
         for (int j = 0; j < it.n; ++j, ++kt) {
-          const int s = kt & 1;
-          const uint32_t ph = (kt >> 1) & 1;
-          int blk0 = 0, blk1 = 0;  // PAGED: (page, kv head) blocks of the tile's two pages
-          if constexpr (PAGED) {
-            const int32_t* pt = page_table + (size_t)it.b * max_pages;
-            const int npages = (it.kv_len + 63) >> 6;
-            blk0 = pt[2 * j] * Hkv + it.kvh;
-            // a ragged last tile re-reads its first page for the (fully masked) second half: always finite data
-            blk1 = (2 * j + 1 < npages ? pt[2 * j + 1] : pt[2 * j]) * Hkv + it.kvh;
-          }
+          const int s = kt % KST;
+          const uint32_t ph = (kt / KST) & 1;
+          int blk = 0;  // PAGED: (page, kv head) block of the tile's page
+          if constexpr (PAGED) blk = page_table[(size_t)it.b * max_pages + j] * Hkv + it.kvh;
           mbar_wait(&k_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[s], C::KV_BYTES);
+          if (leader) {
+            mbar_arrive_expect_tx(&k_full[s], C::KV_BYTES);
 #pragma unroll
-          for (int c = 0; c < C::SUB; ++c) {
-            uint8_t* dst = sK + s * C::KV_BYTES + c * (BKV * 128);
-            if constexpr (PAGED) {
-              tma_load_3d(dst, &map_k, &k_full[s], c * 64, 0, blk0, kEvictLast);
-              tma_load_3d(dst + 64 * 128, &map_k, &k_full[s], c * 64, 0, blk1, kEvictLast);
-            } else {
-              tma_load_2d(dst, &map_k, &k_full[s], it.kvh * D + c * 64, it.seq0 + j * BKV, kEvictLast);
+            for (int c = 0; c < C::SUB; ++c) {
+              uint8_t* dst = sK + s * C::KV_BYTES + c * (BKV * 128);
+              if constexpr (PAGED)
+                tma_load_3d(dst, &map_k, &k_full[s], c * 64, 0, blk, kEvictLast);
+              else
+                tma_load_2d(dst, &map_k, &k_full[s], it.kvh * D + c * 64, it.seq0 + j * BKV, kEvictLast);
             }
           }
           mbar_wait(&v_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&v_full[s], C::KV_BYTES);
+          if (leader) {
+            mbar_arrive_expect_tx(&v_full[s], C::KV_BYTES);
 #pragma unroll
-          for (int c = 0; c < C::SUB; ++c) {
-            uint8_t* dst = sV + s * C::KV_BYTES + c * (BKV * 128);
-            if constexpr (PAGED) {
-              tma_load_3d(dst, &map_v, &v_full[s], c * 64, 0, blk0, kEvictLast);
-              tma_load_3d(dst + 64 * 128, &map_v, &v_full[s], c * 64, 0, blk1, kEvictLast);
-            } else {
-              tma_load_2d(dst, &map_v, &v_full[s], it.kvh * D + c * 64, it.seq0 + j * BKV, kEvictLast);
+            for (int c = 0; c < C::SUB; ++c) {
+              uint8_t* dst = sV + s * C::KV_BYTES + c * (BKV * 128);
+              if constexpr (PAGED)
+                tma_load_3d(dst, &map_v, &v_full[s], c * 64, 0, blk, kEvictLast);
+              else
+                tma_load_2d(dst, &map_v, &v_full[s], it.kvh * D + c * 64, it.seq0 + j * BKV, kEvictLast);
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool leader = elect_one_sync();
+    {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // A = P from TMEM, B = V is MN-major
-      auto issue_s = [&](int t, int slot) {  // S_t = Q_t · K^T (K tile in ring slot `slot`)
+      int kt = 0, qi = 0;
+      int jt[2] = {0, 0};  // kv tiles processed so far per q tile: S buffer = (jt + j) & 1, its phase = (jt + j) >> 1
+      int oi[2] = {0, 0};  // items processed so far per q tile (phase of o_free)
+      // S_t(j) = Q_t · K(j)ᵀ into the q tile's buffer (jt + j) & 1
+      auto issue_s = [&](int t, int j) {
+        const int tile = jt[t] + j, slot = (kt + j) % KST;
         const uint32_t q_addr = smem_u32(sQ + t * C::Q_BYTES);
         const uint32_t k_addr = smem_u32(sK + slot * C::KV_BYTES);
+        const uint32_t d_tmem = tmem_base + t * 128 + (tile & 1) * BKV;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * (128 * 128) + (k & 3) * 32;
-          umma_f16_ss(tmem_base + t * BKV, umma_desc_kmajor_sw128(q_addr + off), umma_desc_kmajor_sw128(k_addr + off),
-                      idesc_qk, k != 0 ? 1u : 0u);
-        }
-        umma_commit(&s_full[t]);
-      };
-      // O_t (+)= P_t · V, in two halves of 64 kv positions: the first starts while the softmax warps still produce the second
-      auto issue_pv = [&](int t, int slot, bool first, uint32_t parity) {
-        const uint32_t v_addr = smem_u32(sV + slot * C::KV_BYTES);
-        mbar_wait(&p_half[t], parity);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          if (k == BKV / 32) {
-            mbar_wait(&p_full[t], parity);
-            tc_fence_after();
+          for (int k = 0; k < D / 16; ++k) {
+            umma_f16_ss(d_tmem, umma_desc_kmajor_sw128(q_addr + (k >> 2) * (BQ * 128) + (k & 3) * 32),
+                        umma_desc_kmajor_sw128(k_addr + (k >> 2) * (BKV * 128) + (k & 3) * 32), idesc_qk, k != 0 ? 1u : 0u);
           }
-          const uint64_t bdesc = umma_desc_mnmajor_sw128(v_addr + k * (16 * 128), BKV * 128, 1024);
-          umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * BKV + k * 8, bdesc, idesc_pv, (!first || k != 0) ? 1u : 0u);
+          umma_commit(&s_full[t * 2 + (tile & 1)]);
         }
-        umma_commit(&pv_done[t]);
       };
-      int kt = 0, qi = 0;
-      int jt[2] = {0, 0};  // kv tiles processed so far per q tile (phases of s_full / p_full / pv_done)
-      int oi[2] = {0, 0};  // items processed so far per q tile (phase of o_free)
+      // O_t (+)= P_t(j) · V(j)
+      auto issue_pv = [&](int t, int j) {
+        const int tile = jt[t] + j, slot = (kt + j) % KST;
+        const uint32_t v_addr = smem_u32(sV + slot * C::KV_BYTES);
+        if (j == 0) mbar_wait(&o_free[t], (oi[t] & 1) ^ 1);  // the previous item's O_t has been read out
+        mbar_wait(&p_full[t * 2 + (tile & 1)], (tile >> 1) & 1);
+        tc_fence_after();
+        const uint32_t p_tmem = tmem_base + t * 128 + (tile & 1) * BKV;
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            const uint64_t bdesc = umma_desc_mnmajor_sw128(v_addr + k * (16 * 128), BKV * 128, 1024);
+            umma_f16_ts(tmem_base + 256 + t * 128, p_tmem + k * 8, bdesc, idesc_pv, (j != 0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&pv_done[t * 2 + (tile & 1)]);
+        }
+      };
+      auto wait_k = [&](int j) {
+        mbar_wait(&k_full[(kt + j) % KST], ((kt + j) / KST) & 1);
+        tc_fence_after();
+      };
       for (int idx = blockIdx.x; idx < num_items; idx += gridDim.x) {
         const Item it = get_item(idx);
         if (!it.valid) continue;
         const int n0 = it.n0, n1 = it.n1, n = it.n;
         mbar_wait(q_full, qi & 1);
-        mbar_wait(&k_full[kt & 1], (kt >> 1) & 1);
-        tc_fence_after();
-        if (n0 > 0) issue_s(0, kt & 1);  // S_t is free: the previous item's last PV_t was issued before (in-order retire)
-        if (n1 > 0) issue_s(1, kt & 1);
-        umma_commit(&k_empty[kt & 1]);
-        if (n == 1) umma_commit(q_empty);
+        // S(0), S(1) of both q tiles: buffers (jt)&1 / (jt+1)&1 are free — the PVs that read them were issued earlier
+        for (int j = 0; j < 2 && j < n; ++j) {
+          wait_k(j);
+          if (j < n0) issue_s(0, j);
+          if (j < n1) issue_s(1, j);
+          if (leader) umma_commit(&k_empty[(kt + j) % KST]);
+        }
+        if (n <= 2 && leader) umma_commit(q_empty);
         for (int j = 0; j < n; ++j) {
-          const int s = (kt + j) & 1;
-          mbar_wait(&v_full[s], ((kt + j) >> 1) & 1);
-          if (j < n0) {
-            if (j == 0) mbar_wait(&o_free[0], (oi[0] & 1) ^ 1);  // the previous item's O_0 has been read out
-            issue_pv(0, s, j == 0, (jt[0] + j) & 1);
-          }
-          if (j + 1 < n) {
-            mbar_wait(&k_full[s ^ 1], ((kt + j + 1) >> 1) & 1);
-            tc_fence_after();
-          }
-          if (j + 1 < n0) issue_s(0, s ^ 1);  // overwrites S0/P0 strictly after PV0(j): same-thread MMAs retire in order
-          if (j < n1) {
-            if (j == 0) mbar_wait(&o_free[1], (oi[1] & 1) ^ 1);
-            issue_pv(1, s, j == 0, (jt[1] + j) & 1);
-          }
-          umma_commit(&v_empty[s]);
-          if (j + 1 < n1) issue_s(1, s ^ 1);
-          if (j + 1 < n) {
-            umma_commit(&k_empty[s ^ 1]);
-            if (j + 2 == n) umma_commit(q_empty);  // that was the item's last S MMA: Q may be overwritten
+          const int vs = (kt + j) % KST;
+          mbar_wait(&v_full[vs], ((kt + j) / KST) & 1);
+          tc_fence_after();
+          if (j + 2 < n) wait_k(j + 2);
+          if (j < n0) issue_pv(0, j);
+          if (j + 2 < n0) issue_s(0, j + 2);  // reuses the buffer PV0(j) reads: same-thread MMAs retire in order
+          if (j < n1) issue_pv(1, j);
+          if (leader) umma_commit(&v_empty[vs]);
+          if (j + 2 < n1) issue_s(1, j + 2);
+          if (j + 2 < n && leader) {
+            umma_commit(&k_empty[(kt + j + 2) % KST]);
+            if (j + 3 == n) umma_commit(q_empty);  // that was the item's last S MMA: Q may be overwritten
           }
         }
         kt += n;
@@ -310,52 +324,52 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const int qd = warp & 3;
     const int r = qd * 32 + lane;  // q row in tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t tS = tmem_base + lane_sel + t * BKV;
     const uint32_t tO = tmem_base + lane_sel + 256 + t * 128;
-    int jt = 0;  // kv tiles this warpgroup has processed so far (barrier phases)
+    int jt = 0;  // kv tiles this warpgroup has processed so far (S buffer and barrier phases)
     for (int idx = blockIdx.x; idx < num_items; idx += gridDim.x) {
       const Item it = get_item(idx);
       if (!it.valid) continue;
       const int nt = t == 0 ? it.n0 : it.n1;
       if (nt == 0) continue;
-      const int len = it.kv_len;             // kv positions of the sequence
+      const int len = it.kv_len;                  // kv positions of the sequence
       const int qt0 = it.q_off + it.q0 + t * BQ;  // absolute position of the tile's first q row
       const int qpos = qt0 + r;
-      const int qrow = it.q0 + t * BQ + r;   // row within the sequence's q rows of this step
+      const int qrow = it.q0 + t * BQ + r;        // row within the sequence's q rows of this step
       float m_used = 0.f, l = 0.f;
       for (int j = 0; j < nt; ++j) {
-        mbar_wait(&s_full[t], (jt + j) & 1);
+        const int tile = jt + j;
+        const uint32_t tS = tmem_base + lane_sel + t * 128 + (tile & 1) * BKV;
+        mbar_wait(&s_full[t * 2 + (tile & 1)], (tile >> 1) & 1);
         tc_fence_after();
         const int kv0 = j * BKV;
         const bool need_mask = (kv0 + BKV > len) || (causal && (kv0 + BKV - 1 > qt0));
         const int lim = causal ? min(len - 1, qpos) : len - 1;  // last valid kv position for this row
-        // ---- the S row: four back-to-back TMEM loads, ONE wait (a warpgroup has a single warp per SM sub-partition, so
-        //      nothing else hides the load latency), then max / exp2 / pack entirely in registers
-        uint32_t sv[128];
+        // ---- the S row: back-to-back TMEM loads, ONE wait, then max / exp2 / pack entirely in registers
+        uint32_t sv[BKV];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < BKV / 32; ++c) {
           uint32_t(&dst)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]);
           tmem_ld_32x32b_x32(tS + c * 32, dst);
         }
         tmem_ld_wait();
         if (need_mask) {  // diagonal / ragged tiles only: knock the invalid columns out once, the hot loops stay branch-free
 #pragma unroll
-          for (int i = 0; i < 128; ++i) sv[i] = (kv0 + i <= lim) ? sv[i] : 0xff800000u;  // -inf
+          for (int i = 0; i < BKV; ++i) sv[i] = (kv0 + i <= lim) ? sv[i] : 0xff800000u;  // -inf
         }
-        float mx8[8];  // eight independent chains: a single running max is a 64-deep dependent FMNMX chain
+        float mx8[8];  // eight independent chains instead of one long dependent FMNMX chain
 #pragma unroll
         for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sv[i]);
 #pragma unroll
-        for (int i = 8; i < 128; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sv[i]));
+        for (int i = 8; i < BKV; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sv[i]));
         const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
         float m_new = (mx == -INFINITY) ? m_used : mx * scale_log2;
         if (j == 0) {
           m_used = m_new;
         } else {
           const bool need = m_new > m_used + kRescaleThreshold;
-          mbar_wait(&pv_done[t], (jt + j - 1) & 1);  // O_t consistent (and P_t consumed) before anything below touches them
-          tc_fence_after();
           if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(&pv_done[t * 2 + ((tile - 1) & 1)], ((tile - 1) >> 1) & 1);  // PV(j-1), hence every PV so far, is in O_t
+            tc_fence_after();
             m_new = fmaxf(m_new, m_used);
             const float f = fast_exp2(m_used - m_new);
             m_used = m_new;
@@ -372,12 +386,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             }
           }
         }
-        // ---- p = exp2(s*scale - m) (masked entries are -inf -> 0), row sum, P (bf16x2) written over the S row
+        // ---- p = exp2(s*scale - m) (masked entries are -inf -> 0), row sum, P (bf16x2) written over the S buffer's head.
         //      POLY of every 8 column pairs take the FMA-pipe exp2, the rest the SFU; scale/subtract and the sum are packed
         const uint64_t scale2 = f2_pack(scale_log2, scale_log2), negm2 = f2_pack(-m_used, -m_used);
         uint64_t sum2a = 0, sum2b = 0;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < BKV / 16; ++c) {
           uint32_t pk[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -397,12 +411,6 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             pk[i] = pack_bf16x2(p0, p1);
           }
           tmem_st_32x32b_x8(tS + c * 8, pk);
-          if (c == 3) {  // P columns 0..63 are stored: let the issuer start the first half of PV
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_half[t]);
-          }
         }
         {
           float s0, s1;
@@ -412,10 +420,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) mbar_arrive(&p_full[t * 2 + (tile & 1)]);
       }
       // ---- item epilogue: O / l -> global, then hand O_t back to the MMA issuer
-      mbar_wait(&pv_done[t], (jt + nt - 1) & 1);
+      mbar_wait(&pv_done[t * 2 + ((jt + nt - 1) & 1)], ((jt + nt - 1) >> 1) & 1);
       tc_fence_after();
       const float inv_l = l > 0.f ? 1.0f / l : 0.f;
       bf16* orow = out + (size_t)(it.seq0 + qrow) * ldo + it.h * D;

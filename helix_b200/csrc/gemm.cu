@@ -155,11 +155,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);  // warp-uniform for the compiler too
 
+  // The single-thread roles keep the whole warp converged through their loops and barrier waits and predicate only the
+  // TMA / tcgen05 instructions on an elect.sync leader: descriptors and addresses then live in uniform registers.  Under
+  // `if (lane == 0)` ptxas wraps every UTCHMMA / UTMALDG in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop.
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    const bool elected = elect_one_sync();
+    {
       int s = 0;
       uint32_t phase = 0;
       for (int t = tile_worker; t < num_tiles; t += tile_workers) {
@@ -167,18 +171,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tile_coords(t, num_m, num_n, tile_grp, tile_group_n, mi, ni);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
-          if constexpr (CG == 2) {
-            // both CTAs' bytes complete on the LEADER's barrier (its MMA thread is the only consumer)
-            if (is_leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
-            else mbar_arrive_cluster(&full_bar[s], 0);
-            tma_load_2d_2sm(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K,
-                            mi * TILE_M + (int)cta_rank * BLOCK_M, kEvictNormal);
-            tma_load_2d_2sm(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K,
-                            ni * BN + (int)cta_rank * (BN / 2), kEvictNormal);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-            tma_load_2d(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, mi * BLOCK_M, kEvictNormal);
-            tma_load_2d(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K, ni * BN, kEvictNormal);
+          if (elected) {
+            if constexpr (CG == 2) {
+              // both CTAs' bytes complete on the LEADER's barrier (its MMA thread is the only consumer)
+              if (is_leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+              else mbar_arrive_cluster(&full_bar[s], 0);
+              tma_load_2d_2sm(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K,
+                              mi * TILE_M + (int)cta_rank * BLOCK_M, kEvictNormal);
+              tma_load_2d_2sm(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K,
+                              ni * BN + (int)cta_rank * (BN / 2), kEvictNormal);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+              tma_load_2d(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, mi * BLOCK_M, kEvictNormal);
+              tma_load_2d(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K, ni * BN, kEvictNormal);
+            }
           }
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
@@ -186,7 +192,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && is_leader) {
+    if (is_leader) {
+      const bool elected = elect_one_sync();
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN);
       int s = 0;
       uint32_t phase = 0;
@@ -202,19 +209,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + s * C::A_BYTES);
           const uint32_t b_addr = smem_u32(smem_b + s * C::B_BYTES);
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + k * UMMA_K * 2);
-            const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + k * UMMA_K * 2);
-            if constexpr (CG == 2) umma_f16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t adesc = umma_desc_kmajor_sw128(a_addr + k * UMMA_K * 2);
+              const uint64_t bdesc = umma_desc_kmajor_sw128(b_addr + k * UMMA_K * 2);
+              if constexpr (CG == 2) umma_f16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees this smem stage (in both CTAs when paired) once the MMAs above retire
+            if constexpr (CG == 2) umma_commit_2sm_mc(&empty_bar[s], 0x3); else umma_commit(&empty_bar[s]);
           }
-          // frees this smem stage (in both CTAs when paired) once the MMAs above retire
-          if constexpr (CG == 2) umma_commit_2sm_mc(&empty_bar[s], 0x3); else umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if constexpr (CG == 2) umma_commit_2sm_mc(&tmem_full[as], 0x3); else umma_commit(&tmem_full[as]);
+        if (elected) {
+          if constexpr (CG == 2) umma_commit_2sm_mc(&tmem_full[as], 0x3); else umma_commit(&tmem_full[as]);
+        }
       }
     }
   } else {

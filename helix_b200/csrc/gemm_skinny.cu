@@ -99,22 +99,27 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);  // warp-uniform for the compiler too
 
+  // Single-thread roles: whole warp converged through loops and waits, TMA / tcgen05 instructions predicated on an
+  // elect.sync leader (under `if (lane == 0)` ptxas wraps each of them in a waterfall loop; see gemm.cu).
   if (warp == 0) {
-    if (lane == 0) {
+    const bool elected = elect_one_sync();
+    {
       // Weights are static: fill the whole ring with W tiles BEFORE waiting for the producer of X
       // (programmatic dependent launch) - the HBM stream never stops between back-to-back projections.
       const long long pre_end = min(u1, u0 + STAGES);
       for (long long u = u0; u < pre_end; ++u) {
         const int s = (int)(u - u0);
-        mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-        tma_load_2d(smem_w + s * C::W_BYTES, &map_w, &full_bar[s], (int)(u % KB) * BLOCK_K, (int)(u / KB) * BLOCK_N, kEvictFirst);
+        if (elected) {
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          tma_load_2d(smem_w + s * C::W_BYTES, &map_w, &full_bar[s], (int)(u % KB) * BLOCK_K, (int)(u / KB) * BLOCK_N, kEvictFirst);
+        }
       }
       pdl_wait();
       for (long long u = u0; u < pre_end; ++u) {
         const int s = (int)(u - u0);
-        tma_load_2d(smem_x + s * C::X_BYTES, &map_x, &full_bar[s], (int)(u % KB) * BLOCK_K, 0, kEvictLast);
+        if (elected) tma_load_2d(smem_x + s * C::X_BYTES, &map_x, &full_bar[s], (int)(u % KB) * BLOCK_K, 0, kEvictLast);
       }
       int s = 0;
       uint32_t phase = 1;  // the ring has been filled once
@@ -122,14 +127,17 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       for (long long u = pre_end; u < u1; ++u) {
         const int tile = (int)(u / KB), kb = (int)(u % KB);
         mbar_wait(&empty_bar[s], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-        tma_load_2d(smem_w + s * C::W_BYTES, &map_w, &full_bar[s], kb * BLOCK_K, tile * BLOCK_N, kEvictFirst);
-        tma_load_2d(smem_x + s * C::X_BYTES, &map_x, &full_bar[s], kb * BLOCK_K, 0, kEvictLast);
+        if (elected) {
+          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          tma_load_2d(smem_w + s * C::W_BYTES, &map_w, &full_bar[s], kb * BLOCK_K, tile * BLOCK_N, kEvictFirst);
+          tma_load_2d(smem_x + s * C::X_BYTES, &map_x, &full_bar[s], kb * BLOCK_K, 0, kEvictLast);
+        }
         if (++s == STAGES) { s = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool elected = elect_one_sync();
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_N, MPAD);
       int s = 0;
       uint32_t phase = 0;
@@ -148,16 +156,18 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           tc_fence_after();
           const uint32_t w_addr = smem_u32(smem_w + s * C::W_BYTES);
           const uint32_t x_addr = smem_u32(smem_x + s * C::X_BYTES);
+          if (elected) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_f16_ss(d_tmem, umma_desc_kmajor_sw128(w_addr + k * UMMA_K * 2),
-                        umma_desc_kmajor_sw128(x_addr + k * UMMA_K * 2), idesc, (first && k == 0) ? 0u : 1u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              umma_f16_ss(d_tmem, umma_desc_kmajor_sw128(w_addr + k * UMMA_K * 2),
+                          umma_desc_kmajor_sw128(x_addr + k * UMMA_K * 2), idesc, (first && k == 0) ? 0u : 1u);
+            }
+            umma_commit(&empty_bar[s]);
           }
           first = false;
-          umma_commit(&empty_bar[s]);
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);
+        if (elected) umma_commit(&tmem_full[as]);
         ++it;
       }
     }
