@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -240,84 +241,105 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
     }
   } else if (warp == 1) {
+    // The issuer's own instruction stream is on the critical path (one warp, ~4 cycles per dependent instruction: the
+    // first version of this loop ran 508 SASS instructions per kv tile and took 2100 cycles for 1024 cycles of MMA work),
+    // so: descriptors are a per-kernel base plus a constant (the 14-bit address field never carries), ring slots and
+    // phases are running counters, and the steady state (both q tiles have a PV(j) and an S(j+2) to issue) is a
+    // branch-free instantiation; everything else goes through the flag-driven one.
     const bool leader = elect_one_sync();
-    {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // A = P from TMEM, B = V is MN-major
-      int kt = 0, qi = 0;
-      int jt[2] = {0, 0};  // kv tiles processed so far per q tile: S buffer = (jt + j) & 1, its phase = (jt + j) >> 1
-      int oi[2] = {0, 0};  // items processed so far per q tile (phase of o_free)
-      // S_t(j) = Q_t · K(j)ᵀ into the q tile's buffer (jt + j) & 1
-      auto issue_s = [&](int t, int j) {
-        const int tile = jt[t] + j, slot = (kt + j) % KST;
-        const uint32_t q_addr = smem_u32(sQ + t * C::Q_BYTES);
-        const uint32_t k_addr = smem_u32(sK + slot * C::KV_BYTES);
-        const uint32_t d_tmem = tmem_base + t * 128 + (tile & 1) * BKV;
-        if (leader) {
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // A = P from TMEM, B = V is MN-major
+    const uint64_t qdesc[2] = {umma_desc_kmajor_sw128(smem_u32(sQ)), umma_desc_kmajor_sw128(smem_u32(sQ + C::Q_BYTES))};
+    const uint64_t kdesc0 = umma_desc_kmajor_sw128(smem_u32(sK));
+    const uint64_t vdesc0 = umma_desc_mnmajor_sw128(smem_u32(sV), BKV * 128, 1024);
+    int kslot = 0, vslot = 0;         // ring slots of the next K / V tile to consume
+    uint32_t kphase = 0, vphase = 0;
+    int ps[2] = {0, 0};               // absolute index (over the kernel's life) of q tile t's next PV; S buffer = index & 1
+    int oi[2] = {0, 0};               // items processed so far per q tile (phase of o_free)
+    int qi = 0;
+    // S_t(tile x) = Q_t · Kᵀ (K in ring slot kslot) into buffer x & 1
+    auto mma_s = [&](int t, int x) {
+      const uint32_t d_tmem = tmem_base + t * 128 + (x & 1) * BKV;
+      const uint64_t kd = kdesc0 + (uint64_t)(kslot * (C::KV_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < D / 16; ++k) {
-            umma_f16_ss(d_tmem, umma_desc_kmajor_sw128(q_addr + (k >> 2) * (BQ * 128) + (k & 3) * 32),
-                        umma_desc_kmajor_sw128(k_addr + (k >> 2) * (BKV * 128) + (k & 3) * 32), idesc_qk, k != 0 ? 1u : 0u);
-          }
-          umma_commit(&s_full[t * 2 + (tile & 1)]);
-        }
-      };
-      // O_t (+)= P_t(j) · V(j)
-      auto issue_pv = [&](int t, int j) {
-        const int tile = jt[t] + j, slot = (kt + j) % KST;
-        const uint32_t v_addr = smem_u32(sV + slot * C::KV_BYTES);
-        if (j == 0) mbar_wait(&o_free[t], (oi[t] & 1) ^ 1);  // the previous item's O_t has been read out
-        mbar_wait(&p_full[t * 2 + (tile & 1)], (tile >> 1) & 1);
-        tc_fence_after();
-        const uint32_t p_tmem = tmem_base + t * 128 + (tile & 1) * BKV;
-        if (leader) {
+      for (int k = 0; k < D / 16; ++k)
+        umma_f16_ss(d_tmem, qdesc[t] + (((k >> 2) * (BQ * 128) + (k & 3) * 32) >> 4),
+                    kd + (((k >> 2) * (BKV * 128) + (k & 3) * 32) >> 4), idesc_qk, k != 0 ? 1u : 0u);
+      umma_commit(&s_full[t * 2 + (x & 1)]);
+    };
+    // O_t (+)= P_t(tile x) · V (V in ring slot vslot)
+    auto mma_pv = [&](int t, int x, uint32_t acc) {
+      const uint32_t p_tmem = tmem_base + t * 128 + (x & 1) * BKV;
+      const uint64_t vd = vdesc0 + (uint64_t)(vslot * (C::KV_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            const uint64_t bdesc = umma_desc_mnmajor_sw128(v_addr + k * (16 * 128), BKV * 128, 1024);
-            umma_f16_ts(tmem_base + 256 + t * 128, p_tmem + k * 8, bdesc, idesc_pv, (j != 0 || k != 0) ? 1u : 0u);
-          }
-          umma_commit(&pv_done[t * 2 + (tile & 1)]);
-        }
-      };
-      auto wait_k = [&](int j) {
-        mbar_wait(&k_full[(kt + j) % KST], ((kt + j) / KST) & 1);
+      for (int k = 0; k < BKV / 16; ++k)
+        umma_f16_ts(tmem_base + 256 + t * 128, p_tmem + k * 8, vd + ((k * 16 * 128) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
+      umma_commit(&pv_done[t * 2 + (x & 1)]);
+    };
+    auto k_advance = [&]() { if (++kslot == KST) { kslot = 0; kphase ^= 1; } };
+    auto v_advance = [&]() { if (++vslot == KST) { vslot = 0; vphase ^= 1; } };
+    // one kv tile j: PV_t(j) for the q tiles that have one, S_t(j+2) for those that have one
+    auto step = [&](auto fast_tag, bool pv0, bool s0, bool pv1, bool s1, bool first, bool last_s) {
+      constexpr bool FAST = decltype(fast_tag)::value;
+      const bool has_k = FAST || s0 || s1;
+      mbar_wait(&v_full[vslot], vphase);
+      if (has_k) mbar_wait(&k_full[kslot], kphase);
+      if (FAST || pv0) {
+        if (!FAST && first) mbar_wait(&o_free[0], (oi[0] & 1) ^ 1);  // the previous item's O_0 has been read out
+        mbar_wait(&p_full[ps[0] & 1], (ps[0] >> 1) & 1);
         tc_fence_after();
-      };
-      for (int idx = blockIdx.x; idx < num_items; idx += gridDim.x) {
-        const Item it = get_item(idx);
-        if (!it.valid) continue;
-        const int n0 = it.n0, n1 = it.n1, n = it.n;
-        mbar_wait(q_full, qi & 1);
-        // S(0), S(1) of both q tiles: buffers (jt)&1 / (jt+1)&1 are free — the PVs that read them were issued earlier
-        for (int j = 0; j < 2 && j < n; ++j) {
-          wait_k(j);
-          if (j < n0) issue_s(0, j);
-          if (j < n1) issue_s(1, j);
-          if (leader) umma_commit(&k_empty[(kt + j) % KST]);
+        if (leader) {
+          mma_pv(0, ps[0], FAST ? 1u : (first ? 0u : 1u));
+          if (FAST || s0) mma_s(0, ps[0]);  // S0(j+2) reuses the buffer PV0(j) reads: same-thread MMAs retire in order
         }
-        if (n <= 2 && leader) umma_commit(q_empty);
-        for (int j = 0; j < n; ++j) {
-          const int vs = (kt + j) % KST;
-          mbar_wait(&v_full[vs], ((kt + j) / KST) & 1);
-          tc_fence_after();
-          if (j + 2 < n) wait_k(j + 2);
-          if (j < n0) issue_pv(0, j);
-          if (j + 2 < n0) issue_s(0, j + 2);  // reuses the buffer PV0(j) reads: same-thread MMAs retire in order
-          if (j < n1) issue_pv(1, j);
-          if (leader) umma_commit(&v_empty[vs]);
-          if (j + 2 < n1) issue_s(1, j + 2);
-          if (j + 2 < n && leader) {
-            umma_commit(&k_empty[(kt + j + 2) % KST]);
-            if (j + 3 == n) umma_commit(q_empty);  // that was the item's last S MMA: Q may be overwritten
-          }
-        }
-        kt += n;
-        jt[0] += n0;
-        jt[1] += n1;
-        oi[0] += n0 > 0;
-        oi[1] += n1 > 0;
-        ++qi;
+        ++ps[0];
       }
+      if (FAST || pv1) {
+        if (!FAST && first) mbar_wait(&o_free[1], (oi[1] & 1) ^ 1);
+        mbar_wait(&p_full[2 + (ps[1] & 1)], (ps[1] >> 1) & 1);
+        tc_fence_after();
+        if (leader) {
+          mma_pv(1, ps[1], FAST ? 1u : (first ? 0u : 1u));
+          umma_commit(&v_empty[vslot]);
+          if (FAST || s1) mma_s(1, ps[1]);
+          if (has_k) umma_commit(&k_empty[kslot]);
+          if (!FAST && last_s) umma_commit(q_empty);  // that was the item's last S MMA: Q may be overwritten
+        }
+        ++ps[1];
+      } else if (leader) {
+        umma_commit(&v_empty[vslot]);
+        if (has_k) umma_commit(&k_empty[kslot]);
+        if (last_s) umma_commit(q_empty);
+      }
+      v_advance();
+      if (has_k) k_advance();
+    };
+    for (int idx = blockIdx.x; idx < num_items; idx += gridDim.x) {
+      const Item it = get_item(idx);
+      if (!it.valid) continue;
+      const int n0 = it.n0, n1 = it.n1, n = it.n;
+      mbar_wait(q_full, qi & 1);
+      // S(0), S(1) of both q tiles: their buffers are free — the PVs that read them were issued earlier
+      for (int j = 0; j < 2 && j < n; ++j) {
+        mbar_wait(&k_full[kslot], kphase);
+        tc_fence_after();
+        if (leader) {
+          if (j < n0) mma_s(0, ps[0] + j);
+          if (j < n1) mma_s(1, ps[1] + j);
+          umma_commit(&k_empty[kslot]);
+          if (j + 1 == n || (j == 1 && n == 2)) umma_commit(q_empty);
+        }
+        k_advance();
+      }
+      for (int j = 0; j < n; ++j) {
+        if (j > 0 && j + 3 < n0 && j + 3 < n1)
+          step(std::true_type{}, true, true, true, true, false, false);
+        else
+          step(std::false_type{}, j < n0, j + 2 < n0, j < n1, j + 2 < n1, j == 0, j + 3 == n);
+      }
+      oi[0] += n0 > 0;
+      oi[1] += n1 > 0;
+      ++qi;
     }
   } else {
     const int t = (warp - 2) >> 2;  // q tile of this warpgroup
@@ -527,8 +549,7 @@ int poly_pairs(int D) {
     env = s ? atoi(s) : -1;
   }
   if (env >= 0) return env;
-  (void)D;
-  return 2;  // measured on B200: 2 of 8 is +2-4 %, 4 of 8 already costs more issue slots than the SFU relief is worth
+  return D == 64 ? 2 : 0;  // measured on B200 (64-wide kv tiles): D=64 494 / 467 / 486 TFLOP/s at 2 / 0 / 4 of 8, D=128 1085 / 1114 / 1090
 }
 template <int D, bool PAGED>
 cudaError_t launch(cudaStream_t stream, const AttnPrefillArgs& a) {
