@@ -27,25 +27,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// Packed fp32x2 arithmetic (FFMA2 / FADD2: two lanes per issue slot on sm_100).
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 // 2^x for two values on the FMA/ALU pipes only (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3
 // minimax polynomial for 2^f (relative error 7.6e-5, far below the bf16 rounding P gets), n added into the exponent
 // field.  The SFU does 16 ex2/clk/SM: at 128x128 scores per kv tile that is exactly as long as the tile's two MMAs, so

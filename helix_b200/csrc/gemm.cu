@@ -65,21 +65,27 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int grp
 // (|erf error| <= 2.8e-4, |gelu error| <= 6.5e-4 — below bf16 resolution of the output), clamped to [-1, 1] beyond.
 // 16 FMA-pipe instructions per element instead of libdevice erff (branchy) or rcp+ex2: the FFN1 epilogue of the
 // encoder (K = 768, i.e. only 6144 tensor cycles per tile) must stay shorter than its mainloop.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = x * 0.70710678118654752f;
-  const float u = fminf(z * z, 3.4f * 3.4f);
-  float g = 2.409683474979829e-08f;
-  g = fmaf(g, u, -1.3351223060453776e-06f);
-  g = fmaf(g, u, 3.208911948604509e-05f);
-  g = fmaf(g, u, -0.00044352986151352525f);
-  g = fmaf(g, u, 0.003962765447795391f);
-  g = fmaf(g, u, -0.024541884660720825f);
-  g = fmaf(g, u, 0.11060382425785065f);
-  g = fmaf(g, u, -0.3752793073654175f);
-  g = fmaf(g, u, 1.1283255815505981f);
-  const float e = fmaxf(fminf(z * g, 1.0f), -1.0f);
-  const float hx = 0.5f * x;
-  return fmaf(hx, e, hx);
+// evaluated two elements per FMA-pipe issue slot (FMUL2 / FFMA2): 9.5 instead of 16 instructions per element
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  auto c2 = [](float c) { return f2_pack(c, c); };
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t z = f2_mul(x, c2(0.70710678118654752f));
+  float u0, u1;
+  f2_unpack(f2_mul(z, z), u0, u1);
+  const uint64_t u = f2_pack(fminf(u0, 3.4f * 3.4f), fminf(u1, 3.4f * 3.4f));
+  uint64_t g = f2_fma(c2(2.409683474979829e-08f), u, c2(-1.3351223060453776e-06f));
+  g = f2_fma(g, u, c2(3.208911948604509e-05f));
+  g = f2_fma(g, u, c2(-0.00044352986151352525f));
+  g = f2_fma(g, u, c2(0.003962765447795391f));
+  g = f2_fma(g, u, c2(-0.024541884660720825f));
+  g = f2_fma(g, u, c2(0.11060382425785065f));
+  g = f2_fma(g, u, c2(-0.3752793073654175f));
+  g = f2_fma(g, u, c2(1.1283255815505981f));
+  float e0, e1;
+  f2_unpack(f2_mul(z, g), e0, e1);
+  const uint64_t e = f2_pack(fmaxf(fminf(e0, 1.0f), -1.0f), fmaxf(fminf(e1, 1.0f), -1.0f));
+  const uint64_t hx = f2_mul(x, c2(0.5f));
+  f2_unpack(f2_fma(hx, e, hx), x0, x1);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
@@ -316,7 +322,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             if constexpr (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+              for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
             }
             if constexpr (kResid) {
               if (h == 0) {
