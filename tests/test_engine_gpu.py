@@ -498,3 +498,74 @@ def test_random_arrivals_cancellations_never_leak_pages_and_stay_deterministic()
         for i in range(n):
             if i not in cancelled:
                 assert len(outs[i]) == max_new[i]
+
+
+def test_churn_with_chunked_prefill_prefix_cache_and_sampling_filters():
+    """Everything at once: a 96-token step budget (most prompts are chunked), the prefix cache on with prompts drawn
+    from three shared prefixes (hits, shared pages held by several sequences, evictions in a small pool), random
+    cancellations (also of half-prefilled prompts), a mix of greedy / temperature / top-k / top-p requests.
+    Afterwards no page is leaked, every uncancelled request has its full length and greedy ones agree with the oracle;
+    a second pass over the same requests (now mostly prefix hits) must satisfy the same."""
+    d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000)
+    sd = weights.llama_state_dict(d, 17, 0.05)
+    oracle = LlamaOracle(d, sd)
+    rng = np.random.default_rng(3)
+    prefixes = [weights.random_tokens(700 + i, 130 + 40 * i, d.vocab) for i in range(3)]
+    n = 30
+    prompts, samp = [], []
+    for i in range(n):
+        tail = weights.random_tokens(800 + i, int(rng.integers(1, 120)), d.vocab)
+        prompts.append(np.concatenate([prefixes[i % 3], tail]) if i % 4 else tail)
+        kind = i % 4
+        m = int(rng.integers(2, 20))
+        samp.append([hb.Sampling(max_tokens=m), hb.Sampling(max_tokens=m, temperature=0.8, seed=i),
+                     hb.Sampling(max_tokens=m, temperature=1.1, seed=i, top_k=5),
+                     hb.Sampling(max_tokens=m, temperature=0.9, seed=i, top_p=0.6)][kind])
+
+    def run(e, cancel_some):
+        rids, outs, done, cancelled = {}, {}, set(), set()
+        submitted, steps = 0, 0
+        total = e.stats()["kv_pages_total"]
+        while len(done) < n:
+            while submitted < n and rng.random() < 0.5:
+                rids[submitted] = e.submit(prompts[submitted], samp[submitted])
+                outs[submitted] = []
+                submitted += 1
+            e.step()
+            steps += 1
+            st = e.stats()
+            assert st["running"] <= 4 and 0 <= st["kv_pages_free"] <= total
+            for i, r in list(rids.items()):
+                if i in done:
+                    continue
+                if cancel_some and i % 5 == 2 and i not in cancelled and rng.random() < 0.25:
+                    e.cancel(r)
+                    cancelled.add(i)
+                t, fin = e.poll(r)
+                outs[i] += t
+                if fin:
+                    done.add(i)
+            assert steps < 5000
+        for _ in range(3):
+            e.step()
+        st = e.stats()
+        assert st["kv_pages_free"] == total and st["running"] == 0 and st["waiting"] == 0
+        for r in rids.values():
+            e.release(r)
+        return outs, cancelled
+
+    with hb.Engine(hb.EngineConfig(max_seqs=4, max_ctx=512, max_batched_tokens=96, use_cuda_graphs=1,
+                                   enable_prefix_cache=1)) as e:
+        e.load_state_dict(d, sd)
+        outs1, cancelled = run(e, True)
+        hits1 = e.stats()["prefix_hit_tokens"]
+        outs2, _ = run(e, False)
+        assert e.stats()["prefix_hit_tokens"] > hits1 > 0
+    for i in range(n):
+        assert len(outs2[i]) == samp[i].max_tokens
+        if i not in cancelled:
+            assert len(outs1[i]) == samp[i].max_tokens
+        if i % 4 == 0:
+            check_greedy(oracle, prompts[i], outs2[i])
+            if i not in cancelled:
+                check_greedy(oracle, prompts[i], outs1[i])
