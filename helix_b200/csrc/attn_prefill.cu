@@ -18,7 +18,7 @@ namespace {
 constexpr int BQ = 128;     // q rows per softmax warpgroup
 constexpr int QPAIR = 256;  // q rows per CTA: two q tiles ping-pong on the tensor pipe
 constexpr int BKV = 64;     // kv positions per tile (= one KV page)
-constexpr int kThreads = 320;
+constexpr int kThreads = 352;  // producer warp, one MMA issuer warp per q tile, two softmax warpgroups
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -49,6 +49,21 @@ __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
   const uint32_t r1 = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
   return f2_pack(__uint_as_float(r0), __uint_as_float(r1));
 }
+
+// Optional event trace (tools/attn_test -DHB_ATTN_TRACE): CTA 0 stamps clock64() at the hand-off points of q tile 0.
+#ifdef HB_ATTN_TRACE
+__device__ unsigned long long g_attn_trace[8][4096];
+__device__ int g_attn_trace_n[8];
+#define HB_TRACE(ev)                                                          \
+  do {                                                                        \
+    if (blockIdx.x == 0) {                                                    \
+      const int i_ = g_attn_trace_n[ev];                                      \
+      if (i_ < 4096) { g_attn_trace[ev][i_] = clock64(); g_attn_trace_n[ev] = i_ + 1; } \
+    }                                                                         \
+  } while (0)
+#else
+#define HB_TRACE(ev) do {} while (0)
+#endif
 
 template <int D>
 struct ACfg {
@@ -143,7 +158,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
     mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    mbar_init(q_empty, 2);  // both issuers
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
@@ -152,9 +167,9 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     for (int i = 0; i < 2; ++i) mbar_init(&o_free[i], 4);
     for (int i = 0; i < KST; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], 2);  // released by both issuers
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], 2);
     }
     fence_barrier_init();
   }
@@ -221,109 +236,106 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    // The issuer's own instruction stream is on the critical path (one warp, ~4 cycles per dependent instruction: the
-    // first version of this loop ran 508 SASS instructions per kv tile and took 2100 cycles for 1024 cycles of MMA work),
-    // so: descriptors are a per-kernel base plus a constant (the 14-bit address field never carries), ring slots and
-    // phases are running counters, and the steady state (both q tiles have a PV(j) and an S(j+2) to issue) is a
-    // branch-free instantiation; everything else goes through the flag-driven one.
+  } else if (warp == 1 || warp == 2) {
+    // One MMA issuer warp PER q tile.  With a single in-order issuer for both tiles (PV0 S0 PV1 S1 ...) the event trace
+    // (tools/attn_test -DHB_ATTN_TRACE) showed P0(j) sitting ~900 cycles before the issuer looked at it — it was blocked
+    // on the other warpgroup's P — so S0(j+2) was issued only ~600 cycles before the softmax needed it and the second S
+    // buffer bought nothing.  The two chains are independent except for the K/V ring slots, which are released by both
+    // (empty barriers count 2; a tile one issuer does not need is released by a plain arrive once it has landed).
+    // The issuer's own instruction stream is on the critical path (one warp, ~4 cycles per dependent instruction), so:
+    // descriptors are a per-kernel base plus a constant (the 14-bit address field never carries), ring slots and phases
+    // are running counters, and the steady state is a branch-free instantiation.
+    const int t = warp - 1;
     const bool leader = elect_one_sync();
     constexpr uint32_t idesc_qk = umma_idesc_bf16(BQ, BKV, 0, 0);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, D, 0, 1);  // A = P from TMEM, B = V is MN-major
-    const uint64_t qdesc[2] = {umma_desc_kmajor_sw128(smem_u32(sQ)), umma_desc_kmajor_sw128(smem_u32(sQ + C::Q_BYTES))};
+    const uint64_t qdesc = umma_desc_kmajor_sw128(smem_u32(sQ + t * C::Q_BYTES));
     const uint64_t kdesc0 = umma_desc_kmajor_sw128(smem_u32(sK));
     const uint64_t vdesc0 = umma_desc_mnmajor_sw128(smem_u32(sV), BKV * 128, 1024);
-    int kslot = 0, vslot = 0;         // ring slots of the next K / V tile to consume
+    const uint32_t tmem_s = tmem_base + t * 128, tmem_o = tmem_base + 256 + t * 128;
+    uint64_t* const my_s_full = s_full + t * 2;
+    uint64_t* const my_p_full = p_full + t * 2;
+    uint64_t* const my_pv_done = pv_done + t * 2;
+    int kslot = 0, vslot = 0;  // ring slots of the next K / V tile (this issuer walks ALL tiles of an item)
     uint32_t kphase = 0, vphase = 0;
-    int ps[2] = {0, 0};               // absolute index (over the kernel's life) of q tile t's next PV; S buffer = index & 1
-    int oi[2] = {0, 0};               // items processed so far per q tile (phase of o_free)
-    int qi = 0;
-    // S_t(tile x) = Q_t · Kᵀ (K in ring slot kslot) into buffer x & 1
-    auto mma_s = [&](int t, int x) {
-      const uint32_t d_tmem = tmem_base + t * 128 + (x & 1) * BKV;
+    int ps = 0;                // absolute index (over the kernel's life) of this q tile's next PV; S buffer = index & 1
+    int oi = 0, qi = 0;        // items with work for this q tile (phase of o_free) / items seen (phase of q_full)
+    // S(tile x) = Q_t · Kᵀ (K in ring slot kslot) into buffer x & 1
+    auto mma_s = [&](int x) {
+      const uint32_t d_tmem = tmem_s + (x & 1) * BKV;
       const uint64_t kd = kdesc0 + (uint64_t)(kslot * (C::KV_BYTES >> 4));
 #pragma unroll
       for (int k = 0; k < D / 16; ++k)
-        umma_f16_ss(d_tmem, qdesc[t] + (((k >> 2) * (BQ * 128) + (k & 3) * 32) >> 4),
+        umma_f16_ss(d_tmem, qdesc + (((k >> 2) * (BQ * 128) + (k & 3) * 32) >> 4),
                     kd + (((k >> 2) * (BKV * 128) + (k & 3) * 32) >> 4), idesc_qk, k != 0 ? 1u : 0u);
-      umma_commit(&s_full[t * 2 + (x & 1)]);
+      umma_commit(&my_s_full[x & 1]);
+      umma_commit(&k_empty[kslot]);
     };
-    // O_t (+)= P_t(tile x) · V (V in ring slot vslot)
-    auto mma_pv = [&](int t, int x, uint32_t acc) {
-      const uint32_t p_tmem = tmem_base + t * 128 + (x & 1) * BKV;
+    // O_t (+)= P(tile x) · V (V in ring slot vslot)
+    auto mma_pv = [&](int x, uint32_t acc) {
+      const uint32_t p_tmem = tmem_s + (x & 1) * BKV;
       const uint64_t vd = vdesc0 + (uint64_t)(vslot * (C::KV_BYTES >> 4));
 #pragma unroll
       for (int k = 0; k < BKV / 16; ++k)
-        umma_f16_ts(tmem_base + 256 + t * 128, p_tmem + k * 8, vd + ((k * 16 * 128) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
-      umma_commit(&pv_done[t * 2 + (x & 1)]);
+        umma_f16_ts(tmem_o, p_tmem + k * 8, vd + ((k * 16 * 128) >> 4), idesc_pv, (acc | k) != 0 ? 1u : 0u);
+      umma_commit(&my_pv_done[x & 1]);
+      umma_commit(&v_empty[vslot]);
     };
     auto k_advance = [&]() { if (++kslot == KST) { kslot = 0; kphase ^= 1; } };
     auto v_advance = [&]() { if (++vslot == KST) { vslot = 0; vphase ^= 1; } };
-    // one kv tile j: PV_t(j) for the q tiles that have one, S_t(j+2) for those that have one
-    auto step = [&](auto fast_tag, bool pv0, bool s0, bool pv1, bool s1, bool first, bool last_s) {
+    // one kv tile j of the item: PV(j) if this q tile has one, S(j+2) if it has one; slots it does not use are released
+    auto step = [&](auto fast_tag, bool has_pv, bool has_k, bool has_s, bool first, bool last_s) {
       constexpr bool FAST = decltype(fast_tag)::value;
-      const bool has_k = FAST || s0 || s1;
       mbar_wait(&v_full[vslot], vphase);
-      if (has_k) mbar_wait(&k_full[kslot], kphase);
-      if (FAST || pv0) {
-        if (!FAST && first) mbar_wait(&o_free[0], (oi[0] & 1) ^ 1);  // the previous item's O_0 has been read out
-        mbar_wait(&p_full[ps[0] & 1], (ps[0] >> 1) & 1);
+      if (FAST || has_k) mbar_wait(&k_full[kslot], kphase);
+      if (FAST || has_pv) {
+        if (!FAST && first) mbar_wait(&o_free[t], (oi & 1) ^ 1);  // the previous item's O_t has been read out
+        mbar_wait(&my_p_full[ps & 1], (ps >> 1) & 1);
         tc_fence_after();
+        if (t == 0 && leader) HB_TRACE(0);  // issuer saw P0(j)
         if (leader) {
-          mma_pv(0, ps[0], FAST ? 1u : (first ? 0u : 1u));
-          if (FAST || s0) mma_s(0, ps[0]);  // S0(j+2) reuses the buffer PV0(j) reads: same-thread MMAs retire in order
+          mma_pv(ps, FAST ? 1u : (first ? 0u : 1u));
+          if (FAST || has_s) mma_s(ps);  // S(j+2) reuses the buffer PV(j) reads: same-thread MMAs retire in order
+          if (!FAST && last_s) umma_commit(q_empty);  // that was this q tile's last S MMA of the item
         }
-        ++ps[0];
-      }
-      if (FAST || pv1) {
-        if (!FAST && first) mbar_wait(&o_free[1], (oi[1] & 1) ^ 1);
-        mbar_wait(&p_full[2 + (ps[1] & 1)], (ps[1] >> 1) & 1);
-        tc_fence_after();
-        if (leader) {
-          mma_pv(1, ps[1], FAST ? 1u : (first ? 0u : 1u));
-          umma_commit(&v_empty[vslot]);
-          if (FAST || s1) mma_s(1, ps[1]);
-          if (has_k) umma_commit(&k_empty[kslot]);
-          if (!FAST && last_s) umma_commit(q_empty);  // that was the item's last S MMA: Q may be overwritten
-        }
-        ++ps[1];
+        if (t == 0 && leader) HB_TRACE(1);  // PV0(j), S0(j+2) issued
+        ++ps;
       } else if (leader) {
-        umma_commit(&v_empty[vslot]);
-        if (has_k) umma_commit(&k_empty[kslot]);
-        if (last_s) umma_commit(q_empty);
+        mbar_arrive(&v_empty[vslot]);
       }
+      if (!FAST && has_k && !has_s && leader) mbar_arrive(&k_empty[kslot]);
       v_advance();
-      if (has_k) k_advance();
+      if (FAST || has_k) k_advance();
     };
     for (int idx = blockIdx.x; idx < num_items; idx += gridDim.x) {
       const Item it = get_item(idx);
       if (!it.valid) continue;
-      const int n0 = it.n0, n1 = it.n1, n = it.n;
+      const int nt = t == 0 ? it.n0 : it.n1, n = it.n;
       mbar_wait(q_full, qi & 1);
-      // S(0), S(1) of both q tiles: their buffers are free — the PVs that read them were issued earlier
+      // S(0), S(1): their buffers are free — the PVs that read them were issued earlier by this same thread
       for (int j = 0; j < 2 && j < n; ++j) {
         mbar_wait(&k_full[kslot], kphase);
         tc_fence_after();
         if (leader) {
-          if (j < n0) mma_s(0, ps[0] + j);
-          if (j < n1) mma_s(1, ps[1] + j);
-          umma_commit(&k_empty[kslot]);
-          if (j + 1 == n || (j == 1 && n == 2)) umma_commit(q_empty);
+          if (j < nt) mma_s(ps + j); else mbar_arrive(&k_empty[kslot]);
         }
         k_advance();
       }
-      for (int j = 0; j < n; ++j) {
-        if (j > 0 && j + 3 < n0 && j + 3 < n1)
-          step(std::true_type{}, true, true, true, true, false, false);
-        else
-          step(std::false_type{}, j < n0, j + 2 < n0, j < n1, j + 2 < n1, j == 0, j + 3 == n);
+      if (leader) {
+        if (nt == 0) mbar_arrive(q_empty);
+        else if (nt <= 2) umma_commit(q_empty);
       }
-      oi[0] += n0 > 0;
-      oi[1] += n1 > 0;
+      for (int j = 0; j < n; ++j) {
+        if (j > 0 && j + 3 < nt)
+          step(std::true_type{}, true, true, true, false, false);
+        else
+          step(std::false_type{}, j < nt, j + 2 < n, j + 2 < nt, j == 0, j + 3 == nt);
+      }
+      oi += nt > 0;
       ++qi;
     }
   } else {
-    const int t = (warp - 2) >> 2;  // q tile of this warpgroup
+    const int t = (warp - 3) >> 2;  // q tile of this warpgroup
     const int qd = warp & 3;
     const int r = qd * 32 + lane;  // q row in tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
@@ -342,8 +354,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       for (int j = 0; j < nt; ++j) {
         const int tile = jt + j;
         const uint32_t tS = tmem_base + lane_sel + t * 128 + (tile & 1) * BKV;
+        if (t == 0 && warp == 3 && lane == 0) HB_TRACE(2);  // softmax 0 starts waiting for S0(j)
         mbar_wait(&s_full[t * 2 + (tile & 1)], (tile >> 1) & 1);
         tc_fence_after();
+        if (t == 0 && warp == 3 && lane == 0) HB_TRACE(3);  // got S0(j)
         const int kv0 = j * BKV;
         const bool need_mask = (kv0 + BKV > len) || (causal && (kv0 + BKV - 1 > qt0));
         const int lim = causal ? min(len - 1, qpos) : len - 1;  // last valid kv position for this row
@@ -391,6 +405,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         // ---- p = exp2(s*scale - m) (masked entries are -inf -> 0), row sum, P (bf16x2) written over the S buffer's head.
         //      POLY of every 8 column pairs take the FMA-pipe exp2, the rest the SFU; scale/subtract and the sum are packed
+        if (t == 0 && warp == 3 && lane == 0) HB_TRACE(4);  // loaded, max, rescale decision done
         const uint64_t scale2 = f2_pack(scale_log2, scale_log2), negm2 = f2_pack(-m_used, -m_used);
         uint64_t sum2a = 0, sum2b = 0;
 #pragma unroll
@@ -420,10 +435,12 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           f2_unpack(f2_add(sum2a, sum2b), s0, s1);
           l += s0 + s1;
         }
+        if (t == 0 && warp == 3 && lane == 0) HB_TRACE(5);  // exp loop done, P stores issued
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t * 2 + (tile & 1)]);
+        if (t == 0 && warp == 3 && lane == 0) HB_TRACE(6);  // P0(j) handed over
       }
       // ---- item epilogue: O / l -> global, then hand O_t back to the MMA issuer
       mbar_wait(&pv_done[t * 2 + ((jt + nt - 1) & 1)], ((jt + nt - 1) >> 1) & 1);
@@ -530,7 +547,8 @@ int poly_pairs(int D) {
     env = s ? atoi(s) : -1;
   }
   if (env >= 0) return env;
-  return D == 64 ? 2 : 0;  // measured on B200 (64-wide kv tiles): D=64 494 / 467 / 486 TFLOP/s at 2 / 0 / 4 of 8, D=128 1085 / 1114 / 1090
+  (void)D;
+  return 2;  // measured on B200 (two issuers, 64-wide kv tiles), 0 / 2 / 4 of 8: D=128 1107 / 1171 / 1139, D=64 476 / 501 / 489 TFLOP/s
 }
 template <int D, bool PAGED>
 cudaError_t launch(cudaStream_t stream, const AttnPrefillArgs& a) {
@@ -569,6 +587,20 @@ cudaError_t attn_prefill(cudaStream_t stream, const AttnPrefillArgs& a) {
   if (a.D == 64) return launch<64, false>(stream, a);
   return cudaErrorInvalidValue;
 }
+
+#ifdef HB_ATTN_TRACE
+void attn_trace_dump() {
+  static unsigned long long h[8][4096];
+  int n[8];
+  cudaMemcpyFromSymbol(h, g_attn_trace, sizeof(h));
+  cudaMemcpyFromSymbol(n, g_attn_trace_n, sizeof(n));
+  for (int e = 0; e < 7; ++e) {
+    printf("TRACE %d %d:", e, n[e]);
+    for (int i = 0; i < n[e] && i < 400; ++i) printf(" %llu", h[e][i] - h[2][0]);
+    printf("\n");
+  }
+}
+#endif
 
 cudaError_t attn_naive_check(cudaStream_t stream, const AttnPrefillArgs& a, float* out_f32) {
   dim3 grid((a.max_seqlen + 63) / 64, a.Hq, a.B);

@@ -9,6 +9,9 @@
 
 #include "../helix_b200/csrc/kernels.h"
 using namespace hb;
+#ifdef HB_ATTN_TRACE
+namespace hb { void attn_trace_dump(); }
+#endif
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(2); } } while (0)
 
 int main(int argc, char** argv) {
@@ -28,6 +31,12 @@ int main(int argc, char** argv) {
   AttnPrefillArgs a{};
   a.q = qkv; a.ldq = ld; a.k = qkv + Hq * D; a.ldk = ld; a.v = qkv + (Hq + Hkv) * D; a.ldv = ld; a.out = out; a.ldo = Hq * D;
   a.cu_seqlens = cu; a.B = B; a.T = T; a.max_seqlen = S; a.Hq = Hq; a.Hkv = Hkv; a.D = D; a.causal = causal; a.scale = 1.0f / sqrtf((float)D);
+#ifdef HB_ATTN_TRACE
+  CK(attn_prefill(0, a));
+  CK(cudaDeviceSynchronize());
+  attn_trace_dump();
+  return 0;
+#endif
   for (int i = 0; i < 3; ++i) CK(attn_prefill(0, a));
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
