@@ -150,12 +150,17 @@ def bench_bge(args):
     e.load_random(desc, 2)
     n, L = args.chunks, 512
     rng = np.random.default_rng(2)
-    toks = rng.integers(0, desc.vocab, size=n * L, dtype=np.int64).astype(np.int32)
-    offs = (np.arange(n + 1, dtype=np.int64) * L).astype(np.int32)
+    if args.ragged:  # SURVEY.md §8d config 3, varlen variant: chunk lengths U[64, 512]
+        lens = rng.integers(64, L + 1, size=n)
+    else:
+        lens = np.full(n, L)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    total_tokens = int(offs[-1])
+    toks = rng.integers(0, desc.vocab, size=total_tokens, dtype=np.int64).astype(np.int32)
     out = np.empty((n, desc.hidden), np.float32)
     warm = min(n, 2048)
     for _ in range(max(1, args.warmup)):
-        e.embed_flat(toks[:warm * L], offs[:warm + 1], out[:warm])
+        e.embed_flat(toks[:offs[warm]], offs[:warm + 1], out[:warm])
     torch.cuda.synchronize()
     s0 = e.stats()
     t0 = time.perf_counter()
@@ -168,7 +173,7 @@ def bench_bge(args):
     e.set_profile(True)
     p0 = e.stats()
     sub = min(n, 8192)
-    e.embed_flat(toks[:sub * L], offs[:sub + 1], out[:sub])
+    e.embed_flat(toks[:offs[sub]], offs[:sub + 1], out[:sub])
     p1 = e.stats()
     e.set_profile(False)
     fam = {}
@@ -177,15 +182,17 @@ def bench_bge(args):
         w = p1["prof_work"][i] - p0["prof_work"][i]
         fam[name] = {"ms": ms, "launches": p1["prof_launches"][i] - p0["prof_launches"][i],
                      "tflops" if i < 2 else "gbs": (w / (ms * 1e-3) / (1e12 if i < 2 else 1e9)) if ms else 0.0}
-    flops = n * L * 188.8e6
+    # GEMMs 169.9 MFLOP/token + bidirectional attention 4*len*768 FLOP/token
+    flops = float(total_tokens) * 169.9e6 + float((lens.astype(np.float64) ** 2).sum()) * 4 * 768
     peaks = measured_peaks()
     line = {"metric": "chunks/sec bge-base-en-shaped batch encode (512-token chunks)", "value": n / dev, "unit": "chunks/s",
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"bge-base-en shape random-init, {n} chunks x 512 tokens, CLS+L2, fp32 out"},
+            "config": {"workload": f"bge-base-en shape random-init, {n} chunks x " + ("U[64,512]" if args.ragged else "512") +
+                       " tokens, CLS+L2, fp32 out"},
             "e2e": {"value": n / wall, "unit": "chunks/s", "h2d_bytes_per_step": int(toks.nbytes * 2), "d2h_bytes_per_step": int(out.nbytes)},
             "model_tflops": flops / dev / 1e12, "frac_of_measured_sustained": flops / dev / 1e12 / peaks["bf16_tflops_sustained"],
-            "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]), "tokens_per_s": n * L / dev,
+            "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]), "tokens_per_s": total_tokens / dev,
             "kernels_profiled_subset": fam, "finite": bool(np.isfinite(out).all()), "unit_norm_err": float(np.abs(np.linalg.norm(out, axis=1) - 1).max())}
     print(json.dumps(line), flush=True)
     e.close()
@@ -262,6 +269,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug: truncate the model (INVALID as a bench number)")
     ap.add_argument("--workload", default="llama8b", choices=["llama8b", "bge"])
     ap.add_argument("--chunks", type=int, default=100000)
+    ap.add_argument("--ragged", action="store_true", help="bge workload: chunk lengths U[64,512] instead of 512")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                    const bf16* __restrict__ q, int ldq, const int32_t* __restrict__ page_table, int max_pages,
                    const int32_t* __restrict__ ctx_lens, float* __restrict__ ws, int Hkv, int num_splits,
-                   float scale_log2) {
+                   float scale_log2, bf16* __restrict__ out_direct, int ldo) {
   using C = DCfg<D>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -300,13 +300,24 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
     uint32_t o[16];
     tmem_ld_32x32b_x16(tmem_O + lane_sel, o);
     tmem_ld_wait();
-    if (t < D) {
+    if (out_direct != nullptr) {  // single split: this CTA saw the whole context — normalise and store, no combine pass
+      if (t < D) {
 #pragma unroll
-      for (int g = 0; g < G; ++g) ws_base[g * (D + 2) + t] = __uint_as_float(o[g]);
-    }
-    if (t < G) {
-      ws_base[t * (D + 2) + D] = m_used[t];
-      ws_base[t * (D + 2) + D + 1] = redl[t] + redl[kMaxG + t] + redl[2 * kMaxG + t] + redl[3 * kMaxG + t];
+        for (int g = 0; g < G; ++g) {
+          const float lg = redl[g] + redl[kMaxG + g] + redl[2 * kMaxG + g] + redl[3 * kMaxG + g];
+          out_direct[(size_t)b * ldo + (size_t)(kvh * G + g) * D + t] =
+              __float2bfloat16(lg > 0.f ? __uint_as_float(o[g]) / lg : 0.f);
+        }
+      }
+    } else {
+      if (t < D) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) ws_base[g * (D + 2) + t] = __uint_as_float(o[g]);
+      }
+      if (t < G) {
+        ws_base[t * (D + 2) + D] = m_used[t];
+        ws_base[t * (D + 2) + D + 1] = redl[t] + redl[kMaxG + t] + redl[2 * kMaxG + t] + redl[3 * kMaxG + t];
+      }
     }
   }
   tc_fence_before();
@@ -356,10 +367,11 @@ cudaError_t launch(cudaStream_t stream, const AttnDecodeArgs& a) {
   if (!make_tmap_3d(&mk, a.k_cache, TM_BF16, D, PAGE, blocks, (uint64_t)D * 2, (uint64_t)PAGE * D * 2, 64, PAGE, 1)) return cudaErrorInvalidValue;
   if (!make_tmap_3d(&mv, a.v_cache, TM_BF16, D, PAGE, blocks, (uint64_t)D * 2, (uint64_t)PAGE * D * 2, 64, PAGE, 1)) return cudaErrorInvalidValue;
   dim3 grid(a.num_splits, a.Hkv, a.B);
+  bf16* direct = a.num_splits == 1 ? a.out : nullptr;  // one split per (sequence, kv head): no partials to merge
   cudaError_t e = launch_k(attn_decode_kernel<D, G>, grid, dim3(kThreads), DCfg<D>::SMEM, stream, true, mk, mv, a.q, a.ldq,
                            a.page_table, a.max_pages, a.ctx_lens, a.workspace, a.Hkv, a.num_splits,
-                           a.scale * 1.4426950408889634f);
-  if (e != cudaSuccess) return e;
+                           a.scale * 1.4426950408889634f, direct, a.ldo);
+  if (e != cudaSuccess || direct) return e;
   return launch_k(attn_decode_combine_kernel<D>, dim3(a.Hq, a.B), dim3(D / 2), 0, stream, true,
                   (const float*)a.workspace, a.out, a.ldo, a.Hq, a.Hkv, G, a.num_splits);
 }

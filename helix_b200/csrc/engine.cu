@@ -487,7 +487,7 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
       a.scale = 1.0f / sqrtf((float)D);
       a.num_pages = num_pages_;
       SPAN(2, attn_bytes_, attn_decode(stream_, a));
-      launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel
+      if (a.num_splits > 1) launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel
     }
     {
       GemmArgs g{attn_, QD, w.wo, QD, x_, H, x_, H, nullptr, T, H, QD, EPI_RESID, 0};
@@ -559,7 +559,7 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
       a.scale = 1.0f / sqrtf((float)D);
       a.num_pages = num_pages_;
       SPAN(2, attn_bytes_, attn_decode(stream_, a));
-      launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel
+      if (a.num_splits > 1) launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel
     }
     SPAN(4, wbytes(H, QD), gemm_skinny(stream_, plan_o_, attn_, QD, w.wo, QD, skinny_ws_, B, H, QD));
     SPAN(3, 3 * rowb, dec_resid_rmsnorm(stream_, skinny_ws_, plan_o_, x_, w.mlp_norm, xn_, B, H, d.norm_eps));
