@@ -113,6 +113,44 @@ class EmbedBatcher:
         self.thread.join(timeout=5)
 
 
+class StopMatcher:
+    """OpenAI `stop` (string or list of up to 4 strings): generation ends at the first occurrence and the stop text is
+    not returned.  Streaming: text that could still turn out to be the beginning of a stop string is held back."""
+
+    def __init__(self, stop):
+        if stop is None:
+            stop = []
+        if isinstance(stop, str):
+            stop = [stop]
+        self.stops = [s for s in stop if s]
+        self.hold = max((len(s) for s in self.stops), default=1) - 1
+        self.buf = ""
+        self.hit = False
+
+    def feed(self, text):
+        """Returns the text that may be emitted now."""
+        if self.hit:
+            return ""
+        if not self.stops:
+            return text
+        self.buf += text
+        cut = min((i for i in (self.buf.find(s) for s in self.stops) if i >= 0), default=-1)
+        if cut >= 0:
+            out, self.buf, self.hit = self.buf[:cut], "", True
+            return out
+        keep = 0  # longest suffix of buf that is a proper prefix of some stop string
+        for k in range(min(self.hold, len(self.buf)), 0, -1):
+            if any(s.startswith(self.buf[-k:]) for s in self.stops):
+                keep = k
+                break
+        out, self.buf = self.buf[:len(self.buf) - keep], self.buf[len(self.buf) - keep:]
+        return out
+
+    def flush(self):
+        out, self.buf = ("" if self.hit else self.buf), ""
+        return out
+
+
 def chat_chunk(cid, model, created, delta, finish_reason):
     return {"id": cid, "object": "chat.completion.chunk", "created": created, "model": model,
             "choices": [{"index": 0, "delta": delta, "finish_reason": finish_reason}]}
@@ -171,36 +209,46 @@ class OpenAIServer:
         cid, created, model = "chatcmpl-" + uuid.uuid4().hex[:24], int(time.time()), self.rt.p.model
         yield chat_chunk(cid, model, created, {"role": "assistant", "content": ""}, None)
         n, fin = 0, 0
+        stop = StopMatcher(body.get("stop"))
         try:
-            while not fin:
+            while not fin and not stop.hit:
                 eng.wait(rid, 30000)
                 toks, fin = eng.poll(rid)
                 if toks:
                     n += len(toks)
-                    text = self.tok.decode([t for t in toks if t != sp.eos_token])
+                    text = stop.feed(self.tok.decode([t for t in toks if t != sp.eos_token]))
                     if text:
                         yield chat_chunk(cid, model, created, {"content": text}, None)
-            reason = "length" if n >= sp.max_tokens else "stop"
-            yield chat_chunk(cid, model, created, {}, reason if fin == 1 else "stop")
+            tail = stop.flush()
+            if tail:
+                yield chat_chunk(cid, model, created, {"content": tail}, None)
+            reason = "stop" if (stop.hit or n < sp.max_tokens) else "length"
+            last = chat_chunk(cid, model, created, {}, reason if (fin == 1 or stop.hit) else "stop")
+            last["usage"] = {"prompt_tokens": n_prompt, "completion_tokens": n, "total_tokens": n_prompt + n}
+            yield last
         finally:
             try:
                 if not fin:
-                    eng.cancel(rid)      # client went away: free the sequence's KV pages
-                else:
-                    eng.release(rid)
+                    eng.cancel(rid)      # stop string hit or client went away: free the sequence's KV pages
+                    for _ in range(200):  # the step loop retires it at the next step boundary
+                        if eng.poll(rid)[1]:
+                            break
+                        eng.wait(rid, 10)
+                eng.release(rid)
             except HBError:
                 pass
 
     def chat(self, body):
-        text, reason, cid = "", "stop", None
+        text, reason, cid, usage = "", "stop", None, None
         for ch in self.chat_stream(body):
             cid = ch["id"]
             c = ch["choices"][0]
             text += c["delta"].get("content", "") or ""
             reason = c["finish_reason"] or reason
+            usage = ch.get("usage", usage)
         return {"id": cid, "object": "chat.completion", "created": int(time.time()), "model": self.rt.p.model,
                 "choices": [{"index": 0, "message": {"role": "assistant", "content": text}, "finish_reason": reason}],
-                "usage": {"prompt_tokens": 0, "completion_tokens": 0, "total_tokens": 0}}
+                "usage": usage or {"prompt_tokens": 0, "completion_tokens": 0, "total_tokens": 0}}
 
     # ---- socket plumbing
     def start(self):

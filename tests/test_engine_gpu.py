@@ -367,6 +367,15 @@ def test_runtime_lifecycle_and_openai_http_front():
         r = json.load(post("/v1/chat/completions", {"model": "tiny", "messages": [{"role": "user", "content": "hello"}],
                                                      "max_tokens": 6}))
         assert r["object"] == "chat.completion" and r["choices"][0]["finish_reason"] in ("stop", "length")
+        assert r["usage"]["completion_tokens"] == 6 and r["usage"]["prompt_tokens"] > 0
+        assert r["usage"]["total_tokens"] == r["usage"]["prompt_tokens"] + 6
+        # `stop`: the byte tokenizer's output is arbitrary text; take a piece of it as the stop string of a rerun
+        full = r["choices"][0]["message"]["content"]
+        if len(full) >= 3:
+            r2 = json.load(post("/v1/chat/completions", {"model": "tiny", "max_tokens": 6, "stop": [full[2:3]],
+                                                          "messages": [{"role": "user", "content": "hello"}]}))
+            assert r2["choices"][0]["message"]["content"] == full[:full.index(full[2:3])]
+            assert r2["choices"][0]["finish_reason"] == "stop"
         lines = [l for l in post("/v1/chat/completions", {"model": "tiny", "stream": True, "max_tokens": 5,
                                                           "messages": [{"role": "user", "content": "hello"}]}).read().decode().split("\n\n") if l]
         assert lines[-1] == "data: [DONE]" and all(l.startswith("data: ") for l in lines)

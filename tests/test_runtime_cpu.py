@@ -171,3 +171,24 @@ def test_hf_tokenizer_wrapper_and_llama3_chat_template(tmp_path):
     assert ids[0] == tk.token_to_id("<|begin_of_text|>") and w.EOS == tk.token_to_id("<|eot_id|>")
     assert tk.decode(ids, skip_special_tokens=False) == want
     assert w.decode(w.encode("hello world")) == "hello world"
+
+
+def test_stop_matcher_streaming_semantics():
+    """OpenAI `stop`: cut at the first occurrence, never emit the stop text, hold back text that may still become one."""
+    from helix_b200.server import StopMatcher
+    m = StopMatcher(None)
+    assert m.feed("abc") == "abc" and m.flush() == "" and not m.hit
+    m = StopMatcher("END")
+    out = [m.feed(t) for t in ["hello E", "N", "x EN", "D tail"]]
+    assert out == ["hello ", "", "ENx ", ""] and m.hit and m.flush() == ""
+    assert m.feed("more") == ""
+    m = StopMatcher(["\n\n", "###"])
+    assert m.feed("a\n") == "a" and m.feed("b#") == "\nb" and m.feed("#") == "" and m.flush() == "##" and not m.hit
+    m = StopMatcher(["\n\n", "###"])
+    assert "".join(m.feed(c) for c in "line one\n\nline two") == "line one" and m.hit
+    # every split of a text yields the same visible output
+    text, stops = "alpha <|eot|> beta <|eot|>", ["<|eot|>"]
+    for cut in range(len(text) + 1):
+        m = StopMatcher(stops)
+        got = m.feed(text[:cut]) + m.feed(text[cut:]) + m.flush()
+        assert got == "alpha ", (cut, got)
