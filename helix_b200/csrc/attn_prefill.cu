@@ -291,6 +291,10 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       if (FAST || has_pv) {
         if (!FAST && first) mbar_wait(&o_free[t], (oi & 1) ^ 1);  // the previous item's O_t has been read out
         mbar_wait(&my_p_full[ps & 1], (ps >> 1) & 1);
+        // P(ps) exists, so S(ps) and — issued before it — PV(ps-2) have completed: observe that pv_done phase here (it
+        // costs the issuer nothing) so that no phase of the barrier passes without a wait (compute-sanitizer synccheck);
+        // the softmax warps only wait on pv_done when they rescale O and at the end of an item
+        if (ps >= 2) mbar_wait(&my_pv_done[ps & 1], ((ps - 2) >> 1) & 1);
         tc_fence_after();
         if (t == 0 && leader) HB_TRACE(0);  // issuer saw P0(j)
         if (leader) {
