@@ -74,8 +74,12 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
   uint64_t* pv_done = bars + 2 * STAGES + 6;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 7);
 
+  // Programmatic dependent launch: only two things here depend on the kernel before this one (RoPE + KV write of the
+  // step's new token): q, and the LAST kv tile (it holds the new position).  Everything else — page table, context
+  // lengths (uploaded before the step), all older K/V pages — is immutable during the step, so the TMA ring is filled and
+  // the barriers / TMEM are set up while the predecessor is still draining; griddepcontrol.wait sits right in front of
+  // the first dependent access of each role.
   pdl_launch_dependents();
-  pdl_wait();
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ctx = ctx_lens[b];
@@ -86,6 +90,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
   const int t_end = min(n_tiles_total, t_begin + tps);
   float* ws_base = ws + ((size_t)(b * Hkv + kvh) * num_splits + split) * G * (D + 2);
   if (t_begin >= t_end) {
+    pdl_wait();  // ws may still be read by an earlier launch's combine pass
     for (int i = threadIdx.x; i < G * (D + 2); i += kThreads) ws_base[i] = (i % (D + 2) == D) ? -INFINITY : 0.f;
     return;
   }
@@ -126,6 +131,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
     {
       for (int j = 0; j < n_tiles; ++j) {
         const int pg0 = (t_begin + j) * 2;
+        if (t_begin + j == n_tiles_total - 1) pdl_wait();  // the tile with the step's new position
         // a tile's second page may not exist yet: re-load the first one (finite data, masked by the softmax)
         const int page_a = pt[pg0], page_b = pt[min(pg0 + 1, n_pages - 1)];
 #pragma unroll
@@ -195,6 +201,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
     const int t = qd * 32 + lane;  // kv position within the tile (S^T lane) / head-dim index (O^T lane)
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
     // ---- stage Q^T (G rows of D, rows G..15 zero) into the K-major swizzled B-operand layout; zero P
+    pdl_wait();  // q is written by the predecessor; so is nothing else this role reads
     {
       const bf16* qsrc = q + (size_t)b * ldq + (size_t)kvh * G * D;
       constexpr int CH = D / 8;  // 16-byte chunks per row
