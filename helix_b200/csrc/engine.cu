@@ -993,7 +993,8 @@ int Engine::step(int* did_work) {
       Request* r = waiting_.front();
       const int n = (int)r->prompt.size();
       if (r->pages.empty()) {
-        const int total = (n + r->sp.max_tokens + page_ - 1) / page_;
+        // positions never reach max_ctx (generation stops there), so a sequence never needs more than a full context of pages
+        const int total = std::min((n + r->sp.max_tokens + page_ - 1) / page_, max_pages_per_seq_);
         if ((int)(running_.size() + batch.size()) >= cfg_.max_seqs) break;
         // leading full pages already in the pool (always leave >= 1 prompt token to run: its logits seed the decode)
         std::vector<int32_t> hit;
