@@ -35,6 +35,30 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(_lib.SamplingC) == 40
 
 
+def test_ctypes_layouts_match_the_c_header_field_by_field(tmp_path):
+    """Compile the public header with gcc and compare sizeof / offsetof of every struct field with the ctypes mirror:
+    a cgo / ctypes binding is only as good as its struct layouts."""
+    import ctypes as C
+    import subprocess
+    structs = {"hb_engine_cfg": _lib.EngineCfg, "hb_model_desc": _lib.ModelDescC, "hb_sampling": _lib.SamplingC,
+               "hb_stats": _lib.StatsC}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "helix_b200.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == C.sizeof(ct), (cname, got[cname], C.sizeof(ct))
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, (cname, fname)
+
+
 def test_memory_estimate_matches_survey_numbers():
     est = hb.engine.memory_estimate(configs.llama3_8b(), hb.EngineConfig(max_seqs=32, max_ctx=2048))
     assert abs(est["weights"] - 16.06e9) < 0.02e9            # SURVEY.md §8a: 16.06 GB bf16
