@@ -52,6 +52,7 @@ func NewB200Runtime(_ context.Context, p B200RuntimeParams) (*B200Runtime, error
 	r.cfg.max_seqs = 256 // types/memory.go:11
 	r.cfg.kv_page_size = 64
 	r.cfg.use_cuda_graphs = 1
+	r.cfg.enable_prefix_cache = 1 // vLLM V1's default: Helix sessions resend the whole conversation every turn
 	if p.ContextLength > 0 {
 		r.cfg.max_ctx = C.int32_t(p.ContextLength)
 	}
@@ -65,9 +66,21 @@ func NewB200Runtime(_ context.Context, p B200RuntimeParams) (*B200Runtime, error
 			if v, err := strconv.Atoi(p.Args[i+1]); err == nil {
 				r.cfg.max_ctx = C.int32_t(v)
 			}
+		case "--max-num-batched-tokens":
+			if v, err := strconv.Atoi(p.Args[i+1]); err == nil {
+				r.cfg.max_batched_tokens = C.int32_t(v) // prefill step budget; longer prompts are chunked
+			}
 		case "--task":
 			r.embed = p.Args[i+1] == "embed"
 		}
+	}
+	for _, a := range p.Args {
+		if a == "--no-enable-prefix-caching" {
+			r.cfg.enable_prefix_cache = 0
+		}
+	}
+	if r.embed {
+		r.cfg.enable_prefix_cache = 0
 	}
 	return r, nil
 }
