@@ -1,0 +1,165 @@
+"""CPU: the OpenAI-compatible front (helix_b200/server.py) over real sockets, with a scripted stand-in for the engine —
+the wire behaviour the reference's runner depends on: SSE framing, a final chunk with a non-empty
+finish_reason, `data: [DONE]`, usage accounting, `stop`, request validation, embedding input forms and coalescing."""
+import json
+import threading
+import types
+import urllib.error
+import urllib.request
+
+import numpy as np
+import pytest
+
+from helix_b200.engine import HBError
+from helix_b200.server import ByteTokenizer, OpenAIServer
+
+
+class FakeEngine:
+    """Generates a fixed text, a few tokens per poll; records cancel/release calls."""
+
+    def __init__(self, text="Hello world!\n\nSecond paragraph."):
+        self.tok = ByteTokenizer()
+        self.script = [b + ByteTokenizer.OFFSET for b in text.encode()]
+        self.desc = types.SimpleNamespace(vocab=1000, hidden=8)
+        self.cfg = types.SimpleNamespace(max_ctx=64)
+        self.reqs, self.cancelled, self.released, self.embed_calls = {}, [], [], []
+        self.lock = threading.Lock()
+        self.next_id = 1
+
+    def submit(self, ids, sp):
+        with self.lock:
+            rid = self.next_id
+            self.next_id += 1
+            self.reqs[rid] = {"sp": sp, "pos": 0, "n_prompt": len(ids), "cancelled": False}
+        return rid
+
+    def wait(self, rid, timeout_ms):
+        return True
+
+    def poll(self, rid):
+        r = self.reqs[rid]
+        if r["cancelled"]:
+            return [], 2
+        n = min(3, r["sp"].max_tokens - r["pos"], len(self.script) - r["pos"])
+        toks = self.script[r["pos"]:r["pos"] + n]
+        r["pos"] += n
+        fin = 1 if (r["pos"] >= r["sp"].max_tokens or r["pos"] >= len(self.script)) else 0
+        return toks, fin
+
+    def cancel(self, rid):
+        self.reqs[rid]["cancelled"] = True
+        self.cancelled.append(rid)
+
+    def release(self, rid):
+        self.released.append(rid)
+
+    def embed(self, seqs):
+        self.embed_calls.append(len(seqs))
+        for s in seqs:
+            if len(s) == 0:
+                raise HBError(-1, "empty sequence")
+        return np.stack([np.full(8, float(len(s)), np.float32) for s in seqs])
+
+
+class FakeRuntime:
+    def __init__(self):
+        self.engine = FakeEngine()
+        self.p = types.SimpleNamespace(model="tiny")
+
+    def list_models(self):
+        return ["tiny"]
+
+    def status(self):
+        return "running"
+
+
+@pytest.fixture()
+def front():
+    rt = FakeRuntime()
+    srv = OpenAIServer(rt)
+    base = srv.start()
+    yield rt, base
+    srv.stop()
+
+
+def post(base, path, body, raw=False):
+    req = urllib.request.Request(base + path, json.dumps(body).encode(), {"Content-Type": "application/json"})
+    r = urllib.request.urlopen(req, timeout=20)
+    return r.read().decode() if raw else json.load(r)
+
+
+def test_models_and_health(front):
+    rt, base = front
+    assert json.load(urllib.request.urlopen(base + "/v1/models"))["data"][0]["id"] == "tiny"   # slot.go:606-624
+    assert json.load(urllib.request.urlopen(base + "/healthz"))["status"] == "running"
+
+
+def test_chat_json_usage_and_length(front):
+    rt, base = front
+    r = post(base, "/v1/chat/completions", {"model": "tiny", "messages": [{"role": "user", "content": "hi"}], "max_tokens": 5})
+    assert r["object"] == "chat.completion" and r["choices"][0]["message"]["content"] == "Hello"
+    assert r["choices"][0]["finish_reason"] == "length"
+    n_prompt = len(ByteTokenizer().chat([{"role": "user", "content": "hi"}]))
+    assert r["usage"] == {"prompt_tokens": n_prompt, "completion_tokens": 5, "total_tokens": n_prompt + 5}
+    assert rt.engine.released == [1] and rt.engine.cancelled == []
+
+
+def test_chat_stream_sse_framing(front):
+    rt, base = front
+    raw = post(base, "/v1/chat/completions", {"model": "tiny", "stream": True, "max_tokens": 200,
+                                              "messages": [{"role": "user", "content": "hi"}]}, raw=True)
+    events = [e for e in raw.split("\n\n") if e]
+    assert all(e.startswith("data: ") for e in events) and events[-1] == "data: [DONE]"
+    chunks = [json.loads(e[6:]) for e in events[:-1]]
+    assert chunks[0]["choices"][0]["delta"] == {"role": "assistant", "content": ""}
+    assert all(c["object"] == "chat.completion.chunk" and c["id"] == chunks[0]["id"] for c in chunks)
+    assert [c["choices"][0]["finish_reason"] for c in chunks[:-1]] == [None] * (len(chunks) - 1)
+    assert chunks[-1]["choices"][0]["finish_reason"] == "stop"       # closes the control-plane stream (helix_openai_client.go:197)
+    text = "".join(c["choices"][0]["delta"].get("content", "") for c in chunks)
+    assert text == "Hello world!\n\nSecond paragraph."
+    assert chunks[-1]["usage"]["completion_tokens"] == len(text.encode())
+
+
+def test_stop_sequence_cuts_and_cancels(front):
+    rt, base = front
+    r = post(base, "/v1/chat/completions", {"model": "tiny", "max_tokens": 200, "stop": ["\n\n"],
+                                            "messages": [{"role": "user", "content": "hi"}]})
+    assert r["choices"][0]["message"]["content"] == "Hello world!" and r["choices"][0]["finish_reason"] == "stop"
+    assert rt.engine.cancelled == [1] and rt.engine.released == [1]   # the sequence's KV pages are freed, the record released
+
+
+def test_request_validation(front):
+    rt, base = front
+    with pytest.raises(urllib.error.HTTPError) as e:
+        post(base, "/v1/chat/completions", {"model": "other", "messages": []})
+    assert e.value.code == 400 and "model mismatch" in json.load(e.value)["error"]["message"]   # openai_chat_handlers.go:44-50
+    with pytest.raises(urllib.error.HTTPError) as e:
+        post(base, "/v1/embeddings", {"model": "tiny", "input": 7})
+    assert e.value.code == 400
+    with pytest.raises(urllib.error.HTTPError) as e:
+        post(base, "/v1/nothing", {})
+    assert e.value.code == 404
+
+
+def test_embedding_input_forms_and_coalescing(front):
+    rt, base = front
+    one = post(base, "/v1/embeddings", {"model": "tiny", "input": "abc"})                 # string
+    many = post(base, "/v1/embeddings", {"model": "tiny", "input": ["a", "bcd"]})         # []string
+    ids = post(base, "/v1/embeddings", {"model": "tiny", "input": [[5, 6, 7], [8]]})      # [][]int (types/types.go:2707-2730)
+    flat = post(base, "/v1/embeddings", {"model": "tiny", "input": [5, 6, 7, 8]})         # []int = one sequence
+    assert [d["index"] for d in many["data"]] == [0, 1] and one["data"][0]["embedding"][0] == 4.0   # BOS + 3 bytes
+    assert [d["embedding"][0] for d in ids["data"]] == [3.0, 1.0] and flat["data"][0]["embedding"][0] == 4.0
+    assert ids["usage"] == {"prompt_tokens": 4, "total_tokens": 4}
+    # the RAG caller sends one chunk per request from 10 workers: the batcher turns them into few engine calls
+    before = len(rt.engine.embed_calls)
+    out = [None] * 10
+
+    def worker(i):
+        out[i] = post(base, "/v1/embeddings", {"model": "tiny", "input": "x" * (i + 1)})
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(10)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert [o["data"][0]["embedding"][0] for o in out] == [float(i + 2) for i in range(10)]
+    calls = rt.engine.embed_calls[before:]
+    assert sum(calls) == 10 and len(calls) <= 10
