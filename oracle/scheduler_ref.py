@@ -60,3 +60,87 @@ def pick_best_warm_slot(slots):
     slots: list of dicts {id, active, runner_load, last_activity}; returns the chosen id (deterministic part)."""
     best = min(slots, key=lambda s: (s["active"], s["runner_load"], -s["last_activity"]))
     return best["id"]
+
+
+# ---- allocation planning with eviction (single runner view) ------------------------------------------------------
+# Restatement of GlobalAllocator.PlanAllocation for one runner: api/pkg/scheduler/global_allocator.go:349-452 (single-GPU
+# plans), :455-549 (multi-GPU plans), :551-587 (cheapest plan wins), :589-660 (evictable = stale slots of OTHER
+# model/runtime/lora on that GPU, oldest first; evict the fewest that free enough), :667-707 (costs) and
+# api/pkg/scheduler/runner.go:658-746 (allocated bytes per GPU: whole model on its single GPU, model/n on each of n GPUs).
+# Everything is integer arithmetic on byte counts: the B200 runtime must fit what these plans promise, bit for bit.
+GIB = 1024 ** 3
+
+
+def allocated_per_gpu(slots):
+    """runner.go:658-746.  slots: dicts {id, model, runtime, lora, gpus: [int, ...], memory, stale, last_activity}."""
+    out = {}
+    for s in slots:
+        g = s["gpus"]
+        if len(g) > 1:
+            for i in g:
+                out[i] = out.get(i, 0) + s["memory"] // len(g)
+        elif len(g) == 1:
+            out[g[0]] = out.get(g[0], 0) + s["memory"]
+    return out
+
+
+def _evictable(slots, gpu, work):
+    same = lambda s: (s["model"], s["runtime"], s.get("lora", "")) == (work["model"], work["runtime"], work.get("lora", ""))
+    ev = [s for s in slots if not same(s) and gpu in s["gpus"] and s["stale"]]
+    return sorted(ev, key=lambda s: s["last_activity"])  # oldest first
+
+
+def _select_for_eviction(evictable, needed):
+    chosen, freed = [], 0
+    for s in evictable:
+        if freed >= needed:
+            break
+        chosen.append(s)
+        freed += s["memory"]
+    return chosen
+
+
+def plan_allocation(gpus, slots, work):
+    """gpus: [(index, total_bytes)] in runner order; work: {model, runtime, lora?, memory}.
+    Returns the cheapest plan {gpus, memory_per_gpu, evict: [slot ids], cost, multi} or None ("no viable allocation
+    plans")."""
+    need = work["memory"]
+    alloc = allocated_per_gpu(slots)
+    runner_penalty = sum(s["memory"] for s in slots) // GIB
+    plans = []
+    for idx, total in gpus:                                     # single-GPU plans
+        if need > total:
+            continue
+        free = total - alloc.get(idx, 0)
+        if free >= need:
+            plans.append({"gpus": [idx], "memory_per_gpu": need, "evict": [], "multi": False,
+                          "cost": (total - free) // GIB + runner_penalty})
+        else:
+            ev = _evictable(slots, idx, work)
+            if free + sum(s["memory"] for s in ev) >= need:
+                chosen = _select_for_eviction(ev, need - free)
+                plans.append({"gpus": [idx], "memory_per_gpu": need, "evict": [s["id"] for s in chosen], "multi": False,
+                              "cost": 100 * len(chosen) + (total - free) // GIB + runner_penalty})
+    for n in range(2, len(gpus) + 1):                           # multi-GPU plans: even split over the first n that fit
+        per = need // n
+        viable, evict, ok = [], [], True
+        for idx, total in gpus:
+            free = total - alloc.get(idx, 0)
+            if free >= per:
+                viable.append(idx)
+            else:
+                ev = _evictable(slots, idx, work)
+                if free + sum(s["memory"] for s in ev) >= per:
+                    evict += _select_for_eviction(ev, per - free)
+                    viable.append(idx)
+                else:
+                    ok = False
+                    break
+            if len(viable) >= n:
+                break
+        if ok and len(viable) >= n:
+            plans.append({"gpus": viable[:n], "memory_per_gpu": per, "evict": [s["id"] for s in evict], "multi": True,
+                          "cost": 100 * len(evict) + 1000 * n + runner_penalty})
+    if not plans:
+        return None
+    return min(enumerate(plans), key=lambda ip: (ip[1]["cost"], ip[0]))[1]   # stable: first of the cheapest

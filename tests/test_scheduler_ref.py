@@ -41,3 +41,55 @@ def test_single_gpu_fit_and_routing():
              {"id": "b", "active": 1, "runner_load": 9, "last_activity": 1},
              {"id": "c", "active": 1, "runner_load": 3, "last_activity": 0}]
     assert S.pick_best_warm_slot(slots) == "c"
+
+
+def _slot(i, model, gpus, mem_gb, stale=False, age=0):
+    return {"id": i, "model": model, "runtime": "vllm", "gpus": gpus, "memory": mem_gb * GB, "stale": stale,
+            "last_activity": -age}
+
+
+def test_overscheduling_prevention_scenario():
+    """api/pkg/scheduler/global_allocator_test.go:452-521: two 70 GB models must land on different 80 GB GPUs; a 200 GB
+    model fits nowhere, not even split ("no viable allocation plans")."""
+    gpus = [(0, 80 * GB), (1, 80 * GB)]
+    w70 = {"model": "medium-vllm:20b", "runtime": "vllm", "memory": 70 * GB}
+    p1 = S.plan_allocation(gpus, [], w70)
+    assert p1["gpus"] == [0] and not p1["evict"] and not p1["multi"]
+    slots = [_slot("s1", "medium-vllm:20b", p1["gpus"], 70)]
+    p2 = S.plan_allocation(gpus, slots, w70)
+    assert p2["gpus"] == [1] and not p2["evict"]
+    slots.append(_slot("s2", "medium-vllm:20b", p2["gpus"], 70))
+    assert S.plan_allocation(gpus, slots, {"model": "huge-vllm:200b", "runtime": "vllm", "memory": 200 * GB}) is None
+    assert S.allocated_per_gpu(slots) == {0: 70 * GB, 1: 70 * GB}
+    assert all(v <= 80 * GB for v in S.allocated_per_gpu(slots).values())
+
+
+def test_eviction_scenario():
+    """global_allocator_test.go:342-450: both GPUs hold a stale 70 GB slot; a 45 GB model needs exactly one eviction
+    (the oldest stale slot of the GPU the cheapest plan picks); slots of the SAME model are never evicted for it."""
+    gpus = [(0, 80 * GB), (1, 80 * GB)]
+    slots = [_slot("stale-1", "stale-model-1", [0], 70, stale=True, age=3600),
+             _slot("stale-2", "stale-model-2", [1], 70, stale=True, age=3600)]
+    plan = S.plan_allocation(gpus, slots, {"model": "medium-vllm:20b", "runtime": "vllm", "memory": 45 * GB})
+    assert plan is not None and len(plan["evict"]) == 1 and plan["evict"][0] in ("stale-1", "stale-2")
+    assert plan["gpus"] == [0] and plan["cost"] == 100 + 70 + 140          # eviction + used GB on the GPU + runner load GB
+    fresh = [_slot("a", "m1", [0], 70), _slot("b", "m2", [1], 70)]         # running, not stale: nothing may be evicted
+    assert S.plan_allocation(gpus, fresh, {"model": "x", "runtime": "vllm", "memory": 45 * GB}) is None
+    same = [_slot("a", "x", [0], 70, stale=True), _slot("b", "x", [1], 70, stale=True)]
+    assert S.plan_allocation(gpus, same, {"model": "x", "runtime": "vllm", "memory": 45 * GB}) is None
+
+
+def test_single_gpu_preferred_over_split_and_split_arithmetic():
+    """global_allocator.go:683-693: a multi-GPU plan carries +1000 per GPU, so it only wins when no single GPU can take
+    the model; the split is the integer quotient (runner.go:697-702 accounts it the same way)."""
+    gpus = [(i, 80 * GB) for i in range(4)]
+    p = S.plan_allocation(gpus, [], {"model": "m", "runtime": "vllm", "memory": 60 * GB})
+    assert p["gpus"] == [0] and not p["multi"]
+    p = S.plan_allocation(gpus, [], {"model": "big", "runtime": "vllm", "memory": 150 * GB + 1})
+    assert p["multi"] and p["gpus"] == [0, 1] and p["memory_per_gpu"] == (150 * GB + 1) // 2 and p["cost"] == 2000
+    slots = [_slot("s", "big", p["gpus"], 150)]
+    assert S.allocated_per_gpu(slots) == {0: 75 * GB, 1: 75 * GB}
+    # least-allocated GPU wins among single-GPU plans (cost = used GB after the runner penalty, equal for all)
+    slots = [_slot("a", "m1", [0], 30), _slot("b", "m2", [1], 10), _slot("c", "m3", [2], 20)]
+    assert S.plan_allocation(gpus, slots, {"model": "n", "runtime": "vllm", "memory": 20 * GB})["gpus"] == [3]
+    assert S.plan_allocation(gpus[:3], slots, {"model": "n", "runtime": "vllm", "memory": 20 * GB})["gpus"] == [1]
