@@ -5,11 +5,12 @@ rendering of this file.  Plug-in "Option A" of SURVEY.md §8b: the slot keeps `r
 and the scheduler's vLLM-style args arrive unchanged (`--gpu-memory-utilization`, `--max-num-seqs`,
 `--max-model-len`, `--task embed`; api/pkg/scheduler/runner.go:1187-1259,1344-1397).
 """
+import time
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional
 
 from . import configs
-from .engine import Engine, EngineConfig, HBError, ModelDesc, Sampling
+from .engine import Engine, EngineConfig, HBError, ModelDesc, Sampling, memory_estimate
 
 VERSION = "helix-b200/0.1 (abi 1)"
 DEFAULT_MAX_NUM_SEQS = 256  # types/memory.go:11 (vLLM default concurrency)
@@ -69,6 +70,42 @@ MODEL_CATALOGUE = {
     "meta-llama/Llama-3.2-1B-Instruct": (configs.llama32_1b, False),
     "BAAI/bge-base-en-v1.5": (configs.bge_base, True),
 }
+
+
+def memory_estimation(request: dict, runner_id: str = "", catalogue=None) -> dict:
+    """The runner's POST /memory-estimate for models served by this runtime (scope row F3).
+
+    The reference answers it by parsing a GGUF and calling Ollama's layer estimator for 1/2/4/8 synthetic 80 GB GPUs
+    (api/pkg/runner/memory_estimation_handlers.go:36-327; request/response: api/pkg/types/memory.go:16-50).  Here it is a
+    closed form — `hb_memory_estimate`: weight arena + max_seqs full contexts of paged KV + step workspace — and there is
+    one configuration, `single_gpu`: the runtime places a ModelInstance on one GPU (replicas, no tensor split), which is
+    also what the allocator prefers (multi-GPU plans cost +1000 per GPU, global_allocator.go:683-693).  `num_parallel`
+    is the slot's concurrency (--max-num-seqs); like the reference, KV is sized for num_parallel x context_length."""
+    t0 = time.time()
+    cat = catalogue or MODEL_CATALOGUE
+    name = request.get("model_name", "")
+    resp = {"success": False, "model_name": name, "model_path": "", "architecture": "", "block_count": 0,
+            "configurations": [], "response_time_ms": 0, "runner_id": runner_id}
+    if name not in cat:
+        resp["error"] = f"model {name} is not served by the B200 runtime"
+        return resp
+    desc = cat[name][0]()
+    ctx = int(request.get("context_length") or 0) or min(desc.max_pos, 8192)
+    par = int(request.get("num_parallel") or 0) or DEFAULT_MAX_NUM_SEQS
+    try:
+        est = memory_estimate(desc, EngineConfig(max_seqs=par, max_ctx=ctx,
+                                                 max_batched_tokens=int(request.get("batch_size") or 0) or 16384))
+    except HBError as e:
+        resp["error"] = str(e)
+        return resp
+    total = est["weights"] + est["kv"] + est["workspace"]
+    resp.update(success=True, architecture="llama" if desc.arch == 0 else "bert", block_count=desc.layers,
+                configurations=[{"name": "single_gpu", "gpu_count": 1, "gpu_sizes": [total], "total_memory": total,
+                                 "vram_required": total, "weights_memory": est["weights"], "kv_cache": est["kv"],
+                                 "graph_memory": est["workspace"], "tensor_split": "", "layers_on_gpu": desc.layers + 1,
+                                 "total_layers": desc.layers + 1, "fully_loaded": True}],
+                response_time_ms=int((time.time() - t0) * 1000))
+    return resp
 
 
 @dataclass

@@ -192,3 +192,30 @@ def test_stop_matcher_streaming_semantics():
         m = StopMatcher(stops)
         got = m.feed(text[:cut]) + m.feed(text[cut:]) + m.flush()
         assert got == "alpha ", (cut, got)
+
+
+def test_memory_estimation_endpoint_shape_and_numbers():
+    """POST /memory-estimate for this runtime (api/pkg/types/memory.go:16-50): closed form, one `single_gpu` plan whose
+    total is what the engine will actually allocate and what the allocator packs with."""
+    r = R.memory_estimation({"model_name": "meta-llama/Meta-Llama-3-8B-Instruct", "context_length": 2048,
+                             "batch_size": 16384, "num_parallel": 32}, runner_id="r1")
+    assert r["success"] and r["runner_id"] == "r1" and r["architecture"] == "llama" and r["block_count"] == 32
+    (c,) = r["configurations"]
+    assert c["name"] == "single_gpu" and c["gpu_count"] == 1 and c["fully_loaded"] and c["total_layers"] == 33
+    assert abs(c["weights_memory"] - 16.06e9) < 0.02e9 and c["kv_cache"] == 32 * 2048 * 131072   # SURVEY.md §8a/§8d
+    assert c["vram_required"] == c["total_memory"] == c["weights_memory"] + c["kv_cache"] + c["graph_memory"]
+    assert c["gpu_sizes"] == [c["total_memory"]]
+    # the scheduler packs with this number: two such instances plus the 1B model fit a 180 GB B200, a fourth 8B does not
+    from oracle import scheduler_ref as S
+    need = c["total_memory"]
+    small = R.memory_estimation({"model_name": "meta-llama/Llama-3.2-1B-Instruct", "context_length": 2048, "num_parallel": 32})
+    slots = [{"id": i, "model": f"m{i}", "runtime": "vllm", "gpus": [0], "memory": need, "stale": False, "last_activity": 0}
+             for i in range(2)]
+    gpus = [(0, 180 * 10 ** 9)]
+    assert S.plan_allocation(gpus, slots, {"model": "s", "runtime": "vllm", "memory": small["configurations"][0]["total_memory"]})
+    many = slots + [dict(slots[0], id=9, model="m9")] * 6
+    assert S.plan_allocation(gpus, many, {"model": "x", "runtime": "vllm", "memory": need}) is None
+    bad = R.memory_estimation({"model_name": "unknown/model"})
+    assert not bad["success"] and "not served" in bad["error"] and bad["configurations"] == []
+    emb = R.memory_estimation({"model_name": "BAAI/bge-base-en-v1.5", "context_length": 512, "num_parallel": 64})
+    assert emb["success"] and emb["architecture"] == "bert" and emb["configurations"][0]["kv_cache"] == 0
