@@ -121,6 +121,7 @@ class B200RuntimeParams:
     seed: int = 0
     serve_http: bool = True
     tokenizer: Optional[object] = None
+    engine_factory: Optional[Callable] = None  # EngineConfig -> engine; default: the CUDA engine (tests inject a stand-in)
 
 
 class B200Runtime:
@@ -153,7 +154,7 @@ class B200Runtime:
                            max_seqs=self.parsed.max_num_seqs, max_ctx=max_ctx, use_cuda_graphs=1,
                            max_batched_tokens=self.parsed.max_num_batched_tokens or 16384,
                            enable_prefix_cache=int(self.parsed.enable_prefix_caching and not embed))
-        eng = Engine(cfg)
+        eng = (self.p.engine_factory or Engine)(cfg)
         try:
             if self.p.state_dict is not None:
                 eng.load_state_dict(desc, self.p.state_dict)

@@ -219,3 +219,78 @@ def test_memory_estimation_endpoint_shape_and_numbers():
     assert not bad["success"] and "not served" in bad["error"] and bad["configurations"] == []
     emb = R.memory_estimation({"model_name": "BAAI/bge-base-en-v1.5", "context_length": 512, "num_parallel": 64})
     assert emb["success"] and emb["architecture"] == "bert" and emb["configurations"][0]["kv_cache"] == 0
+
+
+class _StubEngine:
+    """Records what the runtime asks of the engine; `fail_load` makes the weight load raise."""
+    instances = []
+
+    def __init__(self, cfg, fail_load=False):
+        self.cfg, self.fail_load, self.closed, self.started, self.loaded = cfg, fail_load, False, False, None
+        self.desc = None
+        _StubEngine.instances.append(self)
+
+    def load_random(self, desc, seed):
+        if self.fail_load:
+            raise R.HBError(-3, "weights exceed the memory budget")
+        self.loaded, self.desc = ("random", seed), desc
+
+    def load_state_dict(self, desc, sd):
+        self.loaded, self.desc = ("state_dict", len(sd)), desc
+
+    def start(self):
+        self.started = True
+
+    def close(self):
+        self.closed = True
+
+    def stats(self):
+        return {"cuda_error": 0, "kv_pages_free": 7, "kv_pages_total": 8, "running": 0, "waiting": 0}
+
+    def embed(self, seqs):
+        return [[0.0]] * len(seqs)
+
+
+def test_runtime_lifecycle_against_a_stub_engine():
+    """Runtime.Start/Stop/Status/URL/ListModels semantics (api/pkg/runner/slot.go:46-57,113-140) and the engine
+    configuration derived from CreateRunnerSlotAttributes + the scheduler's vLLM-style args — no GPU involved."""
+    _StubEngine.instances.clear()
+    GB = 1024 ** 3
+    p = R.B200RuntimeParams(model="meta-llama/Meta-Llama-3-8B-Instruct", gpu_index=3, model_memory_requirement=40 * GB,
+                            per_gpu_memory=180 * GB, context_length=4096, serve_http=False, seed=5,
+                            args=["--gpu-memory-utilization", "0.22", "--max-num-seqs", "64", "--max-model-len", "8192",
+                                  "--max-num-batched-tokens", "8192"], engine_factory=_StubEngine)
+    rt = R.B200Runtime(p)
+    assert rt.status() == "" and rt.url() == "" and rt.runtime() == "vllm" and rt.list_models() == [p.model]
+    rt.start()
+    (e,) = _StubEngine.instances
+    c = e.cfg
+    assert (c.device, c.memory_budget_bytes, c.max_seqs, c.max_ctx, c.max_batched_tokens) == (3, 40 * GB, 64, 8192, 8192)
+    assert c.enable_prefix_cache == 1 and c.use_cuda_graphs == 1        # exact bytes beat the 2-decimal ratio flag
+    assert e.loaded == ("random", 5) and e.started and e.desc.layers == 32
+    assert rt.status().startswith("running") and "kv_pages_free=7/8" in rt.status()
+    assert "helix-b200" in rt.command_line() and "--max-num-seqs 64" in rt.command_line()
+    seen = []
+    rt.pull_model(p.model, seen.append)
+    assert seen and seen[-1]["status"] == "success"
+    rt.stop()
+    assert e.closed and rt.status() == "" and rt.engine is None
+    # the ratio flag is the fallback when the attributes carry no byte count
+    _StubEngine.instances.clear()
+    rt = R.B200Runtime(R.B200RuntimeParams(model="BAAI/bge-base-en-v1.5", per_gpu_memory=100 * GB, serve_http=False,
+                                           args=["--gpu-memory-utilization", "0.05", "--task", "embed"],
+                                           engine_factory=_StubEngine))
+    rt.start()
+    (e,) = _StubEngine.instances
+    assert e.cfg.memory_budget_bytes == 5 * GB and e.cfg.enable_prefix_cache == 0 and not e.started and rt.is_embed
+    rt.warm("BAAI/bge-base-en-v1.5")
+    rt.stop()
+    # a failing load leaves nothing behind (Slot.Create's deferred Stop would otherwise leak device memory)
+    _StubEngine.instances.clear()
+    rt = R.B200Runtime(R.B200RuntimeParams(model="meta-llama/Llama-3.2-1B-Instruct", serve_http=False,
+                                           engine_factory=lambda cfg: _StubEngine(cfg, fail_load=True)))
+    with pytest.raises(R.HBError):
+        rt.start()
+    assert _StubEngine.instances[0].closed and rt.engine is None and rt.status() == ""
+    with pytest.raises(R.HBError):
+        R.B200Runtime(R.B200RuntimeParams(model="nobody/unknown", serve_http=False, engine_factory=_StubEngine)).start()
