@@ -113,6 +113,24 @@ class EmbedBatcher:
         self.thread.join(timeout=5)
 
 
+class StreamDecoder:
+    """Token ids -> text for streaming: the visible text must not depend on how the tokens were grouped into polls.
+    Decoding each poll's ids on its own garbles any character whose bytes / pieces straddle two polls, so the whole
+    sequence is decoded and only the new, stable suffix is released; a trailing U+FFFD (an incomplete multi-byte
+    sequence so far) is held back until the next tokens complete it or the stream ends."""
+
+    def __init__(self, tok, skip=()):
+        self.tok, self.skip, self.ids, self.emitted = tok, set(skip), [], 0
+
+    def feed(self, ids, final=False):
+        self.ids += [t for t in ids if t not in self.skip]
+        text = self.tok.decode(self.ids)
+        stable = len(text) if final or not text.endswith("\ufffd") else len(text) - 1
+        out = text[self.emitted:stable]
+        self.emitted = max(self.emitted, stable)
+        return out
+
+
 class StopMatcher:
     """OpenAI `stop` (string or list of up to 4 strings): generation ends at the first occurrence and the stop text is
     not returned.  Streaming: text that could still turn out to be the beginning of a stop string is held back."""
@@ -210,13 +228,14 @@ class OpenAIServer:
         yield chat_chunk(cid, model, created, {"role": "assistant", "content": ""}, None)
         n, fin = 0, 0
         stop = StopMatcher(body.get("stop"))
+        dec = StreamDecoder(self.tok, skip=[sp.eos_token])
         try:
             while not fin and not stop.hit:
                 eng.wait(rid, 30000)
                 toks, fin = eng.poll(rid)
-                if toks:
+                if toks or fin:
                     n += len(toks)
-                    text = stop.feed(self.tok.decode([t for t in toks if t != sp.eos_token]))
+                    text = stop.feed(dec.feed(toks, final=bool(fin)))
                     if text:
                         yield chat_chunk(cid, model, created, {"content": text}, None)
             tail = stop.flush()

@@ -163,3 +163,24 @@ def test_embedding_input_forms_and_coalescing(front):
     assert [o["data"][0]["embedding"][0] for o in out] == [float(i + 2) for i in range(10)]
     calls = rt.engine.embed_calls[before:]
     assert sum(calls) == 10 and len(calls) <= 10
+
+
+def test_streamed_text_does_not_depend_on_poll_boundaries(front):
+    """Multi-byte characters whose bytes straddle two polls (the stub hands out 3 tokens per poll) must come out whole,
+    and identically in streaming and non-streaming mode."""
+    rt, base = front
+    text = "naïve café — 日本語 ✓ end"
+    rt.engine.script = [b + ByteTokenizer.OFFSET for b in text.encode()]
+    body = {"model": "tiny", "max_tokens": 500, "messages": [{"role": "user", "content": "hi"}]}
+    assert post(base, "/v1/chat/completions", body)["choices"][0]["message"]["content"] == text
+    raw = post(base, "/v1/chat/completions", dict(body, stream=True), raw=True)
+    chunks = [json.loads(e[6:]) for e in raw.split("\n\n") if e and e != "data: [DONE]"]
+    pieces = [c["choices"][0]["delta"].get("content", "") for c in chunks]
+    assert "".join(pieces) == text and all("�" not in p for p in pieces)
+    # a stop string that itself straddles polls and multi-byte characters
+    r = post(base, "/v1/chat/completions", dict(body, stop=["— 日"]))
+    assert r["choices"][0]["message"]["content"] == "naïve café " and r["choices"][0]["finish_reason"] == "stop"
+    # max_tokens cutting a character in half: the dangling bytes surface as one replacement char at the end, never earlier
+    cut = len("naï".encode()) - 1
+    r = post(base, "/v1/chat/completions", dict(body, max_tokens=cut))
+    assert r["choices"][0]["message"]["content"] == "na�" and r["choices"][0]["finish_reason"] == "length"
