@@ -79,6 +79,8 @@ func (f *openAIFront) chat(w http.ResponseWriter, r *http.Request) {
 	}
 	var full string
 	n := 0
+	var all []int32 // every generated id so far: the text is decoded from the whole sequence (see emitStable)
+	emitted := 0
 	var flusher http.Flusher
 	if req.Stream {
 		w.Header().Set("Content-Type", "text/event-stream")
@@ -88,7 +90,10 @@ func (f *openAIFront) chat(w http.ResponseWriter, r *http.Request) {
 	}
 	fin, err := f.rt.Generate(r.Context(), prompt, maxTokens, req.Temperature, req.TopP, uint64(derefInt(req.Seed)), func(ids []int32) error {
 		n += len(ids)
-		text := f.tok.Decode(dropToken(ids, f.tok.EOS()))
+		all = append(all, dropToken(ids, f.tok.EOS())...)
+		// A character whose bytes / pieces straddle two polls must come out whole: decode everything, release only the
+		// new stable suffix, hold back a trailing U+FFFD (an incomplete sequence so far).  Mirrors server.py StreamDecoder.
+		text := emitStable(f.tok.Decode(all), &emitted, false)
 		full += text
 		if req.Stream && text != "" {
 			return writeSSE(w, flusher, chunk(openai.ChatCompletionStreamChoiceDelta{Content: text}, ""))
@@ -98,6 +103,12 @@ func (f *openAIFront) chat(w http.ResponseWriter, r *http.Request) {
 	if err != nil && fin == 0 {
 		http.Error(w, err.Error(), http.StatusInternalServerError)
 		return
+	}
+	if tail := emitStable(f.tok.Decode(all), &emitted, true); tail != "" { // whatever was still held back
+		full += tail
+		if req.Stream {
+			writeSSE(w, flusher, chunk(openai.ChatCompletionStreamChoiceDelta{Content: tail}, ""))
+		}
 	}
 	reason := openai.FinishReasonStop
 	if n >= maxTokens {
@@ -145,6 +156,21 @@ func (f *openAIFront) embeddings(w http.ResponseWriter, r *http.Request) {
 		resp.Data = append(resp.Data, openai.Embedding{Object: "embedding", Index: i, Embedding: out[i*hidden : (i+1)*hidden]})
 	}
 	_ = json.NewEncoder(w).Encode(resp)
+}
+
+// emitStable returns the part of `decoded` not yet released; unless `final`, one trailing replacement rune stays held.
+func emitStable(decoded string, emitted *int, final bool) string {
+	r := []rune(decoded)
+	stable := len(r)
+	if !final && stable > 0 && r[stable-1] == '\uFFFD' {
+		stable--
+	}
+	if stable <= *emitted {
+		return ""
+	}
+	out := string(r[*emitted:stable])
+	*emitted = stable
+	return out
 }
 
 func writeSSE(w http.ResponseWriter, fl http.Flusher, v any) error {
