@@ -184,3 +184,31 @@ def test_streamed_text_does_not_depend_on_poll_boundaries(front):
     cut = len("naï".encode()) - 1
     r = post(base, "/v1/chat/completions", dict(body, max_tokens=cut))
     assert r["choices"][0]["message"]["content"] == "na�" and r["choices"][0]["finish_reason"] == "length"
+
+
+def test_stream_decoder_and_stop_matcher_properties():
+    """Property checks (hypothesis): any grouping of the token stream into polls yields the same visible text as decoding
+    everything at once; with stop strings, the visible text is the full text cut at the first stop occurrence."""
+    from hypothesis import given, settings, strategies as st
+    from helix_b200.server import StopMatcher, StreamDecoder
+    tok = ByteTokenizer()
+    alphabet = st.sampled_from(list("ab é日✓\n#"))
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(alphabet, max_size=30), st.lists(st.integers(1, 5), min_size=1, max_size=40),
+           st.lists(st.text(alphabet=list("ab\n#é"), min_size=1, max_size=3), max_size=2))
+    def prop(chars, cuts, stops):
+        text = "".join(chars)
+        ids = [b + ByteTokenizer.OFFSET for b in text.encode()]
+        dec, sm, out, i, k = StreamDecoder(tok), StopMatcher(stops), "", 0, 0
+        while i < len(ids) and not sm.hit:
+            n = cuts[k % len(cuts)]
+            k += 1
+            piece = ids[i:i + n]
+            i += n
+            out += sm.feed(dec.feed(piece, final=i >= len(ids)))
+        out += sm.flush()
+        first = min((text.find(s) for s in stops if s in text), default=-1)
+        assert out == (text if first < 0 else text[:first])
+
+    prop()
