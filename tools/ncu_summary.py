@@ -2,6 +2,7 @@
 """Summarise ncu outputs brought back in gpurun_out/ into small text files under profiles/ (tracked).
   python tools/ncu_summary.py launches gpurun_out/r01_launches.csv profiles/r01_launches_summary.txt
   python tools/ncu_summary.py raw gpurun_out/r01_prof_gemm.ncu-rep profiles/r01_gemm_ncu.txt
+  python tools/ncu_summary.py stalls gpurun_out/attn.ncu-rep profiles/r01_attn_stalls.txt
 """
 import collections
 import csv
@@ -59,5 +60,36 @@ def raw(src, dst):
     print(open(dst).read())
 
 
+def stalls(src, dst):
+    """Source-level warp-stall sampling of a `--set full --import-source on` capture: the hottest SASS instructions, every
+    mbarrier wait (fast-path executions, spin-loop executions, samples) and the samples grouped by per-role execution count.
+    This is the view that showed the attention MMA issuer never waiting for its inputs while the tensor pipe idled
+    (per-instruction waterfall loops under `if (lane == 0)`)."""
+    out = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, data = rows[1], rows[2:]
+    ia, isrc, iall, iex = (hdr.index(h) for h in ("Address", "Source", "Warp Stall Sampling (All Samples)", "Instructions Executed"))
+    num = lambda x: int(x or 0)
+    tot = sum(num(r[iall]) for r in data)
+    by_exec = collections.Counter()
+    for r in data:
+        by_exec[num(r[iex])] += num(r[iall])
+    with open(dst, "w") as o:
+        o.write(f"# ncu source page: {src}\n# kernel: {short(rows[0][1])}\ntotal samples {tot}\n\n")
+        o.write("samples by instruction execution count (one count per role / loop level):\n")
+        for k, v in by_exec.most_common(8):
+            o.write(f"  executed {k:>10} times: {v:>8} samples ({100.0 * v / max(tot, 1):.1f} %)\n")
+        o.write("\nhottest instructions:\n")
+        for r in sorted(data, key=lambda r: -num(r[iall]))[:25]:
+            o.write(f"  {r[ia][-6:]} {num(r[iall]):>8} samples  executed {num(r[iex]):>10}  {r[isrc][:100]}\n")
+        o.write("\nmbarrier waits (SYNCS.PHASECHK.TRYWAIT; a fast-path try is followed by its spin loop):\n")
+        for i, r in enumerate(data):
+            if "SYNCS.PHASECHK" in r[isrc] and num(r[iex]) > 0:
+                nxt = data[i + 1] if i + 1 < len(data) else r
+                m = re.search(r"\+0x([0-9a-f]+)\]", r[isrc])
+                o.write(f"  {r[ia][-6:]} executed {num(r[iex]):>10}  samples {num(r[iall]) + num(nxt[iall]):>7}  smem+0x{m.group(1) if m else '?'}\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "raw": raw, "stalls": stalls}[sys.argv[1]](sys.argv[2], sys.argv[3])
