@@ -59,7 +59,8 @@ typedef struct hb_engine_cfg {
   int32_t max_batched_tokens;   /* prompt tokens processed per prefill step (default 16384) */
   int32_t kv_page_size;         /* tokens per KV page; must be 64 */
   int32_t use_cuda_graphs;      /* capture the decode step per batch size */
-  int32_t enable_prefix_cache;  /* --enable-prefix-caching: full KV pages (64 tokens) are content-addressed; a new prompt
+  int32_t enable_prefix_cache;  /* --enable-prefix-caching (a vLLM arg the slot's runtime_args may carry,
+                                   api/pkg/runner/vllm_runtime.go:705-762): full KV pages (64 tokens) are content-addressed; a new prompt
                                    whose leading pages are already in the pool (an earlier turn of the same chat, a
                                    shared system prompt) only prefills the rest */
   int32_t reserved[6];
@@ -86,7 +87,9 @@ typedef struct hb_sampling {
   int32_t max_tokens;  /* generated tokens, >= 1 */
   int32_t eos_token;   /* < 0: none */
   int32_t capture;     /* HB_CAPTURE_* bit mask (parity tap) */
-  int32_t top_k;       /* sampled rows only: keep the k most likely tokens (ties at the k-th logit kept); <= 0: off */
+  int32_t top_k;       /* sampled rows only: keep the k most likely tokens (ties at the k-th logit kept); <= 0: off.
+                          top_k / top_p are request fields the reference forwards untouched to its backend
+                          (openai.ChatCompletionRequest, api/pkg/runner/openai_chat_handlers.go:100-175) */
   float top_p;         /* nucleus: smallest set of most likely tokens (after top_k) with softmax(logits/T) mass >= top_p;
                           values outside (0,1) (so also a zero-initialised struct): off */
   int32_t reserved[1];
