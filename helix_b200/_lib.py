@@ -13,7 +13,9 @@ class LibraryMissing(RuntimeError):
 class EngineCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("memory_budget_bytes", C.c_uint64), ("max_seqs", C.c_int32),
                 ("max_ctx", C.c_int32), ("max_batched_tokens", C.c_int32), ("kv_page_size", C.c_int32),
-                ("use_cuda_graphs", C.c_int32), ("enable_prefix_cache", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("use_cuda_graphs", C.c_int32), ("enable_prefix_cache", C.c_int32), ("sm_budget", C.c_int32),
+                ("sm_partition", C.c_int32), ("stream_priority", C.c_int32), ("decode_with_prefill", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class ModelDescC(C.Structure):
@@ -27,7 +29,8 @@ class ModelDescC(C.Structure):
 
 class SamplingC(C.Structure):
     _fields_ = [("temperature", C.c_float), ("seed", C.c_uint64), ("max_tokens", C.c_int32), ("eos_token", C.c_int32),
-                ("capture", C.c_int32), ("top_k", C.c_int32), ("top_p", C.c_float), ("reserved", C.c_int32 * 1)]
+                ("capture", C.c_int32), ("top_k", C.c_int32), ("top_p", C.c_float), ("logprobs", C.c_int32),
+                ("presence_penalty", C.c_float), ("frequency_penalty", C.c_float), ("reserved2", C.c_int32 * 4)]
 
 
 class StatsC(C.Structure):
@@ -65,6 +68,9 @@ SIGNATURES = {
     "hb_cancel": (I, [P, C.c_uint64]),
     "hb_release": (I, [P, C.c_uint64]),
     "hb_captured_logits": (I, [P, C.c_uint64, C.c_int32, P, C.c_size_t, C.POINTER(C.c_int32)]),
+    "hb_logprobs": (I, [P, C.c_uint64, C.c_int32, C.c_int32, P, P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "hb_replica_unique_id": (I, [P]),
+    "hb_model_load_broadcast": (I, [P, C.POINTER(ModelDescC), P, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "hb_embed": (I, [P, P, P, C.c_int32, P]),
     "hb_get_stats": (I, [P, C.POINTER(StatsC)]),
     "hb_set_profile": (I, [P, C.c_int32]),
@@ -81,6 +87,8 @@ SIGNATURES = {
     "hbk_rope_kv_write": (I, [P, P, P, P, P, P, I, I, I, I, I]),
     "hbk_sample": (I, [P, I, P, P, P, I, I]),
     "hbk_sample_filtered": (I, [P, I, P, P, P, P, P, I, I]),
+    "hbk_apply_penalties": (I, [P, I, P, P, I, I]),
+    "hbk_logprob_topk": (I, [P, I, I, P, P, P, P, I, I]),
     "hbk_cls_pool_l2": (I, [P, P, P, I, I]),
     "hbk_attn_prefill": (I, [P, I, P, I, P, I, P, I, P, I, I, I, I, I, I, I, C.c_float]),
     "hbk_attn_prefill_paged": (I, [P, I, P, P, P, I, P, P, I, P, I, I, I, I, I, I, I, C.c_float, I]),

@@ -78,6 +78,14 @@ int hb_release(hb_engine* e, uint64_t id) { return e ? e->impl.release(id) : HB_
 int hb_captured_logits(hb_engine* e, uint64_t id, int32_t which, float* out, size_t cap, int32_t* rows) {
   return e ? e->impl.captured(id, which, out, cap, rows) : HB_ERR_INVALID;
 }
+int hb_logprobs(hb_engine* e, uint64_t id, int32_t first_row, int32_t max_rows, int32_t* ids, float* lps, int32_t* rows,
+                int32_t* width) {
+  return e ? e->impl.logprobs(id, first_row, max_rows, ids, lps, rows, width) : HB_ERR_INVALID;
+}
+int hb_replica_unique_id(void* id) { return Engine::replica_unique_id(id); }
+int hb_model_load_broadcast(hb_engine* e, const hb_model_desc* d, const void* id, int32_t rank, int32_t world, double* seconds) {
+  return (e && d) ? e->impl.load_broadcast(*d, id, rank, world, seconds) : HB_ERR_INVALID;
+}
 int hb_embed(hb_engine* e, const int32_t* t, const int32_t* off, int32_t n, float* out) {
   return e ? e->impl.embed(t, off, n, out) : HB_ERR_INVALID;
 }
@@ -146,6 +154,13 @@ int hbk_sample(const float* logits, int ldl, const float* temperature, const uin
 int hbk_sample_filtered(const float* logits, int ldl, const float* temperature, const uint64_t* seed, const int32_t* top_k,
                         const float* top_p, int32_t* out, int B, int V) {
   return sample_impl(logits, ldl, temperature, seed, top_k, top_p, out, B, V);
+}
+int hbk_apply_penalties(float* logits, int ldl, const int32_t* pen_off, const void* pen, int B, int V) {
+  return kret(hb::apply_penalties(0, logits, ldl, pen_off, pen, B, V));
+}
+int hbk_logprob_topk(const float* logits, int ldl, int V, const int32_t* sampled, const int32_t* width, int32_t* out_ids,
+                     float* out_lp, int B, int max_width) {
+  return kret(hb::logprob_topk(0, logits, ldl, V, sampled, width, out_ids, out_lp, B, max_width));
 }
 int hbk_cls_pool_l2(const void* x, const int32_t* first_row, float* out, int B, int H) {
   return kret(hb::cls_pool_l2(0, (const hb::bf16*)x, first_row, out, B, H));

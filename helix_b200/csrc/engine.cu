@@ -1,5 +1,6 @@
 #include "engine.h"
 
+#include "nccl_dl.h"
 #include "tma_host.h"
 
 #include <stdlib.h>
@@ -61,6 +62,21 @@ Engine::Engine(const hb_engine_cfg& cfg) : cfg_(cfg) {
 
 Engine::~Engine() {
   stop();
+  {
+    // Runtime.Stop may race with request handlers still parked in hb_wait (the reference's Stop just kills a child
+    // process): fail every open request, wake the waiters and let them leave before anything is freed
+    std::lock_guard<std::mutex> g(mu_);
+    closing_.store(true);
+    for (Request* r : waiting_) finish_request(r, ReqState::CANCELLED);
+    waiting_.clear();
+    for (Request* r : running_) finish_request(r, ReqState::CANCELLED);
+    running_.clear();
+    cv_out_.notify_all();
+  }
+  while (waiters_.load() > 0) {
+    cv_out_.notify_all();
+    std::this_thread::sleep_for(std::chrono::microseconds(100));
+  }
   free_all();
   if (stream_) {
     cudaSetDevice(cfg_.device);
@@ -128,6 +144,8 @@ void Engine::free_all() {
   };
   frh(h_step_);
   frh(h_sampled_);
+  frh(h_lp_ids_);
+  frh(h_lp_vals_);
   frh(h_logits_);
   frh(h_embed_out_);
   loaded_ = false;
@@ -148,6 +166,7 @@ size_t Engine::workspace_bytes() const {
     b += al256(attn_decode_workspace_floats(cfg_.max_seqs, d.heads, d.head_dim, 16) * 4);
     b += al256((size_t)cfg_.max_seqs * 4);                    // sampled
     b += al256(sample_scratch_bytes(cfg_.max_seqs, d.vocab)); // argmax partials
+    b += 2 * al256((size_t)cfg_.max_seqs * HB_MAX_LOGPROBS * 4);  // log-probability records of one step
     b += al256(skinny_ws_bytes(148));                         // decode GEMM partial slabs
   }
   return b;
@@ -184,7 +203,7 @@ void Engine::estimate(const hb_model_desc& d, const hb_engine_cfg& c_in, uint64_
   }
 }
 
-StepLayout Engine::layout(int T, int B) const {
+StepLayout Engine::layout(int T, int B, size_t pen_entries) const {
   StepLayout L;
   size_t o = 0;
   L.tokens = o; o = al16(o + 4 * (size_t)T);
@@ -198,6 +217,9 @@ StepLayout Engine::layout(int T, int B) const {
   L.seed = o; o = al16(o + 8 * (size_t)B);
   L.topk = o; o = al16(o + 4 * (size_t)B);
   L.topp = o; o = al16(o + 4 * (size_t)B);
+  L.lpw = o; o = al16(o + 4 * (size_t)B);
+  L.pen_off = o; o = al16(o + 4 * (size_t)(B + 1));
+  L.pen = o; o = al16(o + 8 * pen_entries);  // {int32 token; float value} entries, last so no offset depends on their number
   L.total = o;
   return L;
 }
@@ -273,6 +295,8 @@ int Engine::alloc_runtime() {
     dec_ws_ = (float*)take(attn_decode_workspace_floats(cfg_.max_seqs, d.heads, d.head_dim, 16) * 4);
     sampled_ = (int32_t*)take((size_t)cfg_.max_seqs * 4);
     sample_ws_ = take(sample_scratch_bytes(cfg_.max_seqs, d.vocab));
+    lp_ids_ = (int32_t*)take((size_t)cfg_.max_seqs * HB_MAX_LOGPROBS * 4);
+    lp_vals_ = (float*)take((size_t)cfg_.max_seqs * HB_MAX_LOGPROBS * 4);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device);
     skinny_ws_ = (float*)take(skinny_ws_bytes(148));
@@ -285,10 +309,16 @@ int Engine::alloc_runtime() {
     CU(gemm_skinny_plan(d.hidden, d.ffn, &plan_down_));
     CU(gemm_skinny_plan(d.vocab, d.hidden, &plan_head_));
   }
-  step_bytes_ = layout(t_cap_, b_cap_).total;
+  // penalty entries: one per distinct generated token of every running sequence, bounded at 4 Mi (32 MB)
+  pen_cap_ = d.arch == HB_ARCH_LLAMA ? std::min<size_t>((size_t)cfg_.max_seqs * cfg_.max_ctx, size_t(4) << 20) : 0;
+  step_bytes_ = layout(t_cap_, b_cap_, pen_cap_).total;
   CU(cudaMalloc(&d_step_, step_bytes_));
   CU(cudaMallocHost(&h_step_, step_bytes_));
   CU(cudaMallocHost(&h_sampled_, (size_t)b_cap_ * 4));
+  if (d.arch == HB_ARCH_LLAMA) {
+    CU(cudaMallocHost(&h_lp_ids_, (size_t)cfg_.max_seqs * HB_MAX_LOGPROBS * 4));
+    CU(cudaMallocHost(&h_lp_vals_, (size_t)cfg_.max_seqs * HB_MAX_LOGPROBS * 4));
+  }
 
   if (d.arch == HB_ARCH_LLAMA) {
     const std::vector<float> f = rope_inv_freq(d);
@@ -318,10 +348,9 @@ int Engine::alloc_runtime() {
     lru_.clear();
     free_pages_.resize(num_pages_);
     for (int i = 0; i < num_pages_; ++i) free_pages_[i] = num_pages_ - 1 - i;  // pop_back hands out page 0 first
-  } else {
-    CU(cudaMalloc(&d_embed_out_, (size_t)b_cap_ * H * 4));
-    CU(cudaMallocHost(&h_embed_out_, (size_t)b_cap_ * H * 4));
   }
+  CU(cudaMalloc(&d_embed_out_, (size_t)b_cap_ * H * 4));  // encoders; decoders serving --task embed (last-token pooling)
+  CU(cudaMallocHost(&h_embed_out_, (size_t)b_cap_ * H * 4));
   return HB_OK;
 }
 
@@ -366,6 +395,69 @@ int Engine::weights_arena(void** p, size_t* bytes) {
   if (!model_.arena) return fail(HB_ERR_STATE, "no model arena");
   if (p) *p = model_.arena;
   if (bytes) *bytes = model_.arena_bytes;
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------ replicas: one NCCL broadcast of the arena
+int Engine::replica_unique_id(void* id) {
+  const char* why = nullptr;
+  const NcclApi* n = nccl_api(&why);
+  if (!n || !id) return HB_ERR_STATE;
+  ncclUniqueId u;
+  if (n->GetUniqueId(&u) != ncclSuccess) return HB_ERR_CUDA;
+  static_assert(sizeof(ncclUniqueId) == HB_REPLICA_ID_BYTES, "NCCL unique id size");
+  memcpy(id, &u, sizeof u);
+  return HB_OK;
+}
+
+int Engine::load_broadcast(const hb_model_desc& d, const void* id, int rank, int world, double* seconds) {
+  if (!id || world < 1 || rank < 0 || rank >= world) return fail(HB_ERR_INVALID, "bad replica rank / world");
+  const char* why = nullptr;
+  const NcclApi* n = nccl_api(&why);
+  if (!n) return fail(HB_ERR_STATE, std::string("NCCL unavailable: ") + (why ? why : ""));
+  if (rank == 0) {
+    if (!loaded_) return fail(HB_ERR_STATE, "replica root must hold a loaded model before the broadcast");
+    if (memcmp(&model_.d, &d, offsetof(hb_model_desc, reserved)) != 0)
+      return fail(HB_ERR_INVALID, "replica root: description differs from the loaded model");
+  } else {
+    int rc = load_begin(d);  // allocates and lays out the arena (fails if a model is already loaded)
+    if (rc != HB_OK) return rc;
+  }
+  std::lock_guard<std::mutex> g(gpu_mu_);
+  CU(cudaSetDevice(cfg_.device));
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof u);
+  ncclComm_t comm = nullptr;
+  ncclResult_t r = n->CommInitRank(&comm, world, u, rank);
+  if (r != ncclSuccess) return fail(HB_ERR_CUDA, std::string("ncclCommInitRank: ") + n->GetErrorString(r));
+  // a 1 MB warm-up broadcast of the arena head keeps channel setup out of the measured copy (contents are rewritten below)
+  const size_t warm = std::min<size_t>(model_.arena_bytes, size_t(1) << 20);
+  r = n->Broadcast(model_.arena, model_.arena, warm, ncclUint8, 0, comm, stream_);
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaStreamSynchronize(stream_);
+  const auto t0 = std::chrono::steady_clock::now();
+  cudaEventRecord(a, stream_);
+  if (r == ncclSuccess) r = n->Broadcast(model_.arena, model_.arena, model_.arena_bytes, ncclUint8, 0, comm, stream_);
+  cudaEventRecord(b, stream_);
+  cudaError_t ce = cudaStreamSynchronize(stream_);
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  n->CommDestroy(comm);
+  if (r != ncclSuccess) return fail(HB_ERR_CUDA, std::string("ncclBroadcast: ") + n->GetErrorString(r));
+  if (ce != cudaSuccess) return fail_cuda(ce, "ncclBroadcast (stream sync)");
+  if (seconds) *seconds = std::max((double)ms * 1e-3, 0.0) > 0 ? (double)ms * 1e-3 : wall;
+  if (rank != 0) {
+    for (auto& kv : model_.placements) model_.filled[kv.first] = true;
+    int rc = alloc_runtime();
+    if (rc != HB_OK) return rc;
+    load_open_ = false;
+    loaded_ = true;
+  }
   return HB_OK;
 }
 
@@ -425,7 +517,8 @@ int Engine::decode_splits(int B) const {
   return std::max(1, std::min(16, (want + ctas - 1) / ctas));
 }
 
-int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits, bool paged) {
+int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits, bool paged,
+                          float* pool_out) {
   if (!prefill && !all_logits && T == B && B <= skinny_max_b_) return forward_llama_decode(B, L);
   const hb_model_desc& d = model_.d;
   const int H = d.hidden, D = d.head_dim, QD = d.heads * D, KD = d.kv_heads * D, QKV = model_.qkv_cols(), F = d.ffn;
@@ -436,10 +529,6 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
   const int32_t* last = (const int32_t*)(d_step_ + L.last);
   const int32_t* ctx = (const int32_t*)(d_step_ + L.ctx);
   const int32_t* pt = (const int32_t*)(d_step_ + L.pt);
-  const float* temp = (const float*)(d_step_ + L.temp);
-  const uint64_t* seed = (const uint64_t*)(d_step_ + L.seed);
-  const int32_t* topk = (const int32_t*)(d_step_ + L.topk);
-  const float* topp = (const float*)(d_step_ + L.topp);
   const size_t layer_kv = (size_t)num_pages_ * d.kv_heads * page_ * D;  // elements per K (or V) plane
 
   const int gcat = prefill ? 0 : 4;  // GEMM family: FLOPs in prefill steps, weight bytes in decode steps
@@ -503,6 +592,11 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
       SPAN(gcat, gwork(T, H, F), gemm_bf16_tn(stream_, g));
     }
   }
+  if (pool_out) {  // decoder embedder (--task embed): final-norm hidden state of each sequence's LAST token, L2-normalised
+    LAUNCH(rmsnorm(stream_, x_, model_.final_norm, h_, last, B, H, d.norm_eps));
+    LAUNCH(cls_pool_l2(stream_, h_, ctx, pool_out, B, H));  // ctx carries 0..B-1 here (rows of h_)
+    return HB_OK;
+  }
   if (all_logits) {
     LAUNCH(rmsnorm(stream_, x_, model_.final_norm, xn_, nullptr, T, H, d.norm_eps));
     GemmArgs g{xn_, H, model_.lm_head, H, all_logits_, d.vocab, nullptr, 0, nullptr, T, d.vocab, H, EPI_F32, 0};
@@ -514,8 +608,25 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
     GemmArgs g{h_, H, model_.lm_head, H, logits_, d.vocab, nullptr, 0, nullptr, B, d.vocab, H, EPI_F32, 0};
     SPAN(gcat, gwork(B, d.vocab, H), gemm_bf16_tn(stream_, g));
   }
-  LAUNCH(sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab, sample_ws_,
-                       step_filtered_ ? topk : nullptr, step_filtered_ ? topp : nullptr));
+  return sample_step(B, L);
+}
+
+// penalties -> (top-k / top-p threshold) -> Gumbel-max / argmax -> log-probabilities, all on logits_[B, vocab]
+int Engine::sample_step(int B, const StepLayout& L) {
+  const hb_model_desc& d = model_.d;
+  const float* temp = (const float*)(d_step_ + L.temp);
+  const uint64_t* seed = (const uint64_t*)(d_step_ + L.seed);
+  const int32_t* topk = (const int32_t*)(d_step_ + L.topk);
+  const float* topp = (const float*)(d_step_ + L.topp);
+  const bool filt = (step_flags_ & STEP_FILTER) != 0;
+  if (step_flags_ & STEP_PENALTY)
+    SPAN(3, 0.0, apply_penalties(stream_, logits_, d.vocab, (const int32_t*)(d_step_ + L.pen_off), d_step_ + L.pen, B, d.vocab));
+  SPAN(3, 4.0 * B * d.vocab, sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab, sample_ws_,
+                                           filt ? topk : nullptr, filt ? topp : nullptr));
+  launches_.fetch_add(filt ? 2 : 1, std::memory_order_relaxed);  // sample_tokens is 2 kernels (+1 threshold pass)
+  if (step_flags_ & STEP_LOGPROBS)
+    SPAN(3, 4.0 * B * d.vocab, logprob_topk(stream_, logits_, d.vocab, d.vocab, sampled_, (const int32_t*)(d_step_ + L.lpw),
+                                            lp_ids_, lp_vals_, B, HB_MAX_LOGPROBS));
   return HB_OK;
 }
 
@@ -529,10 +640,6 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
   const int32_t* slots = (const int32_t*)(d_step_ + L.slots);
   const int32_t* ctx = (const int32_t*)(d_step_ + L.ctx);
   const int32_t* pt = (const int32_t*)(d_step_ + L.pt);
-  const float* temp = (const float*)(d_step_ + L.temp);
-  const uint64_t* seed = (const uint64_t*)(d_step_ + L.seed);
-  const int32_t* topk = (const int32_t*)(d_step_ + L.topk);
-  const float* topp = (const float*)(d_step_ + L.topp);
   const size_t layer_kv = (size_t)num_pages_ * d.kv_heads * page_ * D;
   auto wbytes = [&](double N, double K) { return 2.0 * N * K + 2.0 * B * K + 4.0 * B * N; };
   const double rowb = 4.0 * B * H;
@@ -571,9 +678,7 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
   }
   SPAN(4, wbytes(d.vocab, H), gemm_skinny(stream_, plan_head_, xn_, H, model_.lm_head, H, skinny_ws_, B, d.vocab, H));
   SPAN(3, 8.0 * B * d.vocab, dec_sum_slabs(stream_, skinny_ws_, plan_head_, logits_, d.vocab, B, d.vocab));
-  SPAN(3, 4.0 * B * d.vocab, sample_tokens(stream_, logits_, d.vocab, temp, seed, sampled_, B, d.vocab, sample_ws_,
-                                           step_filtered_ ? topk : nullptr, step_filtered_ ? topp : nullptr));
-  return HB_OK;
+  return sample_step(B, L);
 }
 
 int Engine::forward_bert(int T, int B, int max_seqlen, const StepLayout& L, float* d_out) {
@@ -705,6 +810,10 @@ int Engine::submit(const int32_t* toks, int n, const hb_sampling* sp, uint64_t* 
   r->sp = *sp;
   if (r->sp.max_tokens < 1) r->sp.max_tokens = 1;
   if (n + r->sp.max_tokens > cfg_.max_ctx) r->sp.max_tokens = cfg_.max_ctx - n;
+  if (r->sp.logprobs < 0 || r->sp.logprobs > HB_MAX_LOGPROBS) return fail(HB_ERR_INVALID, "logprobs must be in [0, 21]");
+  if ((r->sp.presence_penalty != 0.f || r->sp.frequency_penalty != 0.f) &&
+      (size_t)r->sp.max_tokens * (size_t)cfg_.max_seqs > pen_cap_)
+    return fail(HB_ERR_INVALID, "max_tokens too large for a request with presence/frequency penalties on this engine");
   std::lock_guard<std::mutex> g(mu_);
   if ((int)waiting_.size() >= 65536) return fail(HB_ERR_BUSY, "queue full");
   r->id = next_id_++;
@@ -729,18 +838,29 @@ int Engine::poll(uint64_t id, int32_t* out, int cap, int* n_out, int* finished) 
 }
 
 int Engine::wait(uint64_t id, int timeout_ms) {
+  struct Guard {  // the destructor of the engine waits for every thread parked here to leave
+    std::atomic<int>& n;
+    explicit Guard(std::atomic<int>& c) : n(c) { n.fetch_add(1); }
+    ~Guard() { n.fetch_sub(1); }
+  } guard(waiters_);
   std::unique_lock<std::mutex> g(mu_);
-  auto it = reqs_.find(id);
-  if (it == reqs_.end()) return fail(HB_ERR_NOT_FOUND, "unknown request id");
-  Request* r = it->second.get();
+  if (closing_.load()) return fail(HB_ERR_STATE, "engine is shutting down");
+  // the record is looked up again after every wake-up: another thread may hb_release it while this one sleeps
   auto ready = [&] {
+    if (closing_.load()) return true;
+    auto it = reqs_.find(id);
+    if (it == reqs_.end()) return true;
+    const Request* r = it->second.get();
     return r->polled < r->out.size() || r->state == ReqState::FINISHED || r->state == ReqState::CANCELLED ||
            r->state == ReqState::FAILED;
   };
+  if (reqs_.find(id) == reqs_.end()) return fail(HB_ERR_NOT_FOUND, "unknown request id");
   if (timeout_ms < 0)
     cv_out_.wait(g, ready);
   else
     cv_out_.wait_for(g, std::chrono::milliseconds(timeout_ms), ready);
+  if (closing_.load()) return fail(HB_ERR_STATE, "engine is shutting down");
+  if (reqs_.find(id) == reqs_.end()) return fail(HB_ERR_NOT_FOUND, "request released while waiting");
   return ready() ? HB_OK : HB_ERR_BUSY;
 }
 
@@ -783,6 +903,77 @@ int Engine::captured(uint64_t id, int which, float* out, size_t cap, int* rows) 
   return HB_OK;
 }
 
+// Per-row sampler inputs of a step (mu_ not needed: the step owns its batch).  Returns the number of penalty entries.
+size_t Engine::fill_sampling(Request* const* batch, int B, const StepLayout& L, int T) {
+  float* temp = (float*)(h_step_ + L.temp);
+  uint64_t* seed = (uint64_t*)(h_step_ + L.seed);
+  int32_t* topk = (int32_t*)(h_step_ + L.topk);
+  float* topp = (float*)(h_step_ + L.topp);
+  int32_t* lpw = (int32_t*)(h_step_ + L.lpw);
+  int32_t* pen_off = (int32_t*)(h_step_ + L.pen_off);
+  struct Entry { int32_t tok; float val; };
+  Entry* pen = (Entry*)(h_step_ + L.pen);
+  step_flags_ = 0;
+  size_t n = 0;
+  for (int i = 0; i < B; ++i) {
+    const Request* r = batch[i];
+    temp[i] = r->sp.temperature;
+    seed[i] = r->sp.seed * 0x9E3779B97F4A7C15ull + (uint64_t)r->out.size();  // one noise stream per generated position
+    topk[i] = r->sp.top_k;
+    topp[i] = r->sp.top_p;
+    lpw[i] = std::max(0, std::min(r->sp.logprobs, (int)HB_MAX_LOGPROBS));
+    if (wants_filter(r->sp, model_.d.vocab)) step_flags_ |= STEP_FILTER;
+    if (lpw[i] > 0) step_flags_ |= STEP_LOGPROBS;
+    pen_off[i] = (int32_t)n;
+    if (r->sp.presence_penalty != 0.f || r->sp.frequency_penalty != 0.f) {
+      step_flags_ |= STEP_PENALTY;
+      for (const auto& kv : r->counts) {
+        if (n >= pen_cap_) break;  // cannot happen: submit() bounds max_tokens of penalised requests by pen_cap_ / max_seqs
+        pen[n++] = Entry{kv.first, r->sp.presence_penalty + r->sp.frequency_penalty * (float)kv.second};
+      }
+    }
+  }
+  pen_off[B] = (int32_t)n;
+  (void)T;
+  return n;
+}
+
+// after the step's stream sync: append each row's [width] record to its request
+int Engine::collect_logprobs(Request* const* batch, int B, bool prefill) {
+  if (!(step_flags_ & STEP_LOGPROBS)) return HB_OK;
+  CU(cudaMemcpyAsync(h_lp_ids_, lp_ids_, (size_t)B * HB_MAX_LOGPROBS * 4, cudaMemcpyDeviceToHost, stream_));
+  CU(cudaMemcpyAsync(h_lp_vals_, lp_vals_, (size_t)B * HB_MAX_LOGPROBS * 4, cudaMemcpyDeviceToHost, stream_));
+  CU(cudaStreamSynchronize(stream_));
+  for (int i = 0; i < B; ++i) {
+    Request* r = batch[i];
+    const int w = std::max(0, std::min(r->sp.logprobs, (int)HB_MAX_LOGPROBS));
+    if (w == 0 || (prefill && r->prefilled + r->chunk < (int)r->prompt.size())) continue;  // not the last chunk: nothing sampled
+    r->lp_ids.insert(r->lp_ids.end(), h_lp_ids_ + (size_t)i * HB_MAX_LOGPROBS, h_lp_ids_ + (size_t)i * HB_MAX_LOGPROBS + w);
+    r->lp_vals.insert(r->lp_vals.end(), h_lp_vals_ + (size_t)i * HB_MAX_LOGPROBS, h_lp_vals_ + (size_t)i * HB_MAX_LOGPROBS + w);
+  }
+  return HB_OK;
+}
+
+int Engine::logprobs(uint64_t id, int first_row, int max_rows, int32_t* ids, float* lps, int* rows, int* width) {
+  std::lock_guard<std::mutex> g(mu_);
+  auto it = reqs_.find(id);
+  if (it == reqs_.end()) return fail(HB_ERR_NOT_FOUND, "unknown request id");
+  const Request* r = it->second.get();
+  const int w = std::max(0, std::min(r->sp.logprobs, (int)HB_MAX_LOGPROBS));
+  if (width) *width = w;
+  int have = w ? (int)(r->lp_ids.size() / w) : 0;
+  have = std::min(have, (int)r->out.size());  // rows become visible together with their token
+  int n = std::max(0, std::min(max_rows, have - std::max(0, first_row)));
+  if (n > 0 && ids && lps) {
+    memcpy(ids, r->lp_ids.data() + (size_t)first_row * w, (size_t)n * w * 4);
+    memcpy(lps, r->lp_vals.data() + (size_t)first_row * w, (size_t)n * w * 4);
+  } else if (n > 0) {
+    n = 0;
+  }
+  if (rows) *rows = n;
+  return HB_OK;
+}
+
 int Engine::run_prefill(std::vector<Request*>& batch) {
   const hb_model_desc& d = model_.d;
   const int B = (int)batch.size();
@@ -803,7 +994,7 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
       all_logits_rows_ = T;
     }
   }
-  const StepLayout L = layout(T, B);
+  StepLayout L = layout(T, B);
   int32_t* tok = (int32_t*)(h_step_ + L.tokens);
   int32_t* pos = (int32_t*)(h_step_ + L.positions);
   int32_t* slot = (int32_t*)(h_step_ + L.slots);
@@ -811,11 +1002,7 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   int32_t* last = (int32_t*)(h_step_ + L.last);
   int32_t* ctx = (int32_t*)(h_step_ + L.ctx);
   int32_t* pt = (int32_t*)(h_step_ + L.pt);
-  float* temp = (float*)(h_step_ + L.temp);
-  uint64_t* seed = (uint64_t*)(h_step_ + L.seed);
-  int32_t* topk = (int32_t*)(h_step_ + L.topk);
-  float* topp = (float*)(h_step_ + L.topp);
-  step_filtered_ = false;
+  L.total = al16(L.pen + 8 * fill_sampling(batch.data(), B, L, T));
   int t = 0;
   for (int i = 0; i < B; ++i) {
     Request* r = batch[i];
@@ -832,11 +1019,6 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
       const int np = (end + page_ - 1) / page_;
       for (int j = 0; j < np; ++j) pt[(size_t)i * max_pages_per_seq_ + j] = r->pages[j];
     }
-    temp[i] = r->sp.temperature;
-    seed[i] = r->sp.seed * 0x9E3779B97F4A7C15ull + 0;
-    topk[i] = r->sp.top_k;
-    topp[i] = r->sp.top_p;
-    step_filtered_ |= wants_filter(r->sp, d.vocab);
   }
   cu[B] = t;
   CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
@@ -858,6 +1040,10 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   }
   steps_prefill_++;
   tok_prefill_ += T;
+  {
+    int rc2 = collect_logprobs(batch.data(), B, true);
+    if (rc2 != HB_OK) return rc2;
+  }
   // captures (test tap; synchronous copies are fine here)
   for (int i = 0; i < B; ++i) {
     Request* r = batch[i];
@@ -878,7 +1064,7 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
 int Engine::run_decode(std::vector<Request*>& batch) {
   const hb_model_desc& d = model_.d;
   const int B = (int)batch.size();
-  const StepLayout L = layout(B, B);
+  StepLayout L = layout(B, B);
   int32_t* tok = (int32_t*)(h_step_ + L.tokens);
   int32_t* pos = (int32_t*)(h_step_ + L.positions);
   int32_t* slot = (int32_t*)(h_step_ + L.slots);
@@ -886,11 +1072,7 @@ int Engine::run_decode(std::vector<Request*>& batch) {
   int32_t* last = (int32_t*)(h_step_ + L.last);
   int32_t* ctx = (int32_t*)(h_step_ + L.ctx);
   int32_t* pt = (int32_t*)(h_step_ + L.pt);
-  float* temp = (float*)(h_step_ + L.temp);
-  uint64_t* seed = (uint64_t*)(h_step_ + L.seed);
-  int32_t* topk = (int32_t*)(h_step_ + L.topk);
-  float* topp = (float*)(h_step_ + L.topp);
-  step_filtered_ = false;
+  L.total = al16(L.pen + 8 * fill_sampling(batch.data(), B, L, B));
   for (int i = 0; i < B; ++i) {
     Request* r = batch[i];
     const int p = r->kv_len;
@@ -902,11 +1084,6 @@ int Engine::run_decode(std::vector<Request*>& batch) {
     ctx[i] = p + 1;
     const int np = (p + 1 + page_ - 1) / page_;
     for (int j = 0; j < np; ++j) pt[(size_t)i * max_pages_per_seq_ + j] = r->pages[j];
-    temp[i] = r->sp.temperature;
-    seed[i] = r->sp.seed * 0x9E3779B97F4A7C15ull + (uint64_t)r->out.size();
-    topk[i] = r->sp.top_k;
-    topp[i] = r->sp.top_p;
-    step_filtered_ |= wants_filter(r->sp, d.vocab);
   }
   cu[B] = B;
   CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
@@ -914,7 +1091,7 @@ int Engine::run_decode(std::vector<Request*>& batch) {
   for (Request* r : batch) attn_bytes_ += (double)(r->kv_len + 1) * 2.0 * d.kv_heads * d.head_dim * 2.0;
   CU(cudaEventRecord(fwd_a_, stream_));
   if (cfg_.use_cuda_graphs && !profile_) {
-    const int gkey = B | (step_filtered_ ? 1 << 20 : 0);  // the filtered sampler is a different kernel sequence
+    const int gkey = B | (step_flags_ << 20);  // filter / penalty / log-probability passes are different kernel sequences
     auto it = graphs_.find(gkey);
     if (it == graphs_.end()) {
       cudaGraph_t graph = nullptr;
@@ -948,6 +1125,10 @@ int Engine::run_decode(std::vector<Request*>& batch) {
   }
   steps_decode_++;
   tok_decode_ += B;
+  {
+    int rc2 = collect_logprobs(batch.data(), B, false);
+    if (rc2 != HB_OK) return rc2;
+  }
   for (int i = 0; i < B; ++i) {
     Request* r = batch[i];
     if (r->sp.capture & HB_CAPTURE_STEP_LOGITS) {
@@ -1068,6 +1249,7 @@ int Engine::step(int* did_work) {
         register_full_pages(r);
       }
       r->out.push_back(t);
+      if (r->sp.presence_penalty != 0.f || r->sp.frequency_penalty != 0.f) r->counts[t] += 1;
       const bool done = (int)r->out.size() >= r->sp.max_tokens || (r->sp.eos_token >= 0 && t == r->sp.eos_token) ||
                         r->kv_len + 1 >= cfg_.max_ctx;
       if (done) {
@@ -1127,23 +1309,24 @@ int Engine::stop() {
 // ------------------------------------------------------------------ embeddings (BERT-style encoders)
 int Engine::embed(const int32_t* toks, const int32_t* offsets, int nseq, float* out) {
   if (!loaded_) return fail(HB_ERR_STATE, "hb_embed before a model is loaded");
-  if (model_.d.arch != HB_ARCH_BERT) return fail(HB_ERR_INVALID, "hb_embed needs an encoder model");
   if (nseq < 0 || (nseq > 0 && (!toks || !offsets || !out))) return fail(HB_ERR_INVALID, "null argument");
   if (cuda_error_.load()) return fail(HB_ERR_CUDA, "engine is in a sticky CUDA error state");
   const hb_model_desc& d = model_.d;
+  const bool dec = d.arch == HB_ARCH_LLAMA;  // decoder embedder: causal pass without KV-cache writes, last-token pooling
   for (int i = 0; i < nseq; ++i) {
     const int n = offsets[i + 1] - offsets[i];
     if (n <= 0) return fail(HB_ERR_INVALID, "empty sequence");
-    if (n > cfg_.max_ctx || n > d.max_pos) return fail(HB_ERR_INVALID, "sequence longer than the model's positions");
+    if (n > cfg_.max_ctx || n > d.max_pos || n > t_cap_) return fail(HB_ERR_INVALID, "sequence longer than the model's positions");
   }
   for (int i = (nseq ? offsets[0] : 0); i < (nseq ? offsets[nseq] : 0); ++i)
     if (toks[i] < 0 || toks[i] >= d.vocab) return fail(HB_ERR_INVALID, "token id out of range");
   std::lock_guard<std::mutex> gg(gpu_mu_);
   CU(cudaSetDevice(cfg_.device));
+  const int bmax = dec ? cfg_.max_seqs : b_cap_;
   int s0 = 0;
   while (s0 < nseq) {
     int s1 = s0, T = 0, max_len = 0;
-    while (s1 < nseq && s1 - s0 < b_cap_) {
+    while (s1 < nseq && s1 - s0 < bmax) {
       const int n = offsets[s1 + 1] - offsets[s1];
       if (T + n > t_cap_) break;
       T += n;
@@ -1163,14 +1346,24 @@ int Engine::embed(const int32_t* toks, const int32_t* offsets, int nseq, float* 
       for (int j = 0; j < n; ++j) pos[o + j] = j;
     }
     cu[B] = T;
+    if (dec) {
+      int32_t* slot = (int32_t*)(h_step_ + L.slots);
+      int32_t* last = (int32_t*)(h_step_ + L.last);
+      int32_t* ctx = (int32_t*)(h_step_ + L.ctx);
+      for (int t = 0; t < T; ++t) slot[t] = -1;  // nothing enters the paged pool
+      for (int i = 0; i < B; ++i) {
+        last[i] = cu[i + 1] - 1;
+        ctx[i] = i;
+      }
+    }
     CU(cudaMemcpyAsync(d_step_, h_step_, L.total, cudaMemcpyHostToDevice, stream_));
     attn_flops_ = 0;
     for (int i = 0; i < B; ++i) {
       const double n = offsets[s0 + i + 1] - offsets[s0 + i];
-      attn_flops_ += 4.0 * n * n * d.head_dim * d.heads;
+      attn_flops_ += (dec ? 2.0 : 4.0) * n * n * d.head_dim * d.heads;
     }
     CU(cudaEventRecord(fwd_a_, stream_));
-    int rc = forward_bert(T, B, max_len, L, d_embed_out_);
+    int rc = dec ? forward_llama(T, B, true, max_len, L, false, false, d_embed_out_) : forward_bert(T, B, max_len, L, d_embed_out_);
     if (rc != HB_OK) return rc;
     CU(cudaEventRecord(fwd_b_, stream_));
     CU(cudaMemcpyAsync(h_embed_out_, d_embed_out_, (size_t)B * d.hidden * 4, cudaMemcpyDeviceToHost, stream_));

@@ -40,11 +40,16 @@ struct Request {
   size_t polled = 0;    // tokens already handed to the caller
   std::vector<float> step_logits;    // rows of [vocab] (HB_CAPTURE_STEP_LOGITS)
   std::vector<float> prompt_logits;  // [n_prompt][vocab] (HB_CAPTURE_PROMPT_LOGITS)
+  std::unordered_map<int32_t, int32_t> counts;  // generated token -> occurrences (presence / frequency penalties)
+  std::vector<int32_t> lp_ids;       // [generated][sp.logprobs]
+  std::vector<float> lp_vals;
+  int preempted = 0;    // times this sequence was evicted and re-queued (pages reclaimed, KV recomputed on re-admission)
 };
 
 struct StepLayout {
-  size_t tokens, positions, slots, cu, last, ctx, pt, temp, seed, topk, topp, total;
+  size_t tokens, positions, slots, cu, last, ctx, pt, temp, seed, topk, topp, lpw, pen_off, pen, total;
 };
+enum StepFlags : int { STEP_FILTER = 1, STEP_PENALTY = 2, STEP_LOGPROBS = 4 };
 
 class Engine {
  public:
@@ -68,6 +73,9 @@ class Engine {
   int release(uint64_t id);
   int captured(uint64_t id, int which, float* out, size_t cap, int* rows);
   int embed(const int32_t* toks, const int32_t* offsets, int nseq, float* out);
+  int logprobs(uint64_t id, int first_row, int max_rows, int32_t* ids, float* lps, int* rows, int* width);
+  static int replica_unique_id(void* id);
+  int load_broadcast(const hb_model_desc& d, const void* id, int rank, int world, double* seconds);
   int stats(hb_stats* s);
   int set_profile(bool on);
   const char* last_error();
@@ -82,8 +90,9 @@ class Engine {
   void free_all();
   void loop();
   void finish_request(Request* r, ReqState st);
-  StepLayout layout(int T, int B) const;
-  int forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits, bool paged = false);
+  StepLayout layout(int T, int B, size_t pen_entries = 0) const;
+  int forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits, bool paged = false,
+                    float* pool_out = nullptr);
   int forward_bert(int T, int B, int max_seqlen, const StepLayout& L, float* d_out);
   int run_prefill(std::vector<Request*>& batch);
   int run_decode(std::vector<Request*>& batch);
@@ -148,7 +157,15 @@ class Engine {
   int skinny_max_b_ = 0;
   int32_t* sampled_ = nullptr;
   void* sample_ws_ = nullptr;
-  bool step_filtered_ = false;  // some sequence of the current step samples with top-k / top-p
+  int step_flags_ = 0;          // StepFlags of the current step: top-k/top-p filter, penalties, log-probabilities
+  size_t pen_cap_ = 0;          // penalty entries the step block can hold
+  int32_t* lp_ids_ = nullptr;   // [b_cap][HB_MAX_LOGPROBS]
+  float* lp_vals_ = nullptr;
+  int32_t* h_lp_ids_ = nullptr;
+  float* h_lp_vals_ = nullptr;
+  size_t fill_sampling(Request* const* batch, int B, const StepLayout& L0, int T);  // per-row sampler inputs; returns pen entries
+  int sample_step(int B, const StepLayout& L);  // penalties -> sample -> logprobs on logits_
+  int collect_logprobs(Request* const* batch, int B, bool prefill);
   uint8_t* d_step_ = nullptr;  // per-step int/float inputs (layout())
   uint8_t* h_step_ = nullptr;  // pinned mirror
   int32_t* h_sampled_ = nullptr;
@@ -173,7 +190,8 @@ class Engine {
   std::unordered_map<uint64_t, std::unique_ptr<Request>> reqs_;
   uint64_t next_id_ = 1;
   std::thread thread_;
-  std::atomic<bool> stop_{false};
+  std::atomic<bool> stop_{false}, closing_{false};
+  std::atomic<int> waiters_{0};  // threads inside wait(): the destructor wakes them and lets them leave first
   bool thread_running_ = false;
 
   std::mutex err_mu_;

@@ -73,6 +73,11 @@ cudaError_t sample_tokens(cudaStream_t s, const float* logits, int ldl, const fl
                           int32_t* out, int B, int V, void* scratch, const int32_t* top_k = nullptr,
                           const float* top_p = nullptr);  // per-row top-k (<=0 off) / top-p (outside (0,1) off), sampled rows only
 size_t sample_scratch_bytes(int B, int V);  // two-stage argmax partials
+// logits[b, tok] -= val for the entries {int32 tok; float val} [pen_off[b], pen_off[b+1]) of row b (distinct tokens per row)
+cudaError_t apply_penalties(cudaStream_t s, float* logits, int ldl, const int32_t* pen_off, const void* pen, int B, int V);
+// rows with width[b] > 0: out_ids/out_lp[b][0] = sampled token and its log-softmax, [1..width) = most likely tokens (desc)
+cudaError_t logprob_topk(cudaStream_t s, const float* logits, int ldl, int V, const int32_t* sampled, const int32_t* width,
+                         int32_t* out_ids, float* out_lp, int B, int max_width);
 // out[b,:] = l2normalize(x[first_row[b], :]) as fp32 (CLS pooling for bge-style encoders)
 cudaError_t cls_pool_l2(cudaStream_t s, const bf16* x, const int32_t* first_row, float* out, int B, int H);
 

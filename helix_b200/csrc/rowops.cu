@@ -431,8 +431,12 @@ sample_stage1_kernel(const float* __restrict__ logits, int ldl, const float* __r
     float x = raw * inv_t;
     if (!greedy) {
       const uint64_t h = mix64(sd ^ (0xD1B54A32D192ED03ull * (uint64_t)(v + 1)));
-      const float u = ((float)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0,1]
-      x += -__logf(-__logf(u));
+      // 23 random bits + 0.5: every value is exact in fp32 and u stays strictly inside (0,1) — with 24 bits the
+      // "+0.5f" rounds the top half of the range up and u == 1.0 made the noise +inf (a uniformly random token won
+      // once per 2^24 draws, ~0.8 % of sampled tokens at a 128k vocabulary).  The inner log is the accurate one: the
+      // fast-math log has an absolute error comparable to log(1 - 2^-24).
+      const float u = ((float)(h >> 41) + 0.5f) * (1.0f / 8388608.0f);
+      x += -__logf(-logf(u));
     }
     if (x > best || (x == best && v < bi)) { best = x; bi = v; }
   }
@@ -459,6 +463,82 @@ sample_stage2_kernel(const float* __restrict__ part_val, const int* __restrict__
     argmax_merge(best, bi, ov, oi);
   }
   if (threadIdx.x == 0) out[b] = bi < 0x7fffffff ? bi : 0;  // all-NaN row: emit a valid id, never an out-of-range one
+}
+
+// ---- OpenAI presence / frequency penalties: logits[b, tok] -= val for the (tok, val) entries of row b ----
+// entries [pen_off[b], pen_off[b+1]) hold the DISTINCT tokens the sequence has generated so far with
+// val = presence + frequency * count (computed on the host from the request's exact integer counts)
+__global__ void __launch_bounds__(256)
+apply_penalties_kernel(float* __restrict__ logits, int ldl, const int32_t* __restrict__ pen_off,
+                       const int2* __restrict__ pen, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  float* row = logits + (size_t)b * ldl;
+  for (int i = pen_off[b] + threadIdx.x; i < pen_off[b + 1]; i += 256) {
+    const int2 e = pen[i];
+    if (e.x >= 0 && e.x < V) row[e.x] -= __int_as_float(e.y);  // distinct tokens: no two threads touch the same logit
+  }
+}
+
+// ---- log-probabilities of the sampled token and of the width-1 most likely tokens (descending, lowest id on ties) ----
+constexpr int kLpThreads = 1024;
+__global__ void __launch_bounds__(kLpThreads)
+logprob_topk_kernel(const float* __restrict__ logits, int ldl, int V, const int32_t* __restrict__ sampled,
+                    const int32_t* __restrict__ width, int32_t* __restrict__ out_ids, float* __restrict__ out_lp,
+                    int max_width) {
+  __shared__ float sval[kLpThreads / 32];
+  __shared__ int sidx[kLpThreads / 32];
+  __shared__ float red[kLpThreads / 32];
+  __shared__ float s_bv;
+  __shared__ int s_bi;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const int w = min(width[b], max_width);
+  if (w <= 0) return;
+  const float* row = logits + (size_t)b * ldl;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += kLpThreads) argmax_merge(best, bi, row[v], v);
+  block_argmax<kLpThreads>(best, bi, sval, sidx);
+  if (threadIdx.x == 0) { s_bv = best; s_bi = bi; }
+  __syncthreads();
+  const float mx = s_bv;
+  float se = 0.f;
+  for (int v = threadIdx.x; v < V; v += kLpThreads) se += expf(row[v] - mx);
+  se = block_sum<kLpThreads>(se, red);
+  const float lse = mx + logf(se);
+  int32_t* ids = out_ids + (size_t)b * max_width;
+  float* lps = out_lp + (size_t)b * max_width;
+  if (threadIdx.x == 0) {
+    const int t = sampled[b];
+    ids[0] = t;
+    lps[0] = (t >= 0 && t < V) ? row[t] - lse : -INFINITY;
+  }
+  float pv = s_bv;   // the j-th most likely token in the order (value desc, id asc); j = 1 is the argmax found above
+  int pi = s_bi;
+  for (int j = 1; j < w; ++j) {
+    if (threadIdx.x == 0) { ids[j] = pi; lps[j] = pv - lse; }
+    if (j + 1 == w) break;
+    best = -INFINITY;
+    bi = 0x7fffffff;
+    for (int v = threadIdx.x; v < V; v += kLpThreads) {
+      const float x = row[v];
+      if (x < pv || (x == pv && v > pi)) argmax_merge(best, bi, x, v);  // strictly after the previous pick
+    }
+    __syncthreads();  // sval/sidx reuse
+    block_argmax<kLpThreads>(best, bi, sval, sidx);
+    if (threadIdx.x == 0) { s_bv = best; s_bi = bi; }
+    __syncthreads();
+    pv = s_bv;
+    pi = s_bi;
+    if (pi == 0x7fffffff) {  // fewer than `w` finite logits in the row
+      if (threadIdx.x == 0)
+        for (int k = j + 1; k < w; ++k) { ids[k] = -1; lps[k] = -INFINITY; }
+      break;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kRowThreads)
@@ -540,6 +620,16 @@ cudaError_t sample_tokens(cudaStream_t s, const float* logits, int ldl, const fl
                (const float*)thr, pv, pi, V);
   if (e != cudaSuccess) return e;
   return launch_k(sample_stage2_kernel, dim3(B), dim3(32), 0, s, true, (const float*)pv, (const int*)pi, out, chunks);
+}
+cudaError_t apply_penalties(cudaStream_t s, float* logits, int ldl, const int32_t* pen_off, const void* pen, int B, int V) {
+  if (B <= 0) return cudaSuccess;
+  return launch_k(apply_penalties_kernel, dim3(B), dim3(256), 0, s, true, logits, ldl, pen_off, (const int2*)pen, V);
+}
+cudaError_t logprob_topk(cudaStream_t s, const float* logits, int ldl, int V, const int32_t* sampled, const int32_t* width,
+                         int32_t* out_ids, float* out_lp, int B, int max_width) {
+  if (B <= 0) return cudaSuccess;
+  return launch_k(logprob_topk_kernel, dim3(B), dim3(kLpThreads), 0, s, true, logits, ldl, V, sampled, width, out_ids,
+                  out_lp, max_width);
 }
 cudaError_t cls_pool_l2(cudaStream_t s, const bf16* x, const int32_t* first_row, float* out, int B, int H) {
   if (B <= 0) return cudaSuccess;

@@ -32,10 +32,15 @@ class EngineConfig:
     kv_page_size: int = 64
     use_cuda_graphs: int = 0
     enable_prefix_cache: int = 0
+    sm_budget: int = 0            # SMs this engine's persistent kernels may occupy (0 = all): multi-model packing
+    sm_partition: int = 0         # 1: enforce sm_budget with a CUDA green context
+    stream_priority: int = 0      # 1: high-priority stream
+    decode_with_prefill: int = 0  # 1: running sequences decode inside prefill steps (mixed batches)
 
     def to_c(self):
         return EngineCfg(self.device, self.memory_budget_bytes, self.max_seqs, self.max_ctx, self.max_batched_tokens,
-                         self.kv_page_size, self.use_cuda_graphs, self.enable_prefix_cache)
+                         self.kv_page_size, self.use_cuda_graphs, self.enable_prefix_cache, self.sm_budget,
+                         self.sm_partition, self.stream_priority, self.decode_with_prefill)
 
 
 @dataclass
@@ -74,9 +79,13 @@ class Sampling:
     capture: int = 0
     top_k: int = 0      # <= 0: off
     top_p: float = 1.0  # outside (0, 1): off
+    logprobs: int = 0   # n >= 1: chosen token + the n-1 most likely alternatives per generated token (n <= 21)
+    presence_penalty: float = 0.0
+    frequency_penalty: float = 0.0
 
     def to_c(self):
-        return SamplingC(self.temperature, self.seed, self.max_tokens, self.eos_token, self.capture, self.top_k, self.top_p)
+        return SamplingC(self.temperature, self.seed, self.max_tokens, self.eos_token, self.capture, self.top_k, self.top_p,
+                         self.logprobs, self.presence_penalty, self.frequency_penalty)
 
 
 def bf16_bits(a):
@@ -84,6 +93,15 @@ def bf16_bits(a):
     u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
     r = ((u >> 16) & 1) + 0x7FFF
     return ((u + r) >> 16).astype(np.uint16)
+
+
+def replica_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (hb_replica_unique_id): 128 bytes to hand to every replica."""
+    buf = C.create_string_buffer(128)
+    rc = _lib.lib().hb_replica_unique_id(buf)
+    if rc != 0:
+        raise HBError(rc, "hb_replica_unique_id failed (libnccl.so.2 not available?)")
+    return buf.raw
 
 
 def memory_estimate(desc: ModelDesc, cfg: EngineConfig):
@@ -135,6 +153,14 @@ class Engine:
         self._ck(self._l.hb_model_load_finish(self._h))
         self.desc = desc
 
+    def load_broadcast(self, desc: ModelDesc, uid: bytes, rank: int, world: int):
+        """Replica load (hb_model_load_broadcast): rank 0 sends its loaded arena, the others receive it. Returns seconds."""
+        sec = C.c_double()
+        buf = C.create_string_buffer(bytes(uid), 128)
+        self._ck(self._l.hb_model_load_broadcast(self._h, C.byref(desc.to_c()), buf, rank, world, C.byref(sec)))
+        self.desc = desc
+        return sec.value
+
     def weights_arena(self):
         p, n = C.c_void_p(), C.c_size_t()
         self._ck(self._l.hb_model_weights_arena(self._h, C.byref(p), C.byref(n)))
@@ -181,6 +207,17 @@ class Engine:
         if rows.value:
             self._ck(self._l.hb_captured_logits(self._h, rid, which, out.ctypes.data, out.size, C.byref(rows)))
         return out
+
+    def logprobs(self, rid, first_row=0, max_rows=4096):
+        """(ids [rows, width], logprobs [rows, width]): column 0 = the sampled token, then the most likely tokens."""
+        rows, width = C.c_int32(), C.c_int32()
+        self._ck(self._l.hb_logprobs(self._h, rid, first_row, 0, None, None, C.byref(rows), C.byref(width)))
+        w = max(1, width.value)
+        ids = np.empty((max_rows, w), dtype=np.int32)
+        lps = np.empty((max_rows, w), dtype=np.float32)
+        self._ck(self._l.hb_logprobs(self._h, rid, first_row, max_rows, ids.ctypes.data, lps.ctypes.data, C.byref(rows),
+                                     C.byref(width)))
+        return ids[:rows.value], lps[:rows.value]
 
     def generate(self, prompts, sampling: Sampling):
         """Synchronous helper: drive hb_step on this thread until every prompt finished."""

@@ -12,7 +12,7 @@ from typing import Callable, List, Optional
 from . import configs
 from .engine import Engine, EngineConfig, HBError, ModelDesc, Sampling, memory_estimate
 
-VERSION = "helix-b200/0.1 (abi 1)"
+VERSION = "helix-b200/0.2 (abi 2)"
 DEFAULT_MAX_NUM_SEQS = 256  # types/memory.go:11 (vLLM default concurrency)
 
 

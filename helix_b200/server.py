@@ -169,9 +169,11 @@ class StopMatcher:
         return out
 
 
-def chat_chunk(cid, model, created, delta, finish_reason):
-    return {"id": cid, "object": "chat.completion.chunk", "created": created, "model": model,
-            "choices": [{"index": 0, "delta": delta, "finish_reason": finish_reason}]}
+def chat_chunk(cid, model, created, delta, finish_reason, index=0, logprobs=None):
+    c = {"index": index, "delta": delta, "finish_reason": finish_reason}
+    if logprobs is not None:
+        c["logprobs"] = logprobs
+    return {"id": cid, "object": "chat.completion.chunk", "created": created, "model": model, "choices": [c]}
 
 
 class OpenAIServer:
@@ -181,6 +183,18 @@ class OpenAIServer:
         self.host, self.port = host, port
         self.httpd = None
         self.batcher = None
+        self._active = 0                       # POST handlers in flight (stop() drains them before the engine goes away)
+        self._active_cv = threading.Condition()
+        self._stopping = False
+
+    def _enter(self):
+        with self._active_cv:
+            self._active += 1
+
+    def _leave(self):
+        with self._active_cv:
+            self._active -= 1
+            self._active_cv.notify_all()
 
     # ---- request handlers (pure functions of the parsed body: unit-testable without sockets)
     def models(self):
@@ -197,7 +211,9 @@ class OpenAIServer:
         else:
             raise ValueError("input must be a string, a list of strings or token arrays")
         vocab = self.rt.engine.desc.vocab
-        seqs = [[t % vocab for t in s][: self.rt.engine.cfg.max_ctx] for s in seqs]
+        if any(not isinstance(t, int) or isinstance(t, bool) or t < 0 or t >= vocab for s in seqs for t in s):
+            raise ValueError(f"input holds token ids outside [0, {vocab})")
+        seqs = [list(s)[: self.rt.engine.cfg.max_ctx] for s in seqs]
         if self.batcher is None:
             self.batcher = EmbedBatcher(self.rt.engine)
         vecs = self.batcher.embed(seqs)
@@ -205,69 +221,158 @@ class OpenAIServer:
                 "data": [{"object": "embedding", "index": i, "embedding": [float(x) for x in v]} for i, v in enumerate(vecs)],
                 "usage": {"prompt_tokens": sum(map(len, seqs)), "total_tokens": sum(map(len, seqs))}}
 
-    def _submit_chat(self, body):
+    def _parse_chat(self, body):
+        """Validates the request and returns (prompt ids, [Sampling per choice]).  Raises ValueError -> HTTP 400."""
         if body.get("model") and body["model"] != self.rt.p.model:
             raise ValueError(f"model mismatch, expecting {self.rt.p.model}")  # openai_chat_handlers.go:44-50
         msgs = body.get("messages")
-        ids = self.tok.chat(msgs) if msgs is not None else body["prompt"]
+        if msgs is not None:
+            if not isinstance(msgs, list) or not all(isinstance(m, dict) for m in msgs):
+                raise ValueError("messages must be a list of {role, content} objects")
+            ids = self.tok.chat(msgs)
+        else:
+            prompt = body.get("prompt")
+            if isinstance(prompt, str):          # /v1/completions with the standard string prompt
+                ids = self.tok.encode(prompt)
+            elif isinstance(prompt, list) and prompt and all(isinstance(t, int) and not isinstance(t, bool) for t in prompt):
+                ids = list(prompt)               # token-id array form
+            else:
+                raise ValueError("request needs `messages`, or `prompt` as a string or an array of token ids")
         vocab = self.rt.engine.desc.vocab
-        ids = [t % vocab for t in ids]
+        if not ids or any(t < 0 or t >= vocab for t in ids):
+            raise ValueError(f"prompt is empty or holds token ids outside [0, {vocab})")
         temp = body.get("temperature", 0.0) or 0.0   # the runner already rewrote 0 -> 0.1 (openai_chat_handlers.go:52-58)
-        sp = Sampling(temperature=float(temp), seed=int(body.get("seed", 0) or 0),
-                      max_tokens=int(body.get("max_tokens") or body.get("max_completion_tokens") or 256),
-                      eos_token=getattr(self.tok, "EOS", -1),
-                      top_p=float(body.get("top_p") or 1.0),      # openai.ChatCompletionRequest.TopP (nucleus)
-                      top_k=int(body.get("top_k") or 0))          # vLLM extension the reference's backend accepts
-        return self.rt.engine.submit(ids, sp), len(ids), sp
+        n = body.get("n")
+        n = 1 if n is None else n
+        if not isinstance(n, int) or isinstance(n, bool) or n < 1 or n > 16:
+            raise ValueError("n must be an integer in [1, 16]")
+        top_lp = body.get("top_logprobs")
+        want_lp = bool(body.get("logprobs")) or top_lp is not None
+        if top_lp is not None and not (isinstance(top_lp, int) and 0 <= top_lp <= 20):
+            raise ValueError("top_logprobs must be an integer in [0, 20]")
+        pres, freq = float(body.get("presence_penalty") or 0.0), float(body.get("frequency_penalty") or 0.0)
+        if not (-2.0 <= pres <= 2.0 and -2.0 <= freq <= 2.0):
+            raise ValueError("presence_penalty / frequency_penalty must be in [-2, 2]")
+        seed = int(body.get("seed", 0) or 0)
+        sps = [Sampling(temperature=float(temp), seed=seed + i,   # n > 1: one noise stream per choice
+                        max_tokens=int(body.get("max_tokens") or body.get("max_completion_tokens") or 256),
+                        eos_token=getattr(self.tok, "EOS", -1),
+                        top_p=float(body.get("top_p") or 1.0),      # openai.ChatCompletionRequest.TopP (nucleus)
+                        top_k=int(body.get("top_k") or 0),          # vLLM extension the reference's backend accepts
+                        logprobs=(1 + int(top_lp or 0)) if want_lp else 0,
+                        presence_penalty=pres, frequency_penalty=freq) for i in range(n)]
+        return ids, sps
+
+    def _lp_entry(self, ids, lps):
+        """One OpenAI `logprobs.content[]` element from a row of hb_logprobs (column 0 = the sampled token)."""
+        def one(t, lp):
+            text = self.tok.decode([int(t)]) if t >= 0 else ""
+            return {"token": text, "logprob": float(max(lp, -9999.0)), "bytes": list(text.encode("utf-8"))}
+        e = one(ids[0], lps[0])
+        e["top_logprobs"] = [one(t, lp) for t, lp in zip(ids[1:], lps[1:]) if t >= 0]
+        return e
 
     def chat_stream(self, body):
-        """Yields SSE chunk dicts; the last one carries finish_reason."""
+        """Generator of SSE chunk dicts; the last chunk of every choice carries its finish_reason, the very last one the
+        usage.  Validation and submission happen BEFORE the first yield (`next()` on the generator raises), so the HTTP
+        layer can still answer 4xx/5xx instead of an already-open 200 stream."""
         eng = self.rt.engine
-        rid, n_prompt, sp = self._submit_chat(body)
-        cid, created, model = "chatcmpl-" + uuid.uuid4().hex[:24], int(time.time()), self.rt.p.model
-        yield chat_chunk(cid, model, created, {"role": "assistant", "content": ""}, None)
-        n, fin = 0, 0
-        stop = StopMatcher(body.get("stop"))
-        dec = StreamDecoder(self.tok, skip=[sp.eos_token])
+        ids, sps = self._parse_chat(body)
+        rids = []
         try:
-            while not fin and not stop.hit:
-                eng.wait(rid, 30000)
-                toks, fin = eng.poll(rid)
-                if toks or fin:
-                    n += len(toks)
-                    text = stop.feed(dec.feed(toks, final=bool(fin)))
-                    if text:
-                        yield chat_chunk(cid, model, created, {"content": text}, None)
-            tail = stop.flush()
-            if tail:
-                yield chat_chunk(cid, model, created, {"content": tail}, None)
-            reason = "stop" if (stop.hit or n < sp.max_tokens) else "length"
-            last = chat_chunk(cid, model, created, {}, reason if (fin == 1 or stop.hit) else "stop")
-            last["usage"] = {"prompt_tokens": n_prompt, "completion_tokens": n, "total_tokens": n_prompt + n}
-            yield last
+            for sp in sps:
+                rids.append(eng.submit(ids, sp))
+        except Exception:
+            for r in rids:
+                self._retire(r, finished=False)
+            raise
+        return self._stream_choices(body, ids, sps, rids)
+
+    def _retire(self, rid, finished):
+        eng = self.rt.engine
+        try:
+            if not finished:
+                eng.cancel(rid)      # stop string hit / client gone / error: free the sequence's KV pages
+                for _ in range(200):  # the step loop retires it at the next step boundary
+                    if eng.poll(rid)[1]:
+                        break
+                    eng.wait(rid, 10)
+            eng.release(rid)
+        except HBError:
+            pass
+
+    def _stream_choices(self, body, ids, sps, rids):
+        eng = self.rt.engine
+        n_prompt = len(ids)
+        cid, created, model = "chatcmpl-" + uuid.uuid4().hex[:24], int(time.time()), self.rt.p.model
+        ch = [{"rid": r, "sp": sp, "n": 0, "fin": 0, "done": False, "lp_row": 0,
+               "stop": StopMatcher(body.get("stop")), "dec": StreamDecoder(self.tok, skip=[sp.eos_token])}
+              for r, sp in zip(rids, sps)]
+        try:
+            for i in range(len(ch)):
+                yield chat_chunk(cid, model, created, {"role": "assistant", "content": ""}, None, i)
+            while not all(c["done"] for c in ch):
+                first = next(c for c in ch if not c["done"])
+                eng.wait(first["rid"], 30000 if len(ch) == 1 else 5)
+                for i, c in enumerate(ch):
+                    if c["done"]:
+                        continue
+                    toks, fin = eng.poll(c["rid"])
+                    if not toks and not fin:
+                        continue
+                    c["n"] += len(toks)
+                    c["fin"] = fin
+                    text = c["stop"].feed(c["dec"].feed(toks, final=bool(fin)))
+                    lp = None
+                    if c["sp"].logprobs and toks:
+                        lid, lpv = eng.logprobs(c["rid"], c["lp_row"], len(toks))
+                        c["lp_row"] += len(lid)
+                        lp = {"content": [self._lp_entry(a, b) for a, b in zip(lid, lpv)]}
+                    if text or lp:
+                        yield chat_chunk(cid, model, created, {"content": text}, None, i, lp)
+                    if fin or c["stop"].hit:
+                        tail = c["stop"].flush()
+                        if tail:
+                            yield chat_chunk(cid, model, created, {"content": tail}, None, i)
+                        if fin == 2 and not c["stop"].hit:
+                            # the engine FAILED or CANCELLED the sequence: not a normal completion
+                            raise HBError(-2, "generation aborted by the engine: " + str(self.rt.status() or "engine stopped"))
+                        reason = "stop" if (c["stop"].hit or c["n"] < c["sp"].max_tokens) else "length"
+                        c["done"] = True
+                        self._retire(c["rid"], finished=bool(fin))   # a stop hit frees the sequence's KV pages now
+                        c["retired"] = True
+                        last = chat_chunk(cid, model, created, {}, reason, i)
+                        if all(x["done"] for x in ch):
+                            done_toks = sum(x["n"] for x in ch)
+                            last["usage"] = {"prompt_tokens": n_prompt, "completion_tokens": done_toks,
+                                             "total_tokens": n_prompt + done_toks}
+                        yield last
         finally:
-            try:
-                if not fin:
-                    eng.cancel(rid)      # stop string hit or client went away: free the sequence's KV pages
-                    for _ in range(200):  # the step loop retires it at the next step boundary
-                        if eng.poll(rid)[1]:
-                            break
-                        eng.wait(rid, 10)
-                eng.release(rid)
-            except HBError:
-                pass
+            for c in ch:
+                if not c.get("retired"):
+                    self._retire(c["rid"], finished=bool(c["fin"]))
 
     def chat(self, body):
-        text, reason, cid, usage = "", "stop", None, None
-        for ch in self.chat_stream(body):
-            cid = ch["id"]
-            c = ch["choices"][0]
-            text += c["delta"].get("content", "") or ""
-            reason = c["finish_reason"] or reason
-            usage = ch.get("usage", usage)
+        texts, reasons, lps = {}, {}, {}
+        cid, usage = None, None
+        for chk in self.chat_stream(body):
+            cid = chk["id"]
+            c = chk["choices"][0]
+            i = c["index"]
+            texts[i] = texts.get(i, "") + (c["delta"].get("content", "") or "")
+            if c.get("logprobs"):
+                lps.setdefault(i, []).extend(c["logprobs"]["content"])
+            if c["finish_reason"]:
+                reasons[i] = c["finish_reason"]
+            usage = chk.get("usage", usage)
+        choices = []
+        for i in sorted(texts):
+            one = {"index": i, "message": {"role": "assistant", "content": texts[i]}, "finish_reason": reasons.get(i, "stop")}
+            if i in lps:
+                one["logprobs"] = {"content": lps[i]}
+            choices.append(one)
         return {"id": cid, "object": "chat.completion", "created": int(time.time()), "model": self.rt.p.model,
-                "choices": [{"index": 0, "message": {"role": "assistant", "content": text}, "finish_reason": reason}],
-                "usage": usage or {"prompt_tokens": 0, "completion_tokens": 0, "total_tokens": 0}}
+                "choices": choices, "usage": usage or {"prompt_tokens": 0, "completion_tokens": 0, "total_tokens": 0}}
 
     # ---- socket plumbing
     def start(self):
@@ -296,34 +401,55 @@ class OpenAIServer:
                     self._json(404, {"error": "not found"})
 
             def do_POST(self):
+                srv._enter()
+                headers_sent = False
                 try:
                     n = int(self.headers.get("Content-Length", "0"))
                     if n > 10 * 1024 * 1024:   # openai_chat_handlers.go:40
                         return self._json(413, {"error": "request too large"})
                     body = json.loads(self.rfile.read(n) or b"{}")
+                    if not isinstance(body, dict):
+                        raise ValueError("request body must be a JSON object")
                     path = self.path.rstrip("/")
                     if path.endswith("/embeddings"):
                         return self._json(200, srv.embeddings(body))
                     if path.endswith("/chat/completions") or path.endswith("/completions"):
                         if not body.get("stream"):
                             return self._json(200, srv.chat(body))
+                        # validation + submission run before any byte of the response: errors are still real 4xx/5xx
+                        chunks = srv.chat_stream(body)
+                        first = next(chunks)
                         self.send_response(200)
                         self.send_header("Content-Type", "text/event-stream")
                         self.send_header("Cache-Control", "no-cache")
                         self.send_header("Connection", "close")
                         self.end_headers()
-                        for ch in srv.chat_stream(body):
+                        headers_sent = True
+                        self.close_connection = True
+                        self.wfile.write(b"data: " + json.dumps(first).encode() + b"\n\n")
+                        for ch in chunks:
                             self.wfile.write(b"data: " + json.dumps(ch).encode() + b"\n\n")
                             self.wfile.flush()
                         self.wfile.write(b"data: [DONE]\n\n")
                         self.wfile.flush()
-                        self.close_connection = True
                         return
                     self._json(404, {"error": "not found"})
-                except (ValueError, KeyError, HBError) as e:
-                    self._json(400, {"error": {"message": str(e), "type": "invalid_request_error"}})
                 except (BrokenPipeError, ConnectionResetError):
                     pass
+                except Exception as e:  # noqa: BLE001 — every failure must reach the client as an error, never a dropped socket
+                    bad_request = isinstance(e, (ValueError, KeyError, TypeError)) or (isinstance(e, HBError) and e.code in (-1, -5))
+                    err = {"error": {"message": str(e), "type": "invalid_request_error" if bad_request else "server_error"}}
+                    try:
+                        if headers_sent:   # the 200 is out: an SSE error event, then the connection closes without [DONE]
+                            self.wfile.write(b"data: " + json.dumps(err).encode() + b"\n\n")
+                            self.wfile.flush()
+                        else:
+                            busy = isinstance(e, HBError) and e.code == -6
+                            self._json(400 if bad_request else (429 if busy else 500), err)
+                    except (BrokenPipeError, ConnectionResetError):
+                        pass
+                finally:
+                    srv._leave()
 
         self.httpd = ThreadingHTTPServer((self.host, self.port), H)
         self.httpd.daemon_threads = True
@@ -331,7 +457,16 @@ class OpenAIServer:
         threading.Thread(target=self.httpd.serve_forever, daemon=True).start()
         return f"http://{self.host}:{self.port}"
 
-    def stop(self):
+    def stop(self, drain_s=10.0):
+        """Stops accepting connections and waits for in-flight handlers: they hold engine handles, and Runtime.Stop
+        destroys the engine right after this returns.  hb_engine_destroy wakes anything still parked in hb_wait."""
+        self._stopping = True
+        if self.httpd:
+            self.httpd.shutdown()
+        deadline = time.monotonic() + drain_s
+        with self._active_cv:
+            while self._active > 0 and time.monotonic() < deadline:
+                self._active_cv.wait(0.05)
         if self.batcher:
             self.batcher.close()
             self.batcher = None

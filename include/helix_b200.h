@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define HB_ABI_VERSION 1
+#define HB_ABI_VERSION 2
 
 typedef enum hb_status {
   HB_OK = 0,
@@ -63,7 +63,17 @@ typedef struct hb_engine_cfg {
                                    api/pkg/runner/vllm_runtime.go:705-762): full KV pages (64 tokens) are content-addressed; a new prompt
                                    whose leading pages are already in the pool (an earlier turn of the same chat, a
                                    shared system prompt) only prefills the rest */
-  int32_t reserved[6];
+  int32_t sm_budget;            /* SMs this ModelInstance may occupy (0 = the whole device).  Multi-model packing: the
+                                   scheduler places several slots on one GPU by memory (api/pkg/scheduler/global_allocator.go:349-452);
+                                   every persistent kernel of this engine sizes its grid to sm_budget so co-resident
+                                   engines run side by side on disjoint SMs instead of time-slicing whole kernels.  With
+                                   sm_partition != 0 the budget is also enforced by the hardware (CUDA green context). */
+  int32_t sm_partition;         /* 1: create the engine's stream inside a green context of sm_budget SMs */
+  int32_t stream_priority;      /* 0 default; 1 = high priority stream (small latency-bound models in a pack) */
+  int32_t decode_with_prefill;  /* 1 (what the runtime passes): running sequences decode inside prefill steps (vLLM-style
+                                   mixed batches) so a long prompt never stalls the streams; 0: prefill steps exclude
+                                   decode rows (benchmark-pure phases) */
+  int32_t reserved[2];
 } hb_engine_cfg;
 
 typedef struct hb_model_desc {
@@ -92,8 +102,14 @@ typedef struct hb_sampling {
                           (openai.ChatCompletionRequest, api/pkg/runner/openai_chat_handlers.go:100-175) */
   float top_p;         /* nucleus: smallest set of most likely tokens (after top_k) with softmax(logits/T) mass >= top_p;
                           values outside (0,1) (so also a zero-initialised struct): off */
-  int32_t reserved[1];
+  int32_t logprobs;    /* 0: off.  n >= 1: record, for every generated token, the log-probability of the chosen token and of
+                          the n-1 most likely alternatives (OpenAI `logprobs: true, top_logprobs: n-1`; n <= 21), read back
+                          with hb_logprobs.  Computed on the GPU from the penalised, un-tempered logits. */
+  float presence_penalty;  /* OpenAI presence_penalty: subtracted once from the logit of every token already generated */
+  float frequency_penalty; /* OpenAI frequency_penalty: subtracted per previous occurrence of the token in the output */
+  int32_t reserved2[4];
 } hb_sampling;
+#define HB_MAX_LOGPROBS 21
 
 #define HB_CAPTURE_NONE 0
 #define HB_CAPTURE_STEP_LOGITS 1   /* fp32 logits row of every generated token */
@@ -137,6 +153,19 @@ int hb_model_load_finish(hb_engine* e);
 int hb_model_load_random(hb_engine* e, const hb_model_desc* desc, uint64_t seed);
 /* device address/size of the contiguous weight arena: replicas receive it by one NCCL broadcast */
 int hb_model_weights_arena(hb_engine* e, void** dev_ptr, size_t* bytes);
+/* ---- replicas: one engine per GPU, weights loaded on rank 0 and copied to the others by ONE
+ *      ncclBroadcast of the arena over NVLink; nothing collective on the request path.  The reference's only multi-GPU
+ *      mechanism is the backend's own NCCL (api/pkg/runner/vllm_runtime.go:748-754); the Go host needs no NCCL binding:
+ *      it moves the 128-byte id between its per-GPU runtimes (same process) or runners.
+ *      hb_replica_unique_id: ncclGetUniqueId into id[HB_REPLICA_ID_BYTES] (call once, on the root).
+ *      hb_model_load_broadcast: every rank calls it with the same id/world.  rank 0 must already hold a loaded model
+ *      (hb_model_load_finish / hb_model_load_random) and sends; the other ranks must be freshly created engines: they
+ *      allocate the arena for `desc`, receive it and finish loading.  *seconds (optional) = duration of the broadcast
+ *      itself (communicator setup excluded).  libnccl.so.2 is opened on first use; HB_ERR_STATE if it is not installed. */
+#define HB_REPLICA_ID_BYTES 128
+int hb_replica_unique_id(void* id);
+int hb_model_load_broadcast(hb_engine* e, const hb_model_desc* desc, const void* id, int32_t rank, int32_t world,
+                            double* seconds);
 /* closed-form footprint for the scheduler's packing (weights + max_seqs*max_ctx KV + workspace) */
 int hb_memory_estimate(const hb_model_desc* desc, const hb_engine_cfg* cfg, uint64_t* weights, uint64_t* kv,
                        uint64_t* workspace);
@@ -153,7 +182,17 @@ int hb_release(hb_engine* e, uint64_t req_id); /* drop a finished request's reco
 /* parity tap: rows captured for req (see HB_CAPTURE_*), fp32 [rows][vocab] */
 int hb_captured_logits(hb_engine* e, uint64_t req_id, int32_t which, float* out, size_t cap_floats, int32_t* rows);
 
-/* ---- embeddings: nseq sequences, tokens[offsets[i]..offsets[i+1]) -> out[nseq][hidden] fp32 (CLS + L2) ---- */
+/* rows [first_row, first_row + max_rows) of the request's log-probability record (hb_sampling.logprobs = width):
+ * ids / logprobs are [rows][width], column 0 = the sampled token, columns 1.. = the most likely tokens in descending
+ * order.  *rows = rows written, *width = the request's width.  <- `logprobs` / `top_logprobs` of
+ * openai.ChatCompletionRequest, forwarded untouched by api/pkg/runner/openai_chat_handlers.go:100-175. */
+int hb_logprobs(hb_engine* e, uint64_t req_id, int32_t first_row, int32_t max_rows, int32_t* ids, float* logprobs,
+                int32_t* rows, int32_t* width);
+
+/* ---- embeddings: nseq sequences, tokens[offsets[i]..offsets[i+1]) -> out[nseq][hidden] fp32.
+ *      Encoder models (HB_ARCH_BERT): CLS row + L2.  Decoder models (HB_ARCH_LLAMA): last-token pooling of the final-norm
+ *      hidden state + L2 — the `--task embed` mode of the reference's default embedding model, a Qwen2-style decoder
+ *      (api/pkg/model/models.go:421-433); needs an engine that is not running generations concurrently. ---- */
 int hb_embed(hb_engine* e, const int32_t* tokens, const int32_t* offsets, int32_t nseq, float* out);
 
 int hb_get_stats(hb_engine* e, hb_stats* out);

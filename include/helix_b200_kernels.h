@@ -34,6 +34,13 @@ int hbk_sample(const float* logits, int ldl, const float* temperature, const uin
 /* as hbk_sample, restricted per row to the top_k / top_p survivors (either pointer may be NULL) */
 int hbk_sample_filtered(const float* logits, int ldl, const float* temperature, const uint64_t* seed, const int32_t* top_k,
                         const float* top_p, int32_t* out, int B, int V);
+/* OpenAI presence / frequency penalties: logits[b, tok] -= val over row b's entries {int32 tok; float val}
+ * [pen_off[b], pen_off[b+1]) (distinct tokens per row; val = presence + frequency * count, computed by the caller) */
+int hbk_apply_penalties(float* logits, int ldl, const int32_t* pen_off, const void* pen_entries, int B, int V);
+/* rows with width[b] > 0: out_ids/out_lp[b][0] = sampled[b] and its log-softmax; [1..width[b]) = the most likely tokens in
+ * descending order (lowest id first on ties).  out_* are [B][max_width]. */
+int hbk_logprob_topk(const float* logits, int ldl, int V, const int32_t* sampled, const int32_t* width, int32_t* out_ids,
+                     float* out_lp, int B, int max_width);
 int hbk_cls_pool_l2(const void* x, const int32_t* first_row, float* out, int B, int H);
 
 int hbk_attn_prefill(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,

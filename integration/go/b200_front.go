@@ -1,20 +1,21 @@
 // Package runner — openAIFront: what B200Runtime.URL() serves.  The reference's handlers build a go-openai client on
 // slot.URL()+"/v1" (openai_chat_handlers.go:100, openai_embedding_handlers.go:291, openai_model_handlers.go:36), so this
-// front speaks exactly that dialect: POST /v1/chat/completions (JSON, or SSE when stream=true: one `data: {chunk}`
-// per poll, a final chunk with a non-empty finish_reason, then `data: [DONE]`), POST /v1/embeddings, GET /v1/models.
-// Source only (no Go toolchain in this image); helix_b200/server.py is the executable mirror the tests drive.
+// front speaks exactly that dialect: POST /v1/chat/completions (JSON, or SSE when stream=true: `data: {chunk}` events, a
+// final chunk per choice with a non-empty finish_reason, then `data: [DONE]`), POST /v1/embeddings, GET /v1/models.
+// Pure Go over B200Runtime.Generate / Embed (no cgo in this file).  Source only (no Go toolchain in this image);
+// helix_b200/server.py is the executable mirror the tests drive over real sockets (tests/test_server_cpu.py).
 package runner
 
-/*
-#include "helix_b200.h"
-*/
-import "C"
-
 import (
+	"crypto/rand"
+	"encoding/hex"
 	"encoding/json"
+	"errors"
 	"fmt"
 	"net"
 	"net/http"
+	"strings"
+	"sync"
 	"time"
 
 	openai "github.com/sashabaranov/go-openai"
@@ -51,77 +52,276 @@ func newOpenAIFront(rt *B200Runtime) (*openAIFront, error) {
 }
 
 func (f *openAIFront) URL() string { return "http://" + f.ln.Addr().String() }
-func (f *openAIFront) Close()      { _ = f.srv.Close() }
+
+// Close stops accepting connections and closes the open ones; handlers notice through their request context and retire
+// their sequences (Generate cancels + releases) before B200Runtime.Stop destroys the engine.
+func (f *openAIFront) Close() { _ = f.srv.Close() }
+
+func randomID() string {
+	var b [12]byte
+	_, _ = rand.Read(b[:])
+	return hex.EncodeToString(b[:])
+}
+
+func derefInt(p *int) int {
+	if p == nil {
+		return 0
+	}
+	return *p
+}
+
+// dropToken returns ids without any occurrence of tok (the EOS id never reaches the visible text).
+func dropToken(ids []int32, tok int32) []int32 {
+	out := make([]int32, 0, len(ids))
+	for _, t := range ids {
+		if t != tok {
+			out = append(out, t)
+		}
+	}
+	return out
+}
+
+// decodeEmbeddingInput accepts the three forms the reference forwards (types/types.go:2707-2730):
+// "text" | ["text", ...] | [[id, ...], ...]; a flat [id, ...] is one sequence.
+func decodeEmbeddingInput(raw json.RawMessage, tok Tokenizer) ([][]int32, error) {
+	var s string
+	if json.Unmarshal(raw, &s) == nil {
+		return [][]int32{tok.Encode(s)}, nil
+	}
+	var ss []string
+	if json.Unmarshal(raw, &ss) == nil && len(ss) > 0 {
+		out := make([][]int32, len(ss))
+		for i, x := range ss {
+			out[i] = tok.Encode(x)
+		}
+		return out, nil
+	}
+	var flat []int32
+	if json.Unmarshal(raw, &flat) == nil && len(flat) > 0 {
+		return [][]int32{flat}, nil
+	}
+	var nested [][]int32
+	if json.Unmarshal(raw, &nested) == nil && len(nested) > 0 {
+		return nested, nil
+	}
+	return nil, errors.New("input must be a string, a list of strings or token arrays")
+}
 
 func (f *openAIFront) models(w http.ResponseWriter, _ *http.Request) {
 	_ = json.NewEncoder(w).Encode(openai.ModelsList{Models: []openai.Model{{ID: f.rt.p.Model, Object: "model", OwnedBy: "helix-b200"}}})
 }
 
+func jsonError(w http.ResponseWriter, code int, kind, msg string) {
+	w.Header().Set("Content-Type", "application/json")
+	w.WriteHeader(code)
+	_ = json.NewEncoder(w).Encode(map[string]any{"error": map[string]string{"message": msg, "type": kind}})
+}
+
+// firstStop returns the index of the earliest stop string in text, or -1.
+func firstStop(text string, stops []string) int {
+	cut := -1
+	for _, s := range stops {
+		if s == "" {
+			continue
+		}
+		if i := strings.Index(text, s); i >= 0 && (cut < 0 || i < cut) {
+			cut = i
+		}
+	}
+	return cut
+}
+
 func (f *openAIFront) chat(w http.ResponseWriter, r *http.Request) {
 	var req openai.ChatCompletionRequest
 	if err := json.NewDecoder(http.MaxBytesReader(w, r.Body, 10*1024*1024)).Decode(&req); err != nil { // openai_chat_handlers.go:40
-		http.Error(w, err.Error(), http.StatusBadRequest)
+		jsonError(w, http.StatusBadRequest, "invalid_request_error", err.Error())
 		return
 	}
 	if req.Model != "" && req.Model != f.rt.p.Model {
-		http.Error(w, fmt.Sprintf("model mismatch, expecting %s", f.rt.p.Model), http.StatusBadRequest)
+		jsonError(w, http.StatusBadRequest, "invalid_request_error", fmt.Sprintf("model mismatch, expecting %s", f.rt.p.Model))
+		return
+	}
+	nChoices := req.N
+	if nChoices == 0 {
+		nChoices = 1
+	}
+	if nChoices < 1 || nChoices > 16 || req.TopLogProbs < 0 || req.TopLogProbs > 20 {
+		jsonError(w, http.StatusBadRequest, "invalid_request_error", "n must be in [1,16], top_logprobs in [0,20]")
 		return
 	}
 	prompt := f.tok.EncodeChat(req.Messages)
+	if len(prompt) == 0 {
+		jsonError(w, http.StatusBadRequest, "invalid_request_error", "empty prompt")
+		return
+	}
 	maxTokens := req.MaxTokens
+	if maxTokens == 0 {
+		maxTokens = req.MaxCompletionTokens
+	}
 	if maxTokens == 0 {
 		maxTokens = 256
 	}
+	gp := GenParams{MaxTokens: maxTokens, Temperature: req.Temperature, TopP: req.TopP, Seed: uint64(derefInt(req.Seed)), EOS: f.tok.EOS(),
+		PresencePenalty: req.PresencePenalty, FrequencyPenalty: req.FrequencyPenalty}
+	if req.LogProbs {
+		gp.LogProbs = 1 + req.TopLogProbs
+	}
 	id, created := "chatcmpl-"+randomID(), time.Now().Unix()
-	chunk := func(delta openai.ChatCompletionStreamChoiceDelta, finish openai.FinishReason) openai.ChatCompletionStreamResponse {
-		return openai.ChatCompletionStreamResponse{ID: id, Object: "chat.completion.chunk", Created: created, Model: f.rt.p.Model,
-			Choices: []openai.ChatCompletionStreamChoice{{Index: 0, Delta: delta, FinishReason: finish}}}
+
+	// One goroutine per choice (n > 1: same prompt, seed + i; the prefix cache shares the prompt's KV pages).  All writes
+	// to the response go through `mu`; the headers of a stream go out with the first event, so a failure before any token
+	// is still a real 4xx/5xx.
+	type choiceState struct {
+		text   string
+		n      int
+		reason openai.FinishReason
+		lps    []openai.LogProb
+		err    error
 	}
-	var full string
-	n := 0
-	var all []int32 // every generated id so far: the text is decoded from the whole sequence (see emitStable)
-	emitted := 0
+	states := make([]choiceState, nChoices)
+	var mu sync.Mutex
+	headerSent := false
 	var flusher http.Flusher
-	if req.Stream {
-		w.Header().Set("Content-Type", "text/event-stream")
-		w.Header().Set("Cache-Control", "no-cache")
-		flusher, _ = w.(http.Flusher)
-		writeSSE(w, flusher, chunk(openai.ChatCompletionStreamChoiceDelta{Role: "assistant"}, ""))
-	}
-	fin, err := f.rt.Generate(r.Context(), prompt, maxTokens, req.Temperature, req.TopP, uint64(derefInt(req.Seed)), func(ids []int32) error {
-		n += len(ids)
-		all = append(all, dropToken(ids, f.tok.EOS())...)
-		// A character whose bytes / pieces straddle two polls must come out whole: decode everything, release only the
-		// new stable suffix, hold back a trailing U+FFFD (an incomplete sequence so far).  Mirrors server.py StreamDecoder.
-		text := emitStable(f.tok.Decode(all), &emitted, false)
-		full += text
-		if req.Stream && text != "" {
-			return writeSSE(w, flusher, chunk(openai.ChatCompletionStreamChoiceDelta{Content: text}, ""))
+	sendSSE := func(v any) error { // mu held
+		if !headerSent {
+			w.Header().Set("Content-Type", "text/event-stream")
+			w.Header().Set("Cache-Control", "no-cache")
+			flusher, _ = w.(http.Flusher)
+			headerSent = true
 		}
-		return nil
-	})
-	if err != nil && fin == 0 {
-		http.Error(w, err.Error(), http.StatusInternalServerError)
+		return writeSSE(w, flusher, v)
+	}
+	chunk := func(idx int, delta openai.ChatCompletionStreamChoiceDelta, finish openai.FinishReason) openai.ChatCompletionStreamResponse {
+		return openai.ChatCompletionStreamResponse{ID: id, Object: "chat.completion.chunk", Created: created, Model: f.rt.p.Model,
+			Choices: []openai.ChatCompletionStreamChoice{{Index: idx, Delta: delta, FinishReason: finish}}}
+	}
+	var wg sync.WaitGroup
+	for ci := 0; ci < nChoices; ci++ {
+		wg.Add(1)
+		go func(ci int) {
+			defer wg.Done()
+			st := &states[ci]
+			g := gp
+			g.Seed += uint64(ci)
+			var all []int32 // every generated id so far: text is decoded from the whole sequence (see emitStable)
+			emitted := 0
+			pending := ""  // decoded text not yet released because it may be the beginning of a stop string
+			stopped := false
+			release := func(text string, final bool) (string, bool) { // -> text that may be shown now, stop hit?
+				pending += text
+				if cut := firstStop(pending, req.Stop); cut >= 0 {
+					out := pending[:cut]
+					pending = ""
+					return out, true
+				}
+				if final {
+					out := pending
+					pending = ""
+					return out, false
+				}
+				keep := 0 // longest suffix that is a proper prefix of some stop string
+				for _, s := range req.Stop {
+					for k := len(s) - 1; k > keep; k-- {
+						if k <= len(pending) && strings.HasSuffix(pending, s[:k]) {
+							keep = k
+						}
+					}
+				}
+				out := pending[:len(pending)-keep]
+				pending = pending[len(pending)-keep:]
+				return out, false
+			}
+			errStop := errors.New("stop sequence")
+			started := false
+			fin, err := f.rt.Generate(r.Context(), prompt, g, func(ids []int32, lps []TokenLogProbs) error {
+				mu.Lock()
+				defer mu.Unlock()
+				if req.Stream && !started {
+					started = true
+					if err := sendSSE(chunk(ci, openai.ChatCompletionStreamChoiceDelta{Role: "assistant"}, "")); err != nil {
+						return err
+					}
+				}
+				st.n += len(ids)
+				all = append(all, dropToken(ids, f.tok.EOS())...)
+				for _, lp := range lps {
+					e := openai.LogProb{Token: f.tok.Decode(lp.IDs[:1]), LogProb: float64(lp.LogProbs[0])}
+					for k := 1; k < len(lp.IDs); k++ {
+						if lp.IDs[k] >= 0 {
+							e.TopLogProbs = append(e.TopLogProbs, openai.TopLogProbs{Token: f.tok.Decode(lp.IDs[k : k+1]), LogProb: float64(lp.LogProbs[k])})
+						}
+					}
+					st.lps = append(st.lps, e)
+				}
+				// A character whose bytes / pieces straddle two polls must come out whole: decode everything, release only
+				// the new stable suffix, hold back a trailing U+FFFD.  Mirrors server.py StreamDecoder + StopMatcher.
+				text, hit := release(emitStable(f.tok.Decode(all), &emitted, false), false)
+				st.text += text
+				if req.Stream && text != "" {
+					if err := sendSSE(chunk(ci, openai.ChatCompletionStreamChoiceDelta{Content: text}, "")); err != nil {
+						return err
+					}
+				}
+				if hit {
+					stopped = true
+					return errStop // Generate cancels the sequence (frees its KV pages) and releases the record
+				}
+				return nil
+			})
+			mu.Lock()
+			defer mu.Unlock()
+			if err != nil && !stopped {
+				st.err = err
+				return
+			}
+			if !stopped {
+				tail, _ := release(emitStable(f.tok.Decode(all), &emitted, true), true)
+				st.text += tail
+				if req.Stream && tail != "" {
+					_ = sendSSE(chunk(ci, openai.ChatCompletionStreamChoiceDelta{Content: tail}, ""))
+				}
+			}
+			st.reason = openai.FinishReasonStop
+			if !stopped && fin == 1 && st.n >= maxTokens {
+				st.reason = openai.FinishReasonLength
+			}
+			if req.Stream {
+				_ = sendSSE(chunk(ci, openai.ChatCompletionStreamChoiceDelta{}, st.reason)) // closes the control-plane stream (helix_openai_client.go:197)
+			}
+		}(ci)
+	}
+	wg.Wait()
+	var firstErr error
+	total := 0
+	for i := range states {
+		if states[i].err != nil && firstErr == nil {
+			firstErr = states[i].err
+		}
+		total += states[i].n
+	}
+	if firstErr != nil {
+		if headerSent { // the 200 is out: an SSE error event, no finish_reason / [DONE] — never "stop" on a truncated answer
+			_ = writeSSE(w, flusher, map[string]any{"error": map[string]string{"message": firstErr.Error(), "type": "server_error"}})
+		} else {
+			jsonError(w, http.StatusInternalServerError, "server_error", firstErr.Error())
+		}
 		return
 	}
-	if tail := emitStable(f.tok.Decode(all), &emitted, true); tail != "" { // whatever was still held back
-		full += tail
-		if req.Stream {
-			writeSSE(w, flusher, chunk(openai.ChatCompletionStreamChoiceDelta{Content: tail}, ""))
-		}
-	}
-	reason := openai.FinishReasonStop
-	if n >= maxTokens {
-		reason = openai.FinishReasonLength
-	}
 	if req.Stream {
-		writeSSE(w, flusher, chunk(openai.ChatCompletionStreamChoiceDelta{}, reason)) // closes the control-plane stream (helix_openai_client.go:197)
 		fmt.Fprint(w, "data: [DONE]\n\n")
 		return
 	}
-	_ = json.NewEncoder(w).Encode(openai.ChatCompletionResponse{ID: id, Object: "chat.completion", Created: created, Model: f.rt.p.Model,
-		Choices: []openai.ChatCompletionChoice{{Index: 0, Message: openai.ChatCompletionMessage{Role: "assistant", Content: full}, FinishReason: reason}},
-		Usage:   openai.Usage{PromptTokens: len(prompt), CompletionTokens: n, TotalTokens: len(prompt) + n}})
+	resp := openai.ChatCompletionResponse{ID: id, Object: "chat.completion", Created: created, Model: f.rt.p.Model,
+		Usage: openai.Usage{PromptTokens: len(prompt), CompletionTokens: total, TotalTokens: len(prompt) + total}}
+	for i := range states {
+		c := openai.ChatCompletionChoice{Index: i, Message: openai.ChatCompletionMessage{Role: "assistant", Content: states[i].text}, FinishReason: states[i].reason}
+		if req.LogProbs {
+			c.LogProbs = &openai.LogProbs{Content: states[i].lps}
+		}
+		resp.Choices = append(resp.Choices, c)
+	}
+	w.Header().Set("Content-Type", "application/json")
+	_ = json.NewEncoder(w).Encode(resp)
 }
 
 func (f *openAIFront) embeddings(w http.ResponseWriter, r *http.Request) {
@@ -129,32 +329,31 @@ func (f *openAIFront) embeddings(w http.ResponseWriter, r *http.Request) {
 		Input json.RawMessage `json:"input"` // string | []string | [][]int (types/types.go:2707-2730)
 		Model string          `json:"model"`
 	}
-	if err := json.NewDecoder(r.Body).Decode(&req); err != nil {
-		http.Error(w, err.Error(), http.StatusBadRequest)
+	if err := json.NewDecoder(http.MaxBytesReader(w, r.Body, 10*1024*1024)).Decode(&req); err != nil {
+		jsonError(w, http.StatusBadRequest, "invalid_request_error", err.Error())
 		return
 	}
 	seqs, err := decodeEmbeddingInput(req.Input, f.tok)
 	if err != nil {
-		http.Error(w, err.Error(), http.StatusBadRequest)
+		jsonError(w, http.StatusBadRequest, "invalid_request_error", err.Error())
 		return
 	}
-	// flatten -> one hb_embed call (a micro-batcher in front of this coalesces the RAG caller's 1-chunk requests)
-	var toks []int32
-	offs := []int32{0}
+	// one hb_embed call per request (a micro-batcher in front of this coalesces the RAG caller's 1-chunk requests,
+	// helix_b200/server.py EmbedBatcher)
+	vecs, err := f.rt.Embed(seqs)
+	if err != nil {
+		jsonError(w, http.StatusBadRequest, "invalid_request_error", err.Error())
+		return
+	}
+	nTok := 0
 	for _, s := range seqs {
-		toks = append(toks, s...)
-		offs = append(offs, int32(len(toks)))
+		nTok += len(s)
 	}
-	hidden := int(f.rt.p.Desc.hidden)
-	out := make([]float32, len(seqs)*hidden)
-	if rc := C.hb_embed(f.rt.eng, (*C.int32_t)(&toks[0]), (*C.int32_t)(&offs[0]), C.int32_t(len(seqs)), (*C.float)(&out[0])); rc != C.HB_OK {
-		http.Error(w, f.rt.lastError().Error(), http.StatusInternalServerError)
-		return
+	resp := openai.EmbeddingResponse{Object: "list", Model: openai.EmbeddingModel(f.rt.p.Model), Usage: openai.Usage{PromptTokens: nTok, TotalTokens: nTok}}
+	for i := range vecs {
+		resp.Data = append(resp.Data, openai.Embedding{Object: "embedding", Index: i, Embedding: vecs[i]})
 	}
-	resp := openai.EmbeddingResponse{Object: "list", Model: openai.EmbeddingModel(f.rt.p.Model), Usage: openai.Usage{PromptTokens: len(toks), TotalTokens: len(toks)}}
-	for i := range seqs {
-		resp.Data = append(resp.Data, openai.Embedding{Object: "embedding", Index: i, Embedding: out[i*hidden : (i+1)*hidden]})
-	}
+	w.Header().Set("Content-Type", "application/json")
 	_ = json.NewEncoder(w).Encode(resp)
 }
 

@@ -92,8 +92,17 @@ class LlamaOracle:
             x = x + hmid @ sd[p + "mlp.down_proj.weight"].T
         self.len += n
         x = rmsnorm(x, sd["model.norm.weight"], d.norm_eps)
+        self.last_hidden = x.astype(np.float32)  # final-norm hidden states of the new positions (decoder-embedder pooling)
         head = sd["model.embed_tokens.weight"] if d.tie_embeddings else sd["lm_head.weight"]
         return (x @ head.T).astype(np.float32)
+
+    def embed(self, tokens):
+        """`--task embed` pooling of a decoder embedder (the reference's default embedding model is one:
+        api/pkg/model/models.go:421-433; vLLM pools the LAST token's final hidden state and L2-normalises it)."""
+        self.reset()
+        self.forward(tokens)
+        h = self.last_hidden[-1]
+        return h / max(float(np.linalg.norm(h)), 1e-12)
 
     def greedy(self, prompt, max_tokens):
         """Returns (token ids, logits rows [max_tokens, vocab]) of greedy decoding (argmax, lowest index on ties)."""

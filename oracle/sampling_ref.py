@@ -37,3 +37,25 @@ def threshold(logits, temperature, top_k=0, top_p=1.0):
     """The logit value below which tokens are dropped (-inf if nothing is): what sample_threshold_kernel returns."""
     m = keep_mask(logits, temperature, top_k, top_p)
     return -np.inf if m.all() else float(np.asarray(logits, dtype=np.float64)[m].min())
+
+
+def penalised(logits, generated, presence=0.0, frequency=0.0):
+    """OpenAI presence / frequency penalties (the request fields openai.ChatCompletionRequest carries; the reference
+    forwards them to its backend untouched, api/pkg/runner/openai_chat_handlers.go:100-175), as vLLM applies them
+    (vllm/model_executor/layers/utils.py `apply_penalties`, output tokens only):
+        logits[t] -= frequency * count(t in generated) + presence * [count > 0]"""
+    x = np.asarray(logits, dtype=np.float64).copy()
+    toks, cnt = np.unique(np.asarray(generated, dtype=np.int64), return_counts=True)
+    if len(toks):
+        x[toks] -= frequency * cnt + presence
+    return x
+
+
+def logprob_record(logits, sampled, width):
+    """What hb_logprobs returns for one generated token: (ids, log-probabilities), column 0 = the sampled token, then the
+    width-1 most likely tokens in descending order (lowest id first on ties); log-softmax in float64."""
+    x = np.asarray(logits, dtype=np.float64)
+    lse = x.max() + np.log(np.exp(x - x.max()).sum())
+    order = np.lexsort((np.arange(len(x)), -x))[: max(0, width - 1)]
+    ids = np.concatenate([[sampled], order]).astype(np.int64)
+    return ids, x[ids] - lse

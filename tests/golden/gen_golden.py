@@ -101,7 +101,47 @@ def gen_bert(name, d, seed, lens, std=0.05):
     print(name, "embeddings", np.stack(embs).shape)
 
 
+def gen_llama_fullshape(name, d, seed, n_prompt, n_decode, std=0.02, col_stride=31, rows=(0, 1, 63, 64, 255, 510, 511)):
+    """A BASELINE-shape case (full hidden / heads / ffn / 128256 vocab, few layers).  Full logit rows would be 0.5 MB
+    each, so the fixture keeps every `col_stride`-th vocabulary column of selected prompt rows and of every decode row,
+    plus each row's exact argmax and max value (the quantities parity is judged on)."""
+    sd = weights.llama_state_dict(d, seed, std)
+    m = hf_llama(d, sd)
+    del sd
+    prompt = weights.random_tokens(seed + 1, n_prompt, d.vocab)
+    ids = torch.from_numpy(prompt.astype(np.int64))[None]
+    out = m(ids, use_cache=True)
+    pl = out.logits[0]
+    rows = [r for r in rows if r < n_prompt]
+    cols = np.arange(0, d.vocab, col_stride)
+    past = out.past_key_values
+    logits = pl[-1]
+    toks, srows = [], []
+    for _ in range(n_decode):
+        srows.append(logits.numpy().copy())
+        t = int(torch.argmax(logits))
+        toks.append(t)
+        o = m(torch.tensor([[t]]), past_key_values=past, use_cache=True)
+        past = o.past_key_values
+        logits = o.logits[0, -1]
+    srows = np.stack(srows)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed=seed, std=std, layers=d.layers, prompt=prompt,
+                        rows=np.array(rows, np.int32), cols=cols.astype(np.int32),
+                        prompt_logits=pl[rows][:, cols].numpy().astype(np.float32),
+                        prompt_argmax=pl.argmax(-1).numpy().astype(np.int32), prompt_max=pl.max(-1).values.numpy().astype(np.float32),
+                        prompt_absmax=pl.abs().max(-1).values.numpy().astype(np.float32),
+                        greedy_tokens=np.array(toks, np.int32), step_logits=srows[:, cols].astype(np.float32),
+                        step_max=srows.max(-1).astype(np.float32))
+    print(name, "greedy", toks)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "full":  # the two BASELINE-shape fixtures (minutes, ~10 GB of RAM)
+        gen_bert("bge_base_full", configs.bge_base(), 2, [512, 1, 64, 129, 300, 511], 0.02)
+        d8 = configs.llama3_8b()
+        d8.layers = 2
+        gen_llama_fullshape("llama3_8b_2layer", d8, 4, 512, 8)
+        sys.exit(0)
     gen_llama("llama_tiny_d64", configs.tiny_llama(layers=2, head_dim=64, vocab=1000), 0, 48, 12, 0.02)
     gen_llama("llama_tiny_d64_s05", configs.tiny_llama(layers=2, head_dim=64, vocab=1000), 0, 48, 12, 0.05)
     gen_llama("llama_tiny_d128_rope3", configs.tiny_llama(layers=3, head_dim=128, vocab=1000, rope_scaling=True), 3, 200, 8, 0.05)

@@ -26,13 +26,13 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in sorted(decl) if not hasattr(l, n)]
     assert not missing, missing
     assert decl == set(_lib.SIGNATURES), (decl ^ set(_lib.SIGNATURES))
-    assert l.hb_abi_version() == 1
+    assert l.hb_abi_version() == 2
 
 
 def test_struct_sizes_match_header_layout():
     import ctypes as C
     assert C.sizeof(_lib.EngineCfg) == 64 and C.sizeof(_lib.ModelDescC) == 100
-    assert C.sizeof(_lib.SamplingC) == 40
+    assert C.sizeof(_lib.SamplingC) == 64
 
 
 def test_ctypes_layouts_match_the_c_header_field_by_field(tmp_path):

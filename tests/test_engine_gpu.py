@@ -1,6 +1,7 @@
 """GPU parity of the whole hot path through the engine C ABI (include/helix_b200.h) against the oracle
 and the committed HF golden fixtures.  Tolerance (bf16 activations vs fp32 oracle, stated per north_star):
-per-token logit max-abs-diff <= 3e-2 * max(1, ||logits||_inf); token ids bit-exact wherever the oracle's
+per-token logit max-abs-diff <= 2e-2 * max(1, ||logits||_inf) (the measured worst case is
+about a third of it, see tests/test_baseline_shapes_gpu.py which prints and ratchets the ratio); token ids bit-exact wherever the oracle's
 top-1 margin exceeds twice that bound."""
 import os
 
@@ -24,7 +25,7 @@ LLAMA_CASES = {
 
 
 def tol(ref):
-    return 3e-2 * max(1.0, float(np.abs(ref).max()))
+    return 2e-2 * max(1.0, float(np.abs(ref).max()))
 
 
 def check_tokens_against(oracle, prompt, toks, rows):

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def test_config1_llama32_1b_full_model_vs_oracle():
     """configs[0]: single chat request, 128-token prefill + 32-token decode, Llama-3.2-1B shape (16 layers, head_dim 64,
     GQA 32/8, tied 128256-row LM head, llama3 rope scaling), seeded random init — CUDA path vs the fp32 CPU oracle.
-    Tolerance: per-token logit max-abs-diff <= 3e-2*max(1,|logits|_inf); token ids exact outside near-ties."""
+    Tolerance: per-token logit max-abs-diff <= 2e-2*max(1,|logits|_inf); token ids exact outside near-ties."""
     d = configs.llama32_1b()
     sd = weights.llama_state_dict(d, 0, 0.02)
     prompt = weights.random_tokens(1, 128, d.vocab)
@@ -27,14 +27,15 @@ def test_config1_llama32_1b_full_model_vs_oracle():
     logits = o.forward(prompt)[-1]
     worst = 0.0
     for i, t in enumerate(outs[0]):  # teacher-forced on the engine's tokens
-        bound = 3e-2 * max(1.0, float(np.abs(logits).max()))
+        bound = 2e-2 * max(1.0, float(np.abs(logits).max()))
         diff = float(np.abs(got[i] - logits).max())
         worst = max(worst, diff / bound)
         assert diff <= bound, (i, diff, bound)
         best = int(np.argmax(logits))
         assert t == best or logits[best] - logits[t] <= 2 * bound, (i, t, best)
         logits = o.forward([t])[-1]
-    assert len(outs[0]) == 32 and worst < 1.0
+    print(f"\n[L1B config-1] worst |dlogit|/bound = {worst:.3f}")
+    assert len(outs[0]) == 32 and worst < 0.6  # ratchet: ~2x the measured ratio
 
 
 def test_llama3_8b_prefill_and_decode_paths_agree_at_full_size():
@@ -56,8 +57,8 @@ def test_llama3_8b_prefill_and_decode_paths_agree_at_full_size():
     assert lb.shape == (n + 2, d.vocab)
     scale = max(1.0, float(np.abs(lb[n - 1:]).max()))
     assert np.abs(la[0] - lb[n - 1]).max() <= 1e-2 * scale          # same path (prefill) both times: only batching differs
-    assert np.abs(la[1] - lb[n]).max() <= 3e-2 * scale              # decode path vs prefill path
-    assert np.abs(la[2] - lb[n + 1]).max() <= 3e-2 * scale
+    assert np.abs(la[1] - lb[n]).max() <= 2e-2 * scale              # decode path vs prefill path
+    assert np.abs(la[2] - lb[n + 1]).max() <= 2e-2 * scale
     assert np.isfinite(lb).all() and st["kv_pages_free"] == st["kv_pages_total"]
 
 

@@ -47,3 +47,35 @@ def test_bert_oracle_matches_hf(golden_dir):
     e = bert_embed(d, sd, seqs)
     assert np.abs(e - g["embeddings"]).max() < 2e-5
     assert np.allclose(np.linalg.norm(e, axis=1), 1.0, atol=1e-5)
+
+
+def test_bert_oracle_matches_hf_at_the_full_bge_base_shape(golden_dir):
+    """BASELINE configs[2] shape (12 x 768 x 3072, 512 positions): the oracle is pinned to HF there too, not only on the
+    tiny config."""
+    g = np.load(os.path.join(golden_dir, "bge_base_full.npz"))
+    d = configs.bge_base()
+    sd = weights.bert_state_dict(d, int(g["seed"]), float(g["std"]))
+    lens = g["lens"].tolist()
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    seqs = [g["tokens"][offs[i]:offs[i + 1]] for i in range(len(lens))]
+    e = bert_embed(d, sd, seqs)
+    assert np.abs(e - g["embeddings"]).max() < 5e-5
+
+
+def test_llama_oracle_matches_hf_at_the_llama3_8b_shape(golden_dir):
+    """BASELINE configs[1] kernel shapes (hidden 4096, 32/8 heads x 128, ffn 14336, vocab 128256; 2 layers): sampled logit
+    rows / columns, every row's argmax and max, and the greedy continuation against HF transformers fp32."""
+    g = np.load(os.path.join(golden_dir, "llama3_8b_2layer.npz"))
+    d = configs.llama3_8b()
+    d.layers = int(g["layers"])
+    o = LlamaOracle(d, weights.llama_state_dict(d, int(g["seed"]), float(g["std"])))
+    prompt = g["prompt"]
+    assert np.array_equal(prompt, weights.random_tokens(int(g["seed"]) + 1, len(prompt), d.vocab))
+    logits = o.forward(prompt)
+    rows, cols = g["rows"], g["cols"]
+    assert np.abs(logits[rows][:, cols] - g["prompt_logits"]).max() < 5e-4
+    assert np.abs(logits.max(-1) - g["prompt_max"]).max() < 5e-4
+    assert np.array_equal(logits.argmax(-1), g["prompt_argmax"])
+    toks, srows = o.greedy(prompt, len(g["greedy_tokens"]))
+    assert toks == g["greedy_tokens"].tolist()
+    assert np.abs(srows[:, cols] - g["step_logits"]).max() < 5e-4

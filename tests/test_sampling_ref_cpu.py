@@ -41,3 +41,28 @@ def test_edge_cases():
     lg = np.log(np.array([0.4, 0.3, 0.2, 0.1]))
     assert S.keep_mask(lg, 1.0, top_p=0.75).tolist() == [True, True, True, False]
     assert S.threshold(lg, 1.0, top_p=0.75) == lg[2] and S.threshold(lg, 1.0) == -np.inf
+
+
+def test_penalties_and_logprob_record_against_brute_force():
+    """Pins oracle/sampling_ref.penalised and logprob_record to plain-loop statements of the OpenAI definitions."""
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        V = int(rng.integers(3, 40))
+        x = rng.normal(size=V) * 3
+        gen = rng.integers(0, V, size=int(rng.integers(0, 30))).tolist()
+        pres, freq = float(rng.uniform(-2, 2)), float(rng.uniform(-2, 2))
+        want = x.copy()
+        for t in range(V):
+            c = gen.count(t)
+            if c:
+                want[t] -= pres + freq * c
+        assert np.allclose(S.penalised(x, gen, pres, freq), want, atol=1e-12)
+        w = int(rng.integers(1, min(V, 21) + 1))
+        t = int(rng.integers(0, V))
+        ids, lps = S.logprob_record(x, t, w)
+        probs = np.exp(x) / np.exp(x).sum()
+        assert ids[0] == t and np.isclose(lps[0], np.log(probs[t]))
+        rest = sorted(range(V), key=lambda i: (-x[i], i))[: w - 1]
+        assert ids[1:].tolist() == rest and np.allclose(lps[1:], np.log(probs[rest]))
+    ids, _ = S.logprob_record(np.array([1.0, 3.0, 3.0, 0.0]), 3, 3)
+    assert ids.tolist() == [3, 1, 2]   # ties: lowest id first

@@ -46,6 +46,14 @@ class FakeEngine:
         fin = 1 if (r["pos"] >= r["sp"].max_tokens or r["pos"] >= len(self.script)) else 0
         return toks, fin
 
+    def logprobs(self, rid, first_row, max_rows):
+        r = self.reqs[rid]
+        w = r["sp"].logprobs
+        rows = self.script[first_row:min(r["pos"], first_row + max_rows)]
+        ids = np.array([[t] + [t + 1 + j for j in range(w - 1)] for t in rows], np.int32).reshape(len(rows), w)
+        lps = np.array([[-0.5] + [-1.0 - j for j in range(w - 1)] for _ in rows], np.float32).reshape(len(rows), w)
+        return ids, lps
+
     def cancel(self, rid):
         self.reqs[rid]["cancelled"] = True
         self.cancelled.append(rid)
@@ -212,3 +220,83 @@ def test_stream_decoder_and_stop_matcher_properties():
         assert out == (text if first < 0 else text[:first])
 
     prop()
+
+
+def test_n_choices_logprobs_and_penalties_reach_the_engine(front):
+    """Request fields the runner forwards untouched (openai_chat_handlers.go:100-175): n, logprobs/top_logprobs,
+    presence/frequency penalties — one engine submission per choice with its own seed, OpenAI-shaped logprobs back."""
+    rt, base = front
+    r = post(base, "/v1/chat/completions", {"model": "tiny", "max_tokens": 4, "n": 2, "seed": 5, "logprobs": True,
+                                            "top_logprobs": 2, "presence_penalty": 0.5, "frequency_penalty": -0.25,
+                                            "messages": [{"role": "user", "content": "hi"}]})
+    assert [c["index"] for c in r["choices"]] == [0, 1]
+    assert all(c["message"]["content"] == "Hell" and c["finish_reason"] == "length" for c in r["choices"])
+    sps = [rt.engine.reqs[i]["sp"] for i in (1, 2)]
+    assert [sp.seed for sp in sps] == [5, 6] and all(sp.logprobs == 3 for sp in sps)
+    assert all(sp.presence_penalty == 0.5 and sp.frequency_penalty == -0.25 for sp in sps)
+    lp = r["choices"][0]["logprobs"]["content"]
+    assert [e["token"] for e in lp] == list("Hell") and all(e["logprob"] == -0.5 and len(e["top_logprobs"]) == 2 for e in lp)
+    assert lp[0]["bytes"] == [ord("H")] and lp[0]["top_logprobs"][0]["logprob"] == -1.0
+    assert r["usage"]["completion_tokens"] == 8 and sorted(rt.engine.released) == [1, 2]
+    # streaming: chunks carry the choice index; each choice ends with its own finish_reason, [DONE] closes the stream
+    raw = post(base, "/v1/chat/completions", {"model": "tiny", "max_tokens": 4, "n": 2, "stream": True,
+                                              "messages": [{"role": "user", "content": "hi"}]}, raw=True)
+    chunks = [json.loads(e[6:]) for e in raw.split("\n\n") if e and e != "data: [DONE]"]
+    fins = [(c["choices"][0]["index"], c["choices"][0]["finish_reason"]) for c in chunks if c["choices"][0]["finish_reason"]]
+    assert sorted(fins) == [(0, "length"), (1, "length")] and "usage" in chunks[-1]
+    for bad in ({"n": 0}, {"n": 99}, {"top_logprobs": 21}, {"presence_penalty": 3}):
+        with pytest.raises(urllib.error.HTTPError) as e:
+            post(base, "/v1/chat/completions", dict({"model": "tiny", "messages": [{"role": "user", "content": "x"}]}, **bad))
+        assert e.value.code == 400
+
+
+def test_completions_prompt_forms_and_id_validation(front):
+    rt, base = front
+    r = post(base, "/v1/completions", {"model": "tiny", "prompt": "hello", "max_tokens": 3})      # standard string prompt
+    assert r["choices"][0]["message"]["content"] == "Hel" and rt.engine.reqs[1]["n_prompt"] == 6  # BOS + 5 bytes
+    r = post(base, "/v1/completions", {"model": "tiny", "prompt": [5, 6, 7], "max_tokens": 3})     # token-id array
+    assert rt.engine.reqs[2]["n_prompt"] == 3
+    for bad in ({"prompt": [5, 100000]}, {"prompt": [1.5]}, {"prompt": None}, {"messages": "hi"}, {}):
+        with pytest.raises(urllib.error.HTTPError) as e:
+            post(base, "/v1/completions", dict({"model": "tiny"}, **bad))
+        assert e.value.code == 400, bad                       # never a dropped connection, never a silent id wrap
+    with pytest.raises(urllib.error.HTTPError) as e:
+        post(base, "/v1/embeddings", {"model": "tiny", "input": [[5, 100000]]})
+    assert e.value.code == 400
+
+
+def test_stream_errors_are_real_http_errors_and_engine_failures_are_not_stop(front):
+    """Validation / submission failures of a stream:true request happen before the 200 + event-stream headers, so the
+    client sees a real 4xx/5xx; once the stream is open an engine-side abort becomes an SSE error event without a
+    finish_reason chunk or [DONE] — never `finish_reason: "stop"` on a truncated answer."""
+    rt, base = front
+    with pytest.raises(urllib.error.HTTPError) as e:
+        post(base, "/v1/chat/completions", {"model": "other", "stream": True, "messages": []}, raw=True)
+    assert e.value.code == 400
+    orig = rt.engine.submit
+
+    def full(ids, sp):
+        raise HBError(-6, "queue full")
+    rt.engine.submit = full
+    with pytest.raises(urllib.error.HTTPError) as e:
+        post(base, "/v1/chat/completions", {"model": "tiny", "stream": True, "messages": [{"role": "user", "content": "x"}]}, raw=True)
+    assert e.value.code == 429
+    rt.engine.submit = orig
+    polls = {"n": 0}
+    orig_poll = rt.engine.poll
+
+    def failing_poll(rid):
+        polls["n"] += 1
+        if polls["n"] >= 3:
+            return [], 2          # engine FAILED / CANCELLED the sequence
+        return orig_poll(rid)
+    rt.engine.poll = failing_poll
+    raw = post(base, "/v1/chat/completions", {"model": "tiny", "stream": True, "max_tokens": 100,
+                                              "messages": [{"role": "user", "content": "x"}]}, raw=True)
+    events = [json.loads(e[6:]) for e in raw.split("\n\n") if e.startswith("data: {")]
+    assert "error" in events[-1] and "data: [DONE]" not in raw
+    assert all(ev["choices"][0]["finish_reason"] is None for ev in events[:-1])
+    with pytest.raises(urllib.error.HTTPError) as e:   # same failure without streaming: a 500, not a 200 with finish "stop"
+        polls["n"] = 0
+        post(base, "/v1/chat/completions", {"model": "tiny", "max_tokens": 100, "messages": [{"role": "user", "content": "x"}]})
+    assert e.value.code == 500
