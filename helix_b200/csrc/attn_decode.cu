@@ -16,6 +16,8 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 #include "launch.h"
 #include "ptx.cuh"
@@ -55,7 +57,9 @@ __global__ void __launch_bounds__(kThreads, 2)
 attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                    const bf16* __restrict__ q, int ldq, const int32_t* __restrict__ page_table, int max_pages,
                    const int32_t* __restrict__ ctx_lens, float* __restrict__ ws, int Hkv, int num_splits,
-                   float scale_log2, bf16* __restrict__ out_direct, int ldo) {
+                   float scale_log2, bf16* __restrict__ out_direct, int ldo, const int* sig_wait, int sig_wait_count,
+                   int* sig_done, int bank_tiles, const bf16* __restrict__ k_cache, const bf16* __restrict__ v_cache,
+                   unsigned long long* trace) {
   using C = DCfg<D>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -80,6 +84,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
   // the barriers / TMEM are set up while the predecessor is still draining; griddepcontrol.wait sits right in front of
   // the first dependent access of each role.
   pdl_launch_dependents();
+  if (blockIdx.x | blockIdx.y | blockIdx.z) trace = nullptr;
+  if (threadIdx.x == 0) trace_ev(trace, 0);
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ctx = ctx_lens[b];
@@ -92,6 +98,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
   if (t_begin >= t_end) {
     pdl_wait();  // ws may still be read by an earlier launch's combine pass
     for (int i = threadIdx.x; i < G * (D + 2); i += kThreads) ws_base[i] = (i % (D + 2) == D) ? -INFINITY : 0.f;
+    if (threadIdx.x == 0) sig_add(sig_done);  // every CTA reports, also one without work
     return;
   }
   const int n_tiles = t_end - t_begin;
@@ -151,6 +158,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
           }
         }
       }
+      if (elected) { sig_add(sig_done); trace_ev(trace, 5); }  // this CTA's HBM demand ends here
     }
   } else if (warp == 1) {
     const bool elected = elect_one_sync();
@@ -177,6 +185,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
       };
       mbar_wait(q_ready, 0);
       issue_s(0);
+      if (elected) trace_ev(trace, 4);
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) issue_s(j + 1);
         const int item = 2 * j + 1, s = item % STAGES;
@@ -200,8 +209,31 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
     const int qd = warp & 3;
     const int t = qd * 32 + lane;  // kv position within the tile (S^T lane) / head-dim index (O^T lane)
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
+    // HBM hand-over (ptx.cuh sig_*): tiles 0 and 1 are already on their way into the ring.  Once the previous streaming
+    // kernel has issued its last load, these (still idle) warps pull the next `bank_tiles` K/V tiles into L2, one 128-byte
+    // line of each page per thread, so HBM keeps working while this kernel waits for its q.
+    if (bank_tiles > 0 && n_tiles > 2) {
+      if (lane == 0) sig_wait_ge(sig_wait, sig_wait_count);
+      __syncwarp();
+      constexpr int LINES = PAGE * D * 2 / 128;  // 128-byte lines per (page, kv head) block
+      const int j_end = min(n_tiles, 2 + bank_tiles);
+      for (int jj = 2; jj < j_end; ++jj) {
+        const int p0 = (t_begin + jj) * 2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int pg = pt[min(p0 + h, n_pages - 1)];
+          const size_t off = ((size_t)pg * Hkv + kvh) * PAGE * D + (size_t)t * 64;
+          if (t < LINES) {
+            prefetch_l2_line(k_cache + off);
+            prefetch_l2_line(v_cache + off);
+          }
+        }
+      }
+    }
     // ---- stage Q^T (G rows of D, rows G..15 zero) into the K-major swizzled B-operand layout; zero P
+    if (t == 0) trace_ev(trace, 2);
     pdl_wait();  // q is written by the predecessor; so is nothing else this role reads
+    if (t == 0) trace_ev(trace, 3);
     {
       const bf16* qsrc = q + (size_t)b * ldq + (size_t)kvh * G * D;
       constexpr int CH = D / 8;  // 16-byte chunks per row
@@ -327,6 +359,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
       }
     }
   }
+  if (threadIdx.x == 64) trace_ev(trace, 7);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -375,9 +408,12 @@ cudaError_t launch(cudaStream_t stream, const AttnDecodeArgs& a) {
   if (!make_tmap_3d(&mv, a.v_cache, TM_BF16, D, PAGE, blocks, (uint64_t)D * 2, (uint64_t)PAGE * D * 2, 64, PAGE, 1)) return cudaErrorInvalidValue;
   dim3 grid(a.num_splits, a.Hkv, a.B);
   bf16* direct = a.num_splits == 1 ? a.out : nullptr;  // one split per (sequence, kv head): no partials to merge
+  const size_t ctas = (size_t)a.num_splits * a.Hkv * a.B;
+  const int bank_tiles = (int)std::min<size_t>(a.sig.bank_bytes / (ctas * 2 * DCfg<D>::KV_BYTES), 64);
   cudaError_t e = launch_k(attn_decode_kernel<D, G>, grid, dim3(kThreads), DCfg<D>::SMEM, stream, true, mk, mv, a.q, a.ldq,
                            a.page_table, a.max_pages, a.ctx_lens, a.workspace, a.Hkv, a.num_splits,
-                           a.scale * 1.4426950408889634f, direct, a.ldo);
+                           a.scale * 1.4426950408889634f, direct, a.ldo, a.sig.wait, a.sig.wait_count, a.sig.done, bank_tiles,
+                           a.k_cache, a.v_cache, a.sig.trace);
   if (e != cudaSuccess || direct) return e;
   return launch_k(attn_decode_combine_kernel<D>, dim3(a.Hq, a.B), dim3(D / 2), 0, stream, true,
                   (const float*)a.workspace, a.out, a.ldo, a.Hq, a.Hkv, G, a.num_splits);

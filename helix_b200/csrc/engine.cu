@@ -138,6 +138,7 @@ void Engine::free_all() {
   fr(d_step_);
   fr(all_logits_);
   fr(d_embed_out_);
+  fr(dec_trace_);
   auto frh = [](auto*& p) {
     if (p) cudaFreeHost(p);
     p = nullptr;
@@ -167,6 +168,7 @@ size_t Engine::workspace_bytes() const {
     b += al256((size_t)cfg_.max_seqs * 4);                    // sampled
     b += al256(sample_scratch_bytes(cfg_.max_seqs, d.vocab)); // argmax partials
     b += 2 * al256((size_t)cfg_.max_seqs * HB_MAX_LOGPROBS * 4);  // log-probability records of one step
+    b += al256((size_t)(5 * d.layers + 1) * sizeof(int));         // HBM hand-over counters of the decode step
     b += al256(skinny_ws_bytes(148));                         // decode GEMM partial slabs
   }
   return b;
@@ -295,6 +297,11 @@ int Engine::alloc_runtime() {
     dec_ws_ = (float*)take(attn_decode_workspace_floats(cfg_.max_seqs, d.heads, d.head_dim, 16) * 4);
     sampled_ = (int32_t*)take((size_t)cfg_.max_seqs * 4);
     sample_ws_ = take(sample_scratch_bytes(cfg_.max_seqs, d.vocab));
+    sig_ = (int*)take((size_t)(5 * d.layers + 1) * sizeof(int));
+    if (getenv("HB_DEC_TRACE")) {  // debug timeline: 16 %globaltimer stamps per streaming kernel (tools/dec_trace.py)
+      CU(cudaMalloc(&dec_trace_, (size_t)(5 * d.layers + 1) * 16 * 8));
+      CU(cudaMemset(dec_trace_, 0, (size_t)(5 * d.layers + 1) * 16 * 8));
+    }
     lp_ids_ = (int32_t*)take((size_t)cfg_.max_seqs * HB_MAX_LOGPROBS * 4);
     lp_vals_ = (float*)take((size_t)cfg_.max_seqs * HB_MAX_LOGPROBS * 4);
     int sms = 148;
@@ -644,13 +651,38 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
   auto wbytes = [&](double N, double K) { return 2.0 * N * K + 2.0 * B * K + 4.0 * B * N; };
   const double rowb = 4.0 * B * H;
 
+  // HBM hand-over chain (kernels.h StreamSig): qkv(0) -> attn(0) -> o(0) -> gate/up(0) -> down(0) -> qkv(1) ... -> head.
+  // One counter per streaming kernel of the step, zeroed first (a memset node when the step is a CUDA graph).
+  static const size_t bank_bytes = [] {
+    const char* e = getenv("HB_DECODE_BANK_MB");
+    return (size_t)(e ? atoi(e) : 32) << 20;
+  }();
+  const bool handover = sig_ != nullptr && !profile_ && (bank_bytes > 0 || dec_trace_);
+  if (handover) CU(cudaMemsetAsync(sig_, 0, (size_t)(5 * d.layers + 1) * sizeof(int), stream_));
+  int prev_idx = -1, prev_count = 0;
+  auto next_sig = [&](int idx, int my_ctas) {
+    StreamSig sg{};
+    if (!handover) return sg;
+    if (prev_idx >= 0) { sg.wait = sig_ + prev_idx; sg.wait_count = prev_count; }
+    sg.done = sig_ + idx;
+    sg.bank_bytes = bank_bytes;
+    sg.trace = dec_trace_ ? dec_trace_ + (size_t)idx * 16 : nullptr;
+    prev_idx = idx;
+    prev_count = my_ctas;
+    return sg;
+  };
+  const int splits = decode_splits(B);
+
   SPAN(3, rowb, embed_gather(stream_, tokens, model_.embed, x_, B, H));
   SPAN(3, rowb, rmsnorm(stream_, x_, model_.ll[0].attn_norm, xn_, nullptr, B, H, d.norm_eps));
   for (int l = 0; l < d.layers; ++l) {
     const LlamaLayerW& w = model_.ll[l];
     bf16* kc = kv_ + (size_t)l * 2 * layer_kv;
     bf16* vc = kc + layer_kv;
-    SPAN(4, wbytes(QKV, H), gemm_skinny(stream_, plan_qkv_, xn_, H, w.wqkv, H, skinny_ws_, B, QKV, H));
+    {
+      const StreamSig sg = next_sig(5 * l + 0, plan_qkv_.grid);
+      SPAN(4, wbytes(QKV, H), gemm_skinny(stream_, plan_qkv_, xn_, H, w.wqkv, H, skinny_ws_, B, QKV, H, &sg));
+    }
     SPAN(3, 8.0 * B * QKV, dec_qkv_rope_kvwrite(stream_, skinny_ws_, plan_qkv_, qkv_, positions, slots, model_.inv_freq,
                                                  kc, vc, B, d.heads, d.kv_heads, D, page_));
     {
@@ -662,21 +694,34 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
       a.out = attn_; a.ldo = QD;
       a.workspace = dec_ws_;
       a.B = B; a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D; a.page_size = page_;
-      a.num_splits = decode_splits(B);
+      a.num_splits = splits;
       a.scale = 1.0f / sqrtf((float)D);
       a.num_pages = num_pages_;
+      a.sig = next_sig(5 * l + 1, splits * d.kv_heads * B);
       SPAN(2, attn_bytes_, attn_decode(stream_, a));
       if (a.num_splits > 1) launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel
     }
-    SPAN(4, wbytes(H, QD), gemm_skinny(stream_, plan_o_, attn_, QD, w.wo, QD, skinny_ws_, B, H, QD));
+    {
+      const StreamSig sg = next_sig(5 * l + 2, plan_o_.grid);
+      SPAN(4, wbytes(H, QD), gemm_skinny(stream_, plan_o_, attn_, QD, w.wo, QD, skinny_ws_, B, H, QD, &sg));
+    }
     SPAN(3, 3 * rowb, dec_resid_rmsnorm(stream_, skinny_ws_, plan_o_, x_, w.mlp_norm, xn_, B, H, d.norm_eps));
-    SPAN(4, wbytes(2.0 * F, H), gemm_skinny(stream_, plan_gu_, xn_, H, w.wgu, H, skinny_ws_, B, 2 * F, H));
+    {
+      const StreamSig sg = next_sig(5 * l + 3, plan_gu_.grid);
+      SPAN(4, wbytes(2.0 * F, H), gemm_skinny(stream_, plan_gu_, xn_, H, w.wgu, H, skinny_ws_, B, 2 * F, H, &sg));
+    }
     SPAN(3, 10.0 * B * F, dec_swiglu(stream_, skinny_ws_, plan_gu_, h_, B, F));
-    SPAN(4, wbytes(H, F), gemm_skinny(stream_, plan_down_, h_, F, w.wdown, F, skinny_ws_, B, H, F));
+    {
+      const StreamSig sg = next_sig(5 * l + 4, plan_down_.grid);
+      SPAN(4, wbytes(H, F), gemm_skinny(stream_, plan_down_, h_, F, w.wdown, F, skinny_ws_, B, H, F, &sg));
+    }
     const bf16* next_norm = (l + 1 < d.layers) ? model_.ll[l + 1].attn_norm : model_.final_norm;
     SPAN(3, 3 * rowb, dec_resid_rmsnorm(stream_, skinny_ws_, plan_down_, x_, next_norm, xn_, B, H, d.norm_eps));
   }
-  SPAN(4, wbytes(d.vocab, H), gemm_skinny(stream_, plan_head_, xn_, H, model_.lm_head, H, skinny_ws_, B, d.vocab, H));
+  {
+    const StreamSig sg = next_sig(5 * d.layers, plan_head_.grid);
+    SPAN(4, wbytes(d.vocab, H), gemm_skinny(stream_, plan_head_, xn_, H, model_.lm_head, H, skinny_ws_, B, d.vocab, H, &sg));
+  }
   SPAN(3, 8.0 * B * d.vocab, dec_sum_slabs(stream_, skinny_ws_, plan_head_, logits_, d.vocab, B, d.vocab));
   return sample_step(B, L);
 }
@@ -1383,6 +1428,24 @@ int Engine::embed(const int32_t* toks, const int32_t* offsets, int nseq, float* 
 
 int Engine::stats(hb_stats* s) {
   if (!s) return fail(HB_ERR_INVALID, "null stats");
+  if (dec_trace_ && getenv("HB_DEC_TRACE_DUMP")) {  // debug: timeline of the LAST decode step, ns relative to its first event
+    std::lock_guard<std::mutex> gg(gpu_mu_);
+    const int n = 5 * model_.d.layers + 1;
+    std::vector<unsigned long long> h((size_t)n * 16);
+    cudaMemcpy(h.data(), dec_trace_, h.size() * 8, cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (auto v : h) if (v && v < t0) t0 = v;
+    FILE* f = fopen(getenv("HB_DEC_TRACE_DUMP"), "w");
+    if (f) {
+      static const char* names[5] = {"qkv", "attn", "o", "gu", "down"};
+      for (int i = 0; i < n; ++i) {
+        fprintf(f, "%3d %-5s", i / 5, i == n - 1 ? "head" : names[i % 5]);
+        for (int e = 0; e < 8; ++e) fprintf(f, " %9lld", h[(size_t)i * 16 + e] ? (long long)(h[(size_t)i * 16 + e] - t0) : -1ll);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   memset(s, 0, sizeof *s);
   std::lock_guard<std::mutex> g(mu_);
   s->weights_bytes = model_.arena_bytes;

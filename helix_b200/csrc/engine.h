@@ -159,6 +159,8 @@ class Engine {
   void* sample_ws_ = nullptr;
   int step_flags_ = 0;          // StepFlags of the current step: top-k/top-p filter, penalties, log-probabilities
   size_t pen_cap_ = 0;          // penalty entries the step block can hold
+  unsigned long long* dec_trace_ = nullptr;  // HB_DEC_TRACE timeline buffer (debug)
+  int* sig_ = nullptr;          // [5 * layers + 1] HBM hand-over counters of the decode step (kernels.h StreamSig)
   int32_t* lp_ids_ = nullptr;   // [b_cap][HB_MAX_LOGPROBS]
   float* lp_vals_ = nullptr;
   int32_t* h_lp_ids_ = nullptr;

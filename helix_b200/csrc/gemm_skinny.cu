@@ -11,6 +11,7 @@
 // and fuses the epilogue (residual+RMSNorm, RoPE+KV write, SwiGLU, logits).
 #include <stdio.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -57,7 +58,8 @@ __host__ __device__ inline int owner_of(long long u, long long U, int G) {
 template <int MPAD>
 __global__ void __launch_bounds__(kThreads, (MPAD <= 64 ? 2 : 1))
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
-                   float* __restrict__ ws, int M, int N, int K) {
+                   float* __restrict__ ws, int M, int N, int K, const int* sig_wait, int sig_wait_count, int* sig_done,
+                   int bank_units, const bf16* __restrict__ Wp, int ldw, unsigned long long* trace) {
   using C = SCfg<MPAD>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -79,7 +81,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
   const long long u0 = range_start(blockIdx.x, U, G), u1 = range_start(blockIdx.x + 1, U, G);
 
   pdl_launch_dependents();
+  if (blockIdx.x != 0) trace = nullptr;
   if (threadIdx.x == 0) {
+    trace_ev(trace, 0);
     tma_prefetch_desc(&map_w);
     tma_prefetch_desc(&map_x);
     for (int i = 0; i < STAGES; ++i) {
@@ -116,7 +120,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           tma_load_2d(smem_w + s * C::W_BYTES, &map_w, &full_bar[s], (int)(u % KB) * BLOCK_K, (int)(u / KB) * BLOCK_N, kEvictFirst);
         }
       }
+      if (pre_end >= u1 && elected) sig_add(sig_done);  // the whole range fitted into the ring
+      if (elected) trace_ev(trace, 1);
       pdl_wait();
+      if (elected) trace_ev(trace, 3);
       for (long long u = u0; u < pre_end; ++u) {
         const int s = (int)(u - u0);
         if (elected) tma_load_2d(smem_x + s * C::X_BYTES, &map_x, &full_bar[s], (int)(u % KB) * BLOCK_K, 0, kEvictLast);
@@ -131,6 +138,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           tma_load_2d(smem_w + s * C::W_BYTES, &map_w, &full_bar[s], kb * BLOCK_K, tile * BLOCK_N, kEvictFirst);
           tma_load_2d(smem_x + s * C::X_BYTES, &map_x, &full_bar[s], kb * BLOCK_K, 0, kEvictLast);
+          if (u + 1 == u1) { sig_add(sig_done); trace_ev(trace, 5); }  // this CTA's HBM demand ends here
         }
         if (++s == STAGES) { s = 0; phase ^= 1; }
       }
@@ -153,6 +161,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         bool first = true;
         for (; u < seg_end; ++u) {
           mbar_wait(&full_bar[s], phase);
+          if (u == u0 && elected) trace_ev(trace, 4);
           tc_fence_after();
           const uint32_t w_addr = smem_u32(smem_w + s * C::W_BYTES);
           const uint32_t x_addr = smem_u32(smem_x + s * C::X_BYTES);
@@ -168,6 +177,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
           if (++s == STAGES) { s = 0; phase ^= 1; }
         }
         if (elected) umma_commit(&tmem_full[as]);
+        if (elected && u >= u1) trace_ev(trace, 6);
         ++it;
       }
     }
@@ -176,6 +186,20 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     const int row = q * 32 + lane;  // weight row within the tile == TMEM lane
     int it = 0;
     long long u = u0;
+    // HBM hand-over (ptx.cuh sig_*): these four warps idle until the first accumulator is ready.  Once the previous
+    // streaming kernel has issued its last load, they pull the `bank_units` weight tiles that follow the ring into L2
+    // (one 128-byte row of the tile per thread), so HBM keeps working through the dependency gap and the ring loads of
+    // those tiles hit L2.
+    if (bank_units > 0) {
+      if (lane == 0) sig_wait_ge(sig_wait, sig_wait_count);
+      if (warp == 2 && lane == 0) trace_ev(trace, 2);
+      __syncwarp();
+      const long long pre_end = min(u1, u0 + STAGES), bank_end = min(u1, pre_end + bank_units);
+      for (long long ub = pre_end; ub < bank_end; ++ub) {
+        const long long wrow = (ub / KB) * BLOCK_N + row;
+        if (wrow < N) prefetch_l2_line(Wp + wrow * ldw + (ub % KB) * BLOCK_K);
+      }
+    }
     pdl_wait();  // ws is an activation buffer: never written before the predecessors are done
     while (u < u1) {
       const int tile = (int)(u / KB);
@@ -207,6 +231,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       u = seg_end;
       ++it;
     }
+    if (warp == 2 && lane == 0) trace_ev(trace, 7);
   }
   tc_fence_before();
   __syncthreads();
@@ -225,12 +250,16 @@ std::map<PlanKey, SkinnyPlan> g_plans;
 
 template <int MPAD>
 cudaError_t launch(cudaStream_t stream, const SkinnyPlan& plan, const bf16* X, int ldx, const bf16* W, int ldw,
-                   float* ws, int M, int N, int K) {
+                   float* ws, int M, int N, int K, const StreamSig* sig) {
   using C = SCfg<MPAD>;
+  const StreamSig none{};
+  if (!sig) sig = &none;
+  const int bank_units = (int)std::min<size_t>(sig->bank_bytes / ((size_t)plan.grid * C::W_BYTES), 4096);
   CUtensorMap mw, mx;
   if (!make_tmap_2d(&mw, W, TM_BF16, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BLOCK_K, BLOCK_N)) return cudaErrorInvalidValue;
   if (!make_tmap_2d(&mx, X, TM_BF16, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, BLOCK_K, MPAD)) return cudaErrorInvalidValue;
-  return launch_k(gemm_skinny_kernel<MPAD>, dim3(plan.grid), dim3(kThreads), C::SMEM, stream, true, mw, mx, ws, M, N, K);
+  return launch_k(gemm_skinny_kernel<MPAD>, dim3(plan.grid), dim3(kThreads), C::SMEM, stream, true, mw, mx, ws, M, N, K,
+                  sig->wait, sig->wait_count, sig->done, bank_units, W, ldw, sig->trace);
 }
 
 template <int MPAD>
@@ -295,12 +324,12 @@ int gemm_skinny_max_segs(int N, int K, int sms) {
 size_t gemm_skinny_ws_floats(const SkinnyPlan& p, int M, int N) { return (size_t)p.max_segs * M * N; }
 
 cudaError_t gemm_skinny(cudaStream_t stream, const SkinnyPlan& plan, const bf16* X, int ldx, const bf16* W, int ldw,
-                        float* ws, int M, int N, int K) {
+                        float* ws, int M, int N, int K, const StreamSig* sig) {
   if (M <= 0 || M > 256 || (K % 8) || (ldx % 8) || (ldw % 8)) return cudaErrorInvalidValue;
-  if (M <= 32) return launch<32>(stream, plan, X, ldx, W, ldw, ws, M, N, K);
-  if (M <= 64) return launch<64>(stream, plan, X, ldx, W, ldw, ws, M, N, K);
-  if (M <= 128) return launch<128>(stream, plan, X, ldx, W, ldw, ws, M, N, K);
-  return launch<256>(stream, plan, X, ldx, W, ldw, ws, M, N, K);
+  if (M <= 32) return launch<32>(stream, plan, X, ldx, W, ldw, ws, M, N, K, sig);
+  if (M <= 64) return launch<64>(stream, plan, X, ldx, W, ldw, ws, M, N, K, sig);
+  if (M <= 128) return launch<128>(stream, plan, X, ldx, W, ldw, ws, M, N, K, sig);
+  return launch<256>(stream, plan, X, ldx, W, ldw, ws, M, N, K, sig);
 }
 
 }  // namespace hb

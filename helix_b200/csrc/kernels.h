@@ -105,6 +105,18 @@ cudaError_t attn_prefill(cudaStream_t stream, const AttnPrefillArgs& a);
 // test-only CUDA-core checker, fp32 output [T, ldo]
 cudaError_t attn_naive_check(cudaStream_t stream, const AttnPrefillArgs& a, float* out_f32);
 
+// Stream hand-over between consecutive HBM-streaming kernels of a decode step (see ptx.cuh sig_*): `wait` is the counter
+// the PREVIOUS streaming kernel bumps once per CTA when its last load is issued (`wait_count` = its CTA count), `done`
+// is this kernel's own counter, `bank_bytes` how much of its own stream the kernel may prefetch into L2 once the
+// predecessor's loads have ended.  All-zero = feature off.
+struct StreamSig {
+  const int* wait = nullptr;
+  int wait_count = 0;
+  int* done = nullptr;
+  size_t bank_bytes = 0;
+  unsigned long long* trace = nullptr;  // 16 event slots of this launch (HB_DEC_TRACE), written by CTA 0
+};
+
 // ---- K6: paged-KV decode attention (one query token per sequence), split-KV + combine ----
 struct AttnDecodeArgs {
   const bf16* q; int ldq;          // [B, >=Hq*D] (post-RoPE)
@@ -118,6 +130,7 @@ struct AttnDecodeArgs {
   int B, Hq, Hkv, D, page_size, num_splits;
   float scale;
   int num_pages;                   // pages in the pool (TMA tensor-map extent)
+  StreamSig sig;                   // HBM hand-over with the neighbouring streaming kernels (optional)
 };
 cudaError_t attn_decode(cudaStream_t stream, const AttnDecodeArgs& a);
 size_t attn_decode_workspace_floats(int B, int Hq, int D, int num_splits);
@@ -136,7 +149,7 @@ size_t gemm_skinny_ws_floats(const SkinnyPlan& p, int M, int N);
 int gemm_skinny_max_segs(int N, int K, int sms);  // pure host arithmetic (memory estimates)
 // ws[seg][m][n] (seg < seg_count[n/128]) = partial sums of X[M,K] . W[N,K]^T
 cudaError_t gemm_skinny(cudaStream_t stream, const SkinnyPlan& plan, const bf16* X, int ldx, const bf16* W, int ldw,
-                        float* ws, int M, int N, int K);
+                        float* ws, int M, int N, int K, const StreamSig* sig = nullptr);
 // consumers of the slabs (each sums the slabs in fixed order, then applies its fused epilogue)
 cudaError_t dec_sum_slabs(cudaStream_t s, const float* ws, const SkinnyPlan& p, float* out, int ldo, int M, int N);
 cudaError_t dec_qkv_rope_kvwrite(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* qkv_out,

@@ -110,6 +110,45 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 // 2-CTA flavour: completes the transaction bytes on the leader CTA's barrier (peer bit cleared).
+// L2-only prefetch of the box a tma_load_2d / tma_load_3d with the same map and coordinates would fetch (UTMAPF.L2): no
+// shared memory, no mbarrier — the later TMA load of that box then hits L2 instead of HBM
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// One 128-byte line into L2 through the load/store path: unlike UTMAPF it does not queue in front of the CTA's TMA loads
+// (the TMA unit works in order: a burst of tensor prefetches delayed the operand loads issued after it by microseconds)
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Optional timeline of the decode step (HB_DEC_TRACE=1): event `ev` of this kernel -> trace[ev] = %globaltimer (ns)
+__device__ __forceinline__ void trace_ev(unsigned long long* trace, int ev) {
+  if (trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    trace[ev] = t;
+  }
+}
+// Stream hand-over counters of the decode step (engine.cu `sig_`): a weight / KV streaming kernel adds 1 per CTA once its
+// producer has ISSUED its last HBM load; the next streaming kernel's producers (already resident under PDL, rings full)
+// poll the counter and then start prefetching their own stream into L2, so HBM keeps working through the dependency gap
+// between the two kernels.  Pure hints: no data is guarded by them.
+__device__ __forceinline__ void sig_add(int* p) {
+  if (p) asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ int sig_load(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sig_wait_ge(const int* p, int n) {
+  if (!p) return;
+  while (sig_load(p) < n) __nanosleep(200);
+}
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                                 uint64_t hint = kEvictNormal) {
   uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;

@@ -110,7 +110,7 @@ def test_stop_returns_all_device_memory():
     e.start()
     rid = e.submit(weights.random_tokens(1, 100, d.vocab), hb.Sampling(max_tokens=3000))
     during = _free_bytes()
-    assert before - during > (1 << 30)                           # the KV pool really was allocated
+    assert before - during > (32 << 20)                          # the KV pool (64 MB at this tiny shape) really was allocated
     res = {}
     t = threading.Thread(target=lambda: res.setdefault("rc", e._l.hb_wait(e._h, rid, 60000)))
     for _ in range(50):
