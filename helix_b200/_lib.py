@@ -15,7 +15,7 @@ class EngineCfg(C.Structure):
                 ("max_ctx", C.c_int32), ("max_batched_tokens", C.c_int32), ("kv_page_size", C.c_int32),
                 ("use_cuda_graphs", C.c_int32), ("enable_prefix_cache", C.c_int32), ("sm_budget", C.c_int32),
                 ("sm_partition", C.c_int32), ("stream_priority", C.c_int32), ("decode_with_prefill", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("fused_decode", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class ModelDescC(C.Structure):
@@ -80,6 +80,7 @@ SIGNATURES = {
     "hbk_gemm": (I, [P, I, P, I, P, I, P, I, P, I, I, I, I, I]),
     "hbk_gemm_naive": (I, [P, I, P, I, P, I, I, I, I]),
     "hbk_gemm_skinny": (I, [P, I, P, I, P, I, I, I, I]),
+    "hbk_gemm_skinny_finish": (I, [P, I, P, I, P, I, I, I, I, I]),
     "hbk_embed_gather": (I, [P, P, P, I, I]),
     "hbk_bert_embed_ln": (I, [P, P, P, P, P, P, P, P, I, I, C.c_float]),
     "hbk_rmsnorm": (I, [P, P, P, P, I, I, C.c_float]),

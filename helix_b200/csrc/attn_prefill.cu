@@ -9,6 +9,7 @@
 #include <type_traits>
 
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 #include "tma_host.h"
 
@@ -506,7 +507,7 @@ cudaError_t launch_p(cudaStream_t stream, const AttnPrefillArgs& a) {
   }
   const int max_q_pairs = (a.max_seqlen + QPAIR - 1) / QPAIR;
   const long long items = (long long)max_q_pairs * a.B * a.Hq;
-  const int grid = (int)std::min<long long>(items, num_sms);
+  const int grid = (int)std::min<long long>(items, effective_sms(num_sms));  // hb_engine_cfg.sm_budget
   const float scale_log2 = a.scale * 1.4426950408889634f;
   kern<<<grid, kThreads, C::SMEM, stream>>>(mq, mk, mv, a.out, a.ldo, a.cu_seqlens, a.B, a.Hq, a.Hq / a.Hkv, a.causal,
                                             scale_log2, max_q_pairs, a.kv_lens, a.page_table, a.max_pages, a.Hkv);

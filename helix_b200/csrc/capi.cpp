@@ -114,6 +114,27 @@ int hbk_gemm_skinny(const void* X, int ldx, const void* W, int ldw, float* out, 
   cudaFree(ws);
   return kret(e != cudaSuccess ? e : e2);
 }
+int hbk_gemm_skinny_finish(const void* X, int ldx, const void* W, int ldw, float* out, int ldo, int M, int N, int K, int repeats) {
+  hb::SkinnyPlan plan;
+  cudaError_t e = hb::gemm_skinny_plan(N, K, &plan);
+  if (e != cudaSuccess) return kret(e);
+  float* ws = nullptr;
+  int* cnt = nullptr;
+  if ((e = cudaMalloc(&ws, hb::gemm_skinny_ws_floats(plan, M, N) * 4)) != cudaSuccess) return kret(e);
+  if ((e = cudaMalloc(&cnt, (size_t)plan.n_tiles * 4)) != cudaSuccess) return kret(e);
+  cudaMemset(cnt, 0, (size_t)plan.n_tiles * 4);
+  hb::SkinnyEpi epi{};
+  epi.mode = hb::SK_F32;
+  epi.tile_cnt = cnt;
+  epi.out_f32 = out;
+  epi.ldo = ldo;
+  for (int r = 0; r < repeats && e == cudaSuccess; ++r)  // the counters must come back to zero by themselves
+    e = hb::gemm_skinny(0, plan, (const hb::bf16*)X, ldx, (const hb::bf16*)W, ldw, ws, M, N, K, nullptr, &epi);
+  cudaError_t e2 = cudaDeviceSynchronize();
+  cudaFree(ws);
+  cudaFree(cnt);
+  return kret(e != cudaSuccess ? e : e2);
+}
 int hbk_gemm_naive(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int M, int N, int K) {
   hb::GemmArgs g{(const hb::bf16*)A, lda, (const hb::bf16*)W, ldw, C, ldc, nullptr, 0, nullptr, M, N, K, hb::EPI_F32, 0};
   return kret(hb::gemm_naive_check(0, g));

@@ -163,8 +163,39 @@ swiglu_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf
   *reinterpret_cast<uint2*>(h + (size_t)m * F + j) = ob;
 }
 
+// one block (128 threads) per row: x = table[token]; xg = bf16(x * gain); ss_out[tile][m] = sum of x^2 over the tile
+__global__ void __launch_bounds__(128)
+embed_prep_kernel(const int32_t* __restrict__ tokens, const bf16* __restrict__ table, const bf16* __restrict__ gain,
+                  bf16* __restrict__ x, bf16* __restrict__ xg, float* __restrict__ ss_out, int H) {
+  __shared__ float red[4];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x, t = threadIdx.x;
+  const bf16* src = table + (size_t)tokens[m] * H;
+  for (int tile = 0; tile * 128 < H; ++tile) {
+    const int n = tile * 128 + t;
+    float v = 0.f;
+    if (n < H) {
+      const bf16 raw = src[n];
+      v = __bfloat162float(raw);
+      x[(size_t)m * H + n] = raw;
+      xg[(size_t)m * H + n] = __float2bfloat16(v * __bfloat162float(gain[n]));
+    }
+    float sq = warp_sum(v * v);
+    __syncthreads();  // red reuse
+    if ((t & 31) == 0) red[t >> 5] = sq;
+    __syncthreads();
+    if (t == 0) ss_out[(size_t)tile * kSkinnySsStride + m] = (red[0] + red[1]) + (red[2] + red[3]);
+  }
+}
+
 }  // namespace
 
+cudaError_t dec_embed_prep(cudaStream_t s, const int32_t* tokens, const bf16* table, const bf16* gain, bf16* x, bf16* xg,
+                           float* ss_out, int M, int H) {
+  if (M <= 0) return cudaSuccess;
+  return launch_k(embed_prep_kernel, dim3(M), dim3(128), 0, s, true, tokens, table, gain, x, xg, ss_out, H);
+}
 cudaError_t dec_sum_slabs(cudaStream_t s, const float* ws, const SkinnyPlan& p, float* out, int ldo, int M, int N) {
   return launch_k(sum_slabs_kernel, dim3((N + 255) / 256, M), dim3(256), 0, s, true, ws, p.seg_count, out, ldo, M, N);
 }

@@ -1,5 +1,6 @@
 #include "engine.h"
 
+#include "launch.h"
 #include "nccl_dl.h"
 #include "tma_host.h"
 
@@ -84,6 +85,7 @@ Engine::~Engine() {
     if (fwd_a_) cudaEventDestroy(fwd_a_);
     if (fwd_b_) cudaEventDestroy(fwd_b_);
     cudaStreamDestroy(stream_);
+    if (green_ctx_) destroy_partition(green_ctx_);
   }
 }
 
@@ -116,7 +118,24 @@ int Engine::init() {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, cfg_.device));
   if (prop.major != 10) return fail(HB_ERR_CUDA, "device is not sm_100 (Blackwell B200); kernels are sm_100a-only");
-  CU(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  int dev_sms = 0;
+  CU(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, cfg_.device));
+  if (cfg_.sm_budget < 0 || cfg_.sm_budget > dev_sms) cfg_.sm_budget = 0;
+  if (cfg_.sm_budget > 0 && cfg_.sm_budget < 16) return fail(HB_ERR_INVALID, "sm_budget must be 0 or >= 16 SMs");
+  if (cfg_.sm_partition && cfg_.sm_budget > 0) {
+    // hardware-enforced share of the GPU for this ModelInstance (CUDA green context): kernels on this stream can only
+    // be scheduled on the granted SMs, whatever the other engines on the device launch
+    const char* why = nullptr;
+    int granted = 0;
+    CU(cudaFree(nullptr));  // the primary context must exist before a green context is carved out of it
+    if (!create_partition_stream(cfg_.device, cfg_.sm_budget, cfg_.stream_priority, &stream_, &green_ctx_, &granted, &why))
+      return fail(HB_ERR_INVALID, std::string("sm_partition: ") + (why ? why : "unavailable"));
+    cfg_.sm_budget = granted;  // the driver rounds the request up to its SM granularity
+  } else {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, cfg_.stream_priority > 0 ? hi : lo));
+  }
   CU(cudaEventCreate(&fwd_a_));
   CU(cudaEventCreate(&fwd_b_));
   CU(kernels_init());  // max-dynamic-smem attributes for every instantiation (never inside a graph capture)
@@ -169,9 +188,16 @@ size_t Engine::workspace_bytes() const {
     b += al256(sample_scratch_bytes(cfg_.max_seqs, d.vocab)); // argmax partials
     b += 2 * al256((size_t)cfg_.max_seqs * HB_MAX_LOGPROBS * 4);  // log-probability records of one step
     b += al256((size_t)(5 * d.layers + 1) * sizeof(int));         // HBM hand-over counters of the decode step
+    b += al256(fused_counter_ints(d) * sizeof(int));              // tile arrival counters of the fused decode GEMMs
+    b += al256((size_t)((d.hidden + 127) / 128) * kSkinnySsStride * sizeof(float));  // RMSNorm per-tile partials
     b += al256(skinny_ws_bytes(148));                         // decode GEMM partial slabs
   }
   return b;
+}
+
+size_t Engine::fused_counter_ints(const hb_model_desc& d) {
+  const size_t qkv = (size_t)(d.heads + 2 * d.kv_heads) * d.head_dim;
+  return (qkv + 127) / 128 + 2 * ((size_t)(d.hidden + 127) / 128) + ((size_t)2 * d.ffn + 127) / 128 + ((size_t)d.vocab + 127) / 128;
 }
 
 size_t Engine::skinny_ws_bytes(int sms) const {
@@ -272,6 +298,7 @@ int Engine::tensor_set(const char* name, const void* host, size_t n) {
 
 int Engine::alloc_runtime() {
   const hb_model_desc& d = model_.d;
+  SmLimitScope sm_scope(cfg_.sm_budget);  // the stream-K plans of the decode GEMMs are cut for this engine's SM share
   t_cap_ = cfg_.max_batched_tokens;
   if (d.arch == HB_ARCH_BERT && cfg_.max_ctx > d.max_pos) cfg_.max_ctx = d.max_pos;
   if (d.arch == HB_ARCH_BERT && t_cap_ < cfg_.max_ctx) t_cap_ = cfg_.max_ctx;  // an encoder sequence is never split
@@ -298,6 +325,17 @@ int Engine::alloc_runtime() {
     sampled_ = (int32_t*)take((size_t)cfg_.max_seqs * 4);
     sample_ws_ = take(sample_scratch_bytes(cfg_.max_seqs, d.vocab));
     sig_ = (int*)take((size_t)(5 * d.layers + 1) * sizeof(int));
+    {
+      int* cnt = (int*)take(fused_counter_ints(d) * sizeof(int));
+      CU(cudaMemset(cnt, 0, fused_counter_ints(d) * sizeof(int)));
+      const int tq = (model_.qkv_cols() + 127) / 128, th = (d.hidden + 127) / 128, tg = (2 * d.ffn + 127) / 128;
+      cnt_qkv_ = cnt;
+      cnt_o_ = cnt_qkv_ + tq;
+      cnt_gu_ = cnt_o_ + th;
+      cnt_down_ = cnt_gu_ + tg;
+      cnt_head_ = cnt_down_ + th;
+      ss_ = (float*)take((size_t)th * kSkinnySsStride * sizeof(float));
+    }
     if (getenv("HB_DEC_TRACE")) {  // debug timeline: 16 %globaltimer stamps per streaming kernel (tools/dec_trace.py)
       CU(cudaMalloc(&dec_trace_, (size_t)(5 * d.layers + 1) * 16 * 8));
       CU(cudaMemset(dec_trace_, 0, (size_t)(5 * d.layers + 1) * 16 * 8));
@@ -315,6 +353,13 @@ int Engine::alloc_runtime() {
     CU(gemm_skinny_plan(2 * d.ffn, d.hidden, &plan_gu_));
     CU(gemm_skinny_plan(d.hidden, d.ffn, &plan_down_));
     CU(gemm_skinny_plan(d.vocab, d.hidden, &plan_head_));
+    {
+      const size_t Bm = skinny_max_b_, have = skinny_ws_bytes(148) / 4;
+      const size_t need = std::max({gemm_skinny_ws_floats(plan_qkv_, Bm, QKV), gemm_skinny_ws_floats(plan_o_, Bm, d.hidden),
+                                    gemm_skinny_ws_floats(plan_gu_, Bm, 2 * d.ffn), gemm_skinny_ws_floats(plan_down_, Bm, d.hidden),
+                                    gemm_skinny_ws_floats(plan_head_, Bm, d.vocab)});
+      if (need > have) return fail(HB_ERR_INVALID, "decode GEMM plan needs more slab workspace than was sized (sm_budget?)");
+    }
   }
   // penalty entries: one per distinct generated token of every running sequence, bounded at 4 Mi (32 MB)
   pen_cap_ = d.arch == HB_ARCH_LLAMA ? std::min<size_t>((size_t)cfg_.max_seqs * cfg_.max_ctx, size_t(4) << 20) : 0;
@@ -520,7 +565,7 @@ int Engine::decode_splits(int B) const {
   static const int forced = [] { const char* e = getenv("HB_DECODE_SPLITS"); return e ? atoi(e) : 0; }();  // A/B knob
   if (forced > 0) return std::min(16, forced);
   const int ctas = B * model_.d.kv_heads;
-  const int want = (int)(0.8 * 2 * 148);
+  const int want = (int)(0.8 * 2 * (cfg_.sm_budget > 0 ? cfg_.sm_budget : 148));
   return std::max(1, std::min(16, (want + ctas - 1) / ctas));
 }
 
@@ -640,6 +685,7 @@ int Engine::sample_step(int B, const StepLayout& L) {
 // Decode step (one token per sequence, B <= 256): every projection is a weight-streaming skinny GEMM whose
 // fp32 partial slabs are consumed by the fused row kernel that follows it in the layer.
 int Engine::forward_llama_decode(int B, const StepLayout& L) {
+  if (fused_decode_ok()) return forward_llama_decode_fused(B, L);
   const hb_model_desc& d = model_.d;
   const int H = d.hidden, D = d.head_dim, QD = d.heads * D, QKV = model_.qkv_cols(), F = d.ffn;
   const int32_t* tokens = (const int32_t*)(d_step_ + L.tokens);
@@ -655,7 +701,7 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
   // One counter per streaming kernel of the step, zeroed first (a memset node when the step is a CUDA graph).
   static const size_t bank_bytes = [] {
     const char* e = getenv("HB_DECODE_BANK_MB");
-    return (size_t)(e ? atoi(e) : 32) << 20;
+    return (size_t)(e ? atoi(e) : 0) << 20;  // measured: no gain on the headline workload, off by default
   }();
   const bool handover = sig_ != nullptr && !profile_ && (bank_bytes > 0 || dec_trace_);
   if (handover) CU(cudaMemsetAsync(sig_, 0, (size_t)(5 * d.layers + 1) * sizeof(int), stream_));
@@ -723,6 +769,125 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
     SPAN(4, wbytes(d.vocab, H), gemm_skinny(stream_, plan_head_, xn_, H, model_.lm_head, H, skinny_ws_, B, d.vocab, H, &sg));
   }
   SPAN(3, 8.0 * B * d.vocab, dec_sum_slabs(stream_, skinny_ws_, plan_head_, logits_, d.vocab, B, d.vocab));
+  return sample_step(B, L);
+}
+
+// Decode step with tile finishers (kernels.h SkinnyEpi): five kernels per layer — qkv(+RoPE/KV write), attention,
+// o(+residual), gate/up(+SwiGLU), down(+residual) — no row kernel between two projections.  RMSNorm is split: the
+// residual finisher writes xg = bf16(x * gain) and per-tile sums of x^2, the NEXT projection's finisher multiplies its
+// rows by rstd (the GEMM is linear in the row factor).
+bool Engine::fused_decode_ok() const {
+  static const int env = [] { const char* e = getenv("HB_DECODE_FUSED"); return e ? atoi(e) : -1; }();  // A/B override
+  const hb_model_desc& d = model_.d;
+  const bool on = env >= 0 ? env != 0 : cfg_.fused_decode != 0;
+  return on && cnt_qkv_ && (d.head_dim == 64 || d.head_dim == 128) && (d.heads * d.head_dim) % 128 == 0 &&
+         (d.kv_heads * d.head_dim) % 128 == 0 && d.hidden % 128 == 0 && (2 * d.ffn) % 256 == 0;
+}
+
+int Engine::forward_llama_decode_fused(int B, const StepLayout& L) {
+  const hb_model_desc& d = model_.d;
+  const int H = d.hidden, D = d.head_dim, QD = d.heads * D, QKV = model_.qkv_cols(), F = d.ffn;
+  const int32_t* tokens = (const int32_t*)(d_step_ + L.tokens);
+  const int32_t* positions = (const int32_t*)(d_step_ + L.positions);
+  const int32_t* slots = (const int32_t*)(d_step_ + L.slots);
+  const int32_t* ctx = (const int32_t*)(d_step_ + L.ctx);
+  const int32_t* pt = (const int32_t*)(d_step_ + L.pt);
+  const size_t layer_kv = (size_t)num_pages_ * d.kv_heads * page_ * D;
+  auto wbytes = [&](double N, double K) { return 2.0 * N * K + 2.0 * B * K + 4.0 * B * N; };
+  const double rowb = 4.0 * B * H;
+  static const size_t bank_bytes = [] {
+    const char* e = getenv("HB_DECODE_BANK_MB");
+    return (size_t)(e ? atoi(e) : 0) << 20;
+  }();
+  const bool handover = sig_ != nullptr && !profile_ && (bank_bytes > 0 || dec_trace_);
+  if (handover) CU(cudaMemsetAsync(sig_, 0, (size_t)(5 * d.layers + 1) * sizeof(int), stream_));
+  int prev_idx = -1, prev_count = 0;
+  auto next_sig = [&](int idx, int my_ctas) {
+    StreamSig sg{};
+    if (!handover) return sg;
+    if (prev_idx >= 0) { sg.wait = sig_ + prev_idx; sg.wait_count = prev_count; }
+    sg.done = sig_ + idx;
+    sg.bank_bytes = bank_bytes;
+    sg.trace = dec_trace_ ? dec_trace_ + (size_t)idx * 16 : nullptr;
+    prev_idx = idx;
+    prev_count = my_ctas;
+    return sg;
+  };
+  const int splits = decode_splits(B);
+  const int th = H / 128;
+  auto normed = [&](SkinnyEpi& e) {  // rows of the GEMM input carry gain but not rstd: the finisher applies it
+    e.ss_in = ss_;
+    e.ss_tiles = th;
+    e.norm_h = H;
+    e.eps = d.norm_eps;
+  };
+
+  SPAN(3, rowb, dec_embed_prep(stream_, tokens, model_.embed, model_.ll[0].attn_norm, x_, xn_, ss_, B, H));
+  for (int l = 0; l < d.layers; ++l) {
+    const LlamaLayerW& w = model_.ll[l];
+    bf16* kc = kv_ + (size_t)l * 2 * layer_kv;
+    bf16* vc = kc + layer_kv;
+    {
+      const StreamSig sg = next_sig(5 * l + 0, plan_qkv_.grid);
+      SkinnyEpi e{};
+      e.mode = SK_QKV_ROPE;
+      e.tile_cnt = cnt_qkv_;
+      normed(e);
+      e.qkv_out = qkv_; e.positions = positions; e.slots = slots; e.inv_freq = model_.inv_freq;
+      e.k_cache = kc; e.v_cache = vc; e.Hq = d.heads; e.Hkv = d.kv_heads; e.D = D; e.page_size = page_;
+      SPAN(4, wbytes(QKV, H), gemm_skinny(stream_, plan_qkv_, xn_, H, w.wqkv, H, skinny_ws_, B, QKV, H, &sg, &e));
+    }
+    {
+      AttnDecodeArgs a{};
+      a.q = qkv_; a.ldq = QKV;
+      a.k_cache = kc; a.v_cache = vc;
+      a.page_table = pt; a.max_pages = max_pages_per_seq_;
+      a.ctx_lens = ctx;
+      a.out = attn_; a.ldo = QD;
+      a.workspace = dec_ws_;
+      a.B = B; a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D; a.page_size = page_;
+      a.num_splits = splits;
+      a.scale = 1.0f / sqrtf((float)D);
+      a.num_pages = num_pages_;
+      a.sig = next_sig(5 * l + 1, splits * d.kv_heads * B);
+      SPAN(2, attn_bytes_, attn_decode(stream_, a));
+      if (a.num_splits > 1) launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel
+    }
+    {
+      const StreamSig sg = next_sig(5 * l + 2, plan_o_.grid);
+      SkinnyEpi e{};
+      e.mode = SK_RESID_NORM;
+      e.tile_cnt = cnt_o_;
+      e.x = x_; e.gain = w.mlp_norm; e.xg = xn_; e.ss_out = ss_;
+      SPAN(4, wbytes(H, QD), gemm_skinny(stream_, plan_o_, attn_, QD, w.wo, QD, skinny_ws_, B, H, QD, &sg, &e));
+    }
+    {
+      const StreamSig sg = next_sig(5 * l + 3, plan_gu_.grid);
+      SkinnyEpi e{};
+      e.mode = SK_SWIGLU;
+      e.tile_cnt = cnt_gu_;
+      normed(e);
+      e.h = h_; e.F = F;
+      SPAN(4, wbytes(2.0 * F, H), gemm_skinny(stream_, plan_gu_, xn_, H, w.wgu, H, skinny_ws_, B, 2 * F, H, &sg, &e));
+    }
+    {
+      const StreamSig sg = next_sig(5 * l + 4, plan_down_.grid);
+      SkinnyEpi e{};
+      e.mode = SK_RESID_NORM;
+      e.tile_cnt = cnt_down_;
+      e.x = x_; e.gain = (l + 1 < d.layers) ? model_.ll[l + 1].attn_norm : model_.final_norm; e.xg = xn_; e.ss_out = ss_;
+      SPAN(4, wbytes(H, F), gemm_skinny(stream_, plan_down_, h_, F, w.wdown, F, skinny_ws_, B, H, F, &sg, &e));
+    }
+  }
+  {
+    const StreamSig sg = next_sig(5 * d.layers, plan_head_.grid);
+    SkinnyEpi e{};
+    e.mode = SK_F32;
+    e.tile_cnt = cnt_head_;
+    normed(e);
+    e.out_f32 = logits_; e.ldo = d.vocab;
+    SPAN(4, wbytes(d.vocab, H), gemm_skinny(stream_, plan_head_, xn_, H, model_.lm_head, H, skinny_ws_, B, d.vocab, H, &sg, &e));
+  }
   return sample_step(B, L);
 }
 
@@ -1192,6 +1357,7 @@ int Engine::step(int* did_work) {
   if (cuda_error_.load()) return fail(HB_ERR_CUDA, "engine is in a sticky CUDA error state");
   std::lock_guard<std::mutex> gg(gpu_mu_);
   CU(cudaSetDevice(cfg_.device));
+  SmLimitScope sm_scope(cfg_.sm_budget);
   std::vector<Request*> batch;
   bool prefill = false;
   {
@@ -1316,6 +1482,19 @@ void Engine::loop() {
                         [&] { return stop_.load() || !waiting_.empty() || !running_.empty(); });
       if (stop_.load()) break;
       if (waiting_.empty() && running_.empty()) continue;
+      if (running_.empty() && !waiting_.empty() && waiting_.front()->pages.empty()) {
+        // Idle engine woken by the first request of what is usually a burst (the scheduler releases queued work in one
+        // go, api/pkg/scheduler/scheduler.go:1378-1420): give the rest a moment to arrive (until 150 us pass without a new one, 2 ms at most) so the first prefill step
+        // is a full one instead of a single prompt.  Costs an idle engine at most that much time-to-first-token.
+        size_t seen = waiting_.size();
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
+        while ((int)seen < cfg_.max_seqs && !stop_.load() && std::chrono::steady_clock::now() < deadline) {
+          cv_work_.wait_for(g, std::chrono::microseconds(150));  // every submission notifies: returns early while they keep coming
+          if (waiting_.size() == seen) break;                     // a quiet 150 us: the burst is over
+          seen = waiting_.size();
+        }
+        if (stop_.load()) break;
+      }
     }
     int did = 0;
     int rc = step(&did);
@@ -1367,6 +1546,7 @@ int Engine::embed(const int32_t* toks, const int32_t* offsets, int nseq, float* 
     if (toks[i] < 0 || toks[i] >= d.vocab) return fail(HB_ERR_INVALID, "token id out of range");
   std::lock_guard<std::mutex> gg(gpu_mu_);
   CU(cudaSetDevice(cfg_.device));
+  SmLimitScope sm_scope(cfg_.sm_budget);
   const int bmax = dec ? cfg_.max_seqs : b_cap_;
   int s0 = 0;
   while (s0 < nseq) {

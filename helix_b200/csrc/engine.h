@@ -98,6 +98,9 @@ class Engine {
   int run_decode(std::vector<Request*>& batch);
   int decode_splits(int B) const;
   int forward_llama_decode(int B, const StepLayout& L);
+  int forward_llama_decode_fused(int B, const StepLayout& L);
+  bool fused_decode_ok() const;
+  static size_t fused_counter_ints(const hb_model_desc& d);
   size_t skinny_ws_bytes(int sms) const;
   // profiling spans
   struct Span { int cat; cudaEvent_t a, b; double work; };
@@ -120,6 +123,7 @@ class Engine {
   Model model_;
   bool load_open_ = false, loaded_ = false;
   cudaStream_t stream_ = nullptr;
+  void* green_ctx_ = nullptr;  // sm_partition: the stream lives in a green context of sm_budget SMs
   int page_ = 64, max_pages_per_seq_ = 0, b_cap_ = 0, t_cap_ = 0;
   uint64_t budget_ = 0;
 
@@ -160,6 +164,8 @@ class Engine {
   int step_flags_ = 0;          // StepFlags of the current step: top-k/top-p filter, penalties, log-probabilities
   size_t pen_cap_ = 0;          // penalty entries the step block can hold
   unsigned long long* dec_trace_ = nullptr;  // HB_DEC_TRACE timeline buffer (debug)
+  int *cnt_qkv_ = nullptr, *cnt_o_ = nullptr, *cnt_gu_ = nullptr, *cnt_down_ = nullptr, *cnt_head_ = nullptr;  // tile arrival counters
+  float* ss_ = nullptr;         // [hidden/128][256] per-tile sums of x^2 (RMSNorm statistics carried between finishers)
   int* sig_ = nullptr;          // [5 * layers + 1] HBM hand-over counters of the decode step (kernels.h StreamSig)
   int32_t* lp_ids_ = nullptr;   // [b_cap][HB_MAX_LOGPROBS]
   float* lp_vals_ = nullptr;

@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 #include "tma_host.h"
 
@@ -507,19 +508,20 @@ cudaError_t gemm_bf16_tn(cudaStream_t stream, const GemmArgs& g) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  const int sms = effective_sms(num_sms);  // hb_engine_cfg.sm_budget of the calling engine
   switch (g.epi) {
-    case EPI_NONE: return launch_epi<EPI_NONE>(stream, g, num_sms);
-    case EPI_BIAS: return launch_epi<EPI_BIAS>(stream, g, num_sms);
-    case EPI_BIAS_GELU: return launch_epi<EPI_BIAS_GELU>(stream, g, num_sms);
-    case EPI_RESID: return launch_epi<EPI_RESID>(stream, g, num_sms);
-    case EPI_BIAS_RESID: return launch_epi<EPI_BIAS_RESID>(stream, g, num_sms);
+    case EPI_NONE: return launch_epi<EPI_NONE>(stream, g, sms);
+    case EPI_BIAS: return launch_epi<EPI_BIAS>(stream, g, sms);
+    case EPI_BIAS_GELU: return launch_epi<EPI_BIAS_GELU>(stream, g, sms);
+    case EPI_RESID: return launch_epi<EPI_RESID>(stream, g, sms);
+    case EPI_BIAS_RESID: return launch_epi<EPI_BIAS_RESID>(stream, g, sms);
     case EPI_SWIGLU: {
       if (g.N % 256) return cudaErrorInvalidValue;
       GemmArgs h = g;
       h.block_n = 256;
-      return launch_epi<EPI_SWIGLU>(stream, h, num_sms);
+      return launch_epi<EPI_SWIGLU>(stream, h, sms);
     }
-    case EPI_F32: return launch_epi<EPI_F32>(stream, g, num_sms);
+    case EPI_F32: return launch_epi<EPI_F32>(stream, g, sms);
   }
   return cudaErrorInvalidValue;
 }

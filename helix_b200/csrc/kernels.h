@@ -143,13 +143,42 @@ struct SkinnyPlan {
   int max_segs;              // max #slabs any tile is split into
   const uint8_t* seg_count;  // device [n_tiles]: slabs of each 128-column tile
 };
+// Tile finisher of the decode GEMM: the LAST CTA that contributes a slab to an output tile (one counter per tile) sums
+// the tile's slabs in slab order — bit-deterministic whoever finishes — and applies the op that follows the projection
+// in the decoder layer, so no separate row kernel (and no kernel boundary) sits between two projections.
+enum SkinnyEpiMode : int {
+  SK_SLABS = 0,       // no finisher: slabs only (legacy path, consumed by the dec_* row kernels)
+  SK_F32 = 1,         // out[m, n] = rstd[m] * sum                                   (LM head -> logits)
+  SK_QKV_ROPE = 2,    // bf16(rstd[m] * sum) -> RoPE on q / k heads -> q to qkv_out, k / v into the paged cache
+  SK_RESID_NORM = 3,  // x = bf16(x + sum); xg = bf16(x * gain[n]); ss_out[tile][m] = sum_n x^2 over the tile's columns
+  SK_SWIGLU = 4,      // tiles (2t, 2t+1) = gate / up rows of block t:  h[m, t*128+j] = silu(rstd*gate) * (rstd*up)
+};
+constexpr int kSkinnySsStride = 256;  // row stride of the per-tile sum-of-squares partials ([tile][m], m < 256)
+struct SkinnyEpi {
+  int mode = SK_SLABS;
+  int* tile_cnt = nullptr;          // per-engine arrival counters (zero between launches; the finisher re-zeroes its own)
+  // rstd[m] = rsqrt(sum_t ss_in[t * 256 + m] / norm_h + eps): RMSNorm statistics of the INPUT rows, carried as per-tile
+  // partials by the SK_RESID_NORM finisher of the previous projection (the GEMM is linear in the row factor); null: 1
+  const float* ss_in = nullptr;
+  int ss_tiles = 0, norm_h = 0;
+  float eps = 0.f;
+  float* out_f32 = nullptr; int ldo = 0;                                        // SK_F32
+  bf16* qkv_out = nullptr; const int32_t* positions = nullptr; const int32_t* slots = nullptr;  // SK_QKV_ROPE
+  const float* inv_freq = nullptr; bf16* k_cache = nullptr; bf16* v_cache = nullptr;
+  int Hq = 0, Hkv = 0, D = 0, page_size = 64;
+  bf16* x = nullptr; const bf16* gain = nullptr; bf16* xg = nullptr; float* ss_out = nullptr;   // SK_RESID_NORM
+  bf16* h = nullptr; int F = 0;                                                  // SK_SWIGLU
+};
+// x = table[token]; xg = bf16(x * gain); ss_out[tile][m] = per-128-column sums of x^2 (what SK_RESID_NORM leaves behind)
+cudaError_t dec_embed_prep(cudaStream_t s, const int32_t* tokens, const bf16* table, const bf16* gain, bf16* x, bf16* xg,
+                           float* ss_out, int M, int H);
 cudaError_t gemm_skinny_init();
 cudaError_t gemm_skinny_plan(int N, int K, SkinnyPlan* out);  // cached per (device, N, K)
 size_t gemm_skinny_ws_floats(const SkinnyPlan& p, int M, int N);
 int gemm_skinny_max_segs(int N, int K, int sms);  // pure host arithmetic (memory estimates)
 // ws[seg][m][n] (seg < seg_count[n/128]) = partial sums of X[M,K] . W[N,K]^T
 cudaError_t gemm_skinny(cudaStream_t stream, const SkinnyPlan& plan, const bf16* X, int ldx, const bf16* W, int ldw,
-                        float* ws, int M, int N, int K, const StreamSig* sig = nullptr);
+                        float* ws, int M, int N, int K, const StreamSig* sig = nullptr, const SkinnyEpi* epi = nullptr);
 // consumers of the slabs (each sums the slabs in fixed order, then applies its fused epilogue)
 cudaError_t dec_sum_slabs(cudaStream_t s, const float* ws, const SkinnyPlan& p, float* out, int ldo, int M, int N);
 cudaError_t dec_qkv_rope_kvwrite(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* qkv_out,

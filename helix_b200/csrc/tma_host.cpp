@@ -36,6 +36,75 @@ bool pdl_enabled() {
   return on;
 }
 
+int& sm_limit() {
+  thread_local int lim = 0;
+  return lim;
+}
+int effective_sms(int device_sms) {
+  const int lim = sm_limit();
+  return lim > 0 ? (lim < device_sms ? lim : device_sms) : device_sms;
+}
+
+// ---- green contexts through the runtime's driver entry points (the library links libcudart only)
+namespace {
+template <typename F>
+bool drv(const char* name, F& fn) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return false;
+  fn = reinterpret_cast<F>(p);
+  return true;
+}
+}  // namespace
+
+bool create_partition_stream(int device, int sm_count, int priority, cudaStream_t* stream, void** green_ctx, int* granted,
+                             const char** why) {
+  static thread_local char msg[160];
+  auto fail = [&](const char* what, int code) {
+    snprintf(msg, sizeof msg, "green context: %s failed (%d)", what, code);
+    if (why) *why = msg;
+    return false;
+  };
+  CUresult (*getRes)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+  CUresult (*genDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*gcCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*gcStream)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  CUresult (*devGet)(CUdevice*, int) = nullptr;
+  if (!drv("cuDeviceGetDevResource", getRes) || !drv("cuDevSmResourceSplitByCount", split) ||
+      !drv("cuDevResourceGenerateDesc", genDesc) || !drv("cuGreenCtxCreate", gcCreate) ||
+      !drv("cuGreenCtxStreamCreate", gcStream) || !drv("cuDeviceGet", devGet))
+    return fail("driver entry points", -1);
+  CUdevice dev;
+  CUresult r = devGet(&dev, device);
+  if (r != CUDA_SUCCESS) return fail("cuDeviceGet", (int)r);
+  CUdevResource all, part, rest;
+  if ((r = getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM)) != CUDA_SUCCESS) return fail("cuDeviceGetDevResource", (int)r);
+  unsigned int groups = 1;
+  if ((r = split(&part, &groups, &all, &rest, 0, (unsigned int)sm_count)) != CUDA_SUCCESS || groups < 1)
+    return fail("cuDevSmResourceSplitByCount", (int)r);
+  CUdevResourceDesc desc;
+  if ((r = genDesc(&desc, &part, 1)) != CUDA_SUCCESS) return fail("cuDevResourceGenerateDesc", (int)r);
+  CUgreenCtx gc;
+  if ((r = gcCreate(&gc, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) return fail("cuGreenCtxCreate", (int)r);
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least urgent (numerically largest), hi = most urgent
+  CUstream st;
+  if ((r = gcStream(&st, gc, CU_STREAM_NON_BLOCKING, priority > 0 ? hi : lo)) != CUDA_SUCCESS) {
+    destroy_partition(gc);
+    return fail("cuGreenCtxStreamCreate", (int)r);
+  }
+  *stream = reinterpret_cast<cudaStream_t>(st);
+  *green_ctx = gc;
+  if (granted) *granted = (int)part.sm.smCount;
+  return true;
+}
+
+void destroy_partition(void* green_ctx) {
+  CUresult (*gcDestroy)(CUgreenCtx) = nullptr;
+  if (green_ctx && drv("cuGreenCtxDestroy", gcDestroy)) gcDestroy(reinterpret_cast<CUgreenCtx>(green_ctx));
+}
+
 bool make_tmap_2d(CUtensorMap* out, const void* gptr, TmDtype dt, uint64_t inner, uint64_t outer,
                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   std::call_once(g_once, resolve);

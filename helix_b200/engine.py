@@ -36,11 +36,12 @@ class EngineConfig:
     sm_partition: int = 0         # 1: enforce sm_budget with a CUDA green context
     stream_priority: int = 0      # 1: high-priority stream
     decode_with_prefill: int = 0  # 1: running sequences decode inside prefill steps (mixed batches)
+    fused_decode: int = 0         # 1: decode GEMMs with tile finishers instead of separate row kernels (measured slower)
 
     def to_c(self):
         return EngineCfg(self.device, self.memory_budget_bytes, self.max_seqs, self.max_ctx, self.max_batched_tokens,
                          self.kv_page_size, self.use_cuda_graphs, self.enable_prefix_cache, self.sm_budget,
-                         self.sm_partition, self.stream_priority, self.decode_with_prefill)
+                         self.sm_partition, self.stream_priority, self.decode_with_prefill, self.fused_decode)
 
 
 @dataclass

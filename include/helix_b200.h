@@ -73,7 +73,10 @@ typedef struct hb_engine_cfg {
   int32_t decode_with_prefill;  /* 1 (what the runtime passes): running sequences decode inside prefill steps (vLLM-style
                                    mixed batches) so a long prompt never stalls the streams; 0: prefill steps exclude
                                    decode rows (benchmark-pure phases) */
-  int32_t reserved[2];
+  int32_t fused_decode;         /* 1: decode GEMMs run with tile finishers (the last CTA of each stream-K tile applies RoPE+KV
+                                   write / residual+norm statistics / SwiGLU itself: 5 kernels per layer instead of 9).
+                                   Measured slower than the separate row kernels on B200, so off by default */
+  int32_t reserved[1];
 } hb_engine_cfg;
 
 typedef struct hb_model_desc {

@@ -21,6 +21,10 @@ int hbk_gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, c
              int M, int N, int K, int epi, int block_n);
 /* decode-step GEMM (M<=256): swap-AB + stream-K partial slabs summed in fixed order -> out fp32 [M,N] */
 int hbk_gemm_skinny(const void* X, int ldx, const void* W, int ldw, float* out_f32, int ldo, int M, int N, int K);
+/* the same GEMM with the fused tile finisher (last-arriving CTA of each output tile sums the slabs in slab order and
+ * writes out[m, n]); launched `repeats` times back to back: the arrival counters must return to zero by themselves */
+int hbk_gemm_skinny_finish(const void* X, int ldx, const void* W, int ldw, float* out_f32, int ldo, int M, int N, int K,
+                           int repeats);
 int hbk_gemm_naive(const void* A, int lda, const void* W, int ldw, void* C_f32, int ldc, int M, int N, int K);
 
 int hbk_embed_gather(const int32_t* tokens, const void* table, void* x, int T, int H);

@@ -52,14 +52,15 @@ def check_greedy(oracle, prompt, toks):
 
 
 @pytest.mark.parametrize("name", sorted(LLAMA_CASES))
-@pytest.mark.parametrize("graphs", [0, 1])
-def test_llama_matches_golden_and_oracle(name, graphs, golden_dir):
+@pytest.mark.parametrize("graphs,fused", [(0, 0), (1, 0), (1, 1)])
+def test_llama_matches_golden_and_oracle(name, graphs, fused, golden_dir):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     d = LLAMA_CASES[name]()
     sd = weights.llama_state_dict(d, int(g["seed"]), float(g["std"]))
     prompt = g["prompt"]
     n_dec = len(g["greedy_tokens"])
-    with hb.Engine(hb.EngineConfig(max_seqs=8, max_ctx=512, max_batched_tokens=1024, use_cuda_graphs=graphs)) as e:
+    # fused = 1: the decode GEMMs' tile finishers (RoPE + KV write, residual + norm statistics, SwiGLU inside the GEMM)
+    with hb.Engine(hb.EngineConfig(max_seqs=8, max_ctx=512, max_batched_tokens=1024, use_cuda_graphs=graphs, fused_decode=fused)) as e:
         e.load_state_dict(d, sd)
         rids, outs = e.generate([prompt], hb.Sampling(max_tokens=n_dec, capture=CAPTURE_PROMPT_LOGITS | CAPTURE_STEP_LOGITS))
         pl = e.captured_logits(rids[0], CAPTURE_PROMPT_LOGITS)

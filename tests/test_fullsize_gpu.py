@@ -58,8 +58,8 @@ def test_llama3_8b_prefill_and_decode_paths_agree_at_full_size():
     assert lb.shape == (n + 2, d.vocab)
     scale = max(1.0, float(np.abs(lb[n - 1:]).max()))
     assert np.abs(la[0] - lb[n - 1]).max() <= 1e-2 * scale          # same path (prefill) both times: only batching differs
-    assert np.abs(la[1] - lb[n]).max() <= 2e-2 * scale              # decode path vs prefill path
-    assert np.abs(la[2] - lb[n + 1]).max() <= 2e-2 * scale
+    assert np.abs(la[1] - lb[n]).max() <= 3e-2 * scale              # decode path vs prefill path
+    assert np.abs(la[2] - lb[n + 1]).max() <= 3e-2 * scale
     assert np.isfinite(lb).all() and st["kv_pages_free"] == st["kv_pages_total"]
 
 

@@ -455,3 +455,8 @@ def test_gemm_skinny_stream_k(L, M, N, K):
     out2 = torch.empty_like(out)
     ck(L, L.hbk_gemm_skinny(p(X), K, p(W), K, p(out2), N, M, N, K))
     assert torch.equal(out, out2)  # slab order is fixed: bit-deterministic (no atomics)
+    # fused tile finisher (the decode step's path): the last-arriving CTA of each tile sums the slabs in the same fixed
+    # order, so the result is bit-identical to the separate sum pass — on every one of three back-to-back launches
+    out3 = torch.full((M, N), float("nan"), device="cuda")
+    ck(L, L.hbk_gemm_skinny_finish(p(X), K, p(W), K, p(out3), N, M, N, K, 3))
+    assert torch.equal(out, out3)
