@@ -12,8 +12,9 @@ cache.  tokens = sessions * (seq + decode).
   roofline / kernels : one extra profiled step (CUDA-event span around every launch, same stream)
   fixed_total  : BASELINE configs[4] framing in the same line: 256 sessions in total, routed from rank 0 with the
                  scheduler's least-active rule (replica.route_least_active == pickBestWarmSlot), 256/N per GPU
-  cpu_baseline / --impl reference : HF transformers LlamaForCausalLM on torch CPU (the stand-in for the
-                 reference's llama.cpp CPU path, which cannot run offline), all host threads, bounded sample
+  cpu_baseline / --impl reference : CPU stand-in for the reference's llama.cpp CPU path (cannot run offline): the numpy
+                 oracle port on all host threads (pinned with threadpoolctl), bounded sample; --cpu-impl hf switches to
+                 HF transformers on torch CPU, which measured 30x slower on the GPU box (profiles/r02c_reference_hf.json)
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload llama8b|bge|pack]
 """
@@ -202,55 +203,119 @@ def hf_session(m, torch, prompt_len, decode):
     return time.perf_counter() - t0
 
 
-def cpu_stand_in(layers, prompt_len, decode, steps, warmup, budget_s=None):
-    """Times `steps` sessions (after `warmup`) on all host threads.  With budget_s the prompt length is first calibrated
-    down from `prompt_len` so warmup+steps sessions fit the budget."""
-    threads = os.cpu_count() or 1
-    m, torch = hf_llama_cpu(layers, threads)
-    if budget_s is not None:
-        t_probe = hf_session(m, torch, 128, 2)          # also warms the thread pool / allocator
-        t_probe = hf_session(m, torch, 128, 2)
-        per_tok = t_probe / 130.0
-        while prompt_len > 128 and (warmup + steps) * per_tok * (prompt_len + 3 * decode) > budget_s:
-            prompt_len //= 2
+def host_threads():
+    """All host cores for the BLAS behind numpy / torch, whatever the launcher exported (torch.distributed.run sets
+    OMP_NUM_THREADS=1, which made the r01 reference arm single-threaded at N >= 2)."""
+    n = os.cpu_count() or 1
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(n)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+        from threadpoolctl import threadpool_info
+        got = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        got = n
+    return got
+
+
+def oracle_port(layers, prompt_len):
+    """The numpy fp32 oracle (oracle/llama_ref.py) at the Llama-3-8B shape with `layers` of the 32 identical layers:
+    returns run(decode) -> seconds for one session (prefill + greedy decode)."""
+    from helix_b200 import configs
+    from oracle.llama_ref import LlamaOracle
+    d = configs.llama3_8b()
+    d.layers = layers
+    rng = np.random.default_rng(0)
+    block = (rng.standard_normal(1 << 22, dtype=np.float32) * 0.02)
+
+    def filled(shape):
+        return np.resize(block, int(np.prod(shape))).reshape(shape)
+    H, F, V, D = d.hidden, d.ffn, d.vocab, d.head_dim
+    sd = {"model.embed_tokens.weight": filled((V, H)), "lm_head.weight": filled((V, H)), "model.norm.weight": np.ones(H, np.float32)}
+    for i in range(layers):
+        p = f"model.layers.{i}."
+        sd[p + "input_layernorm.weight"] = np.ones(H, np.float32)
+        sd[p + "post_attention_layernorm.weight"] = np.ones(H, np.float32)
+        sd[p + "self_attn.q_proj.weight"] = filled((d.heads * D, H))
+        sd[p + "self_attn.k_proj.weight"] = filled((d.kv_heads * D, H))
+        sd[p + "self_attn.v_proj.weight"] = filled((d.kv_heads * D, H))
+        sd[p + "self_attn.o_proj.weight"] = filled((H, d.heads * D))
+        sd[p + "mlp.gate_proj.weight"] = filled((F, H))
+        sd[p + "mlp.up_proj.weight"] = filled((F, H))
+        sd[p + "mlp.down_proj.weight"] = filled((H, F))
+    o = LlamaOracle(d, sd)
+    toks = rng.integers(0, V, size=prompt_len).astype(np.int32)
+
+    def run(decode):
+        t0 = time.perf_counter()
+        o.greedy(toks, decode)
+        return time.perf_counter() - t0
+    return run
+
+
+def cpu_stand_in(impl, steps, warmup, budget_s, prompt_len=512, decode=8):
+    """`steps` timed sessions after `warmup` on all host threads.  The model is truncated to as many of the 32 identical
+    layers (8, 4 or 2) as lets warmup+steps sessions finish inside budget_s on this box; the factor 32/layers is reported
+    next to the MEASURED step time, never folded into it."""
+    threads = host_threads()
+    if impl == "hf":
+        m, torch = hf_llama_cpu(8, threads)
+        layers, run = 8, (lambda dec: hf_session(m, torch, prompt_len, dec))
+        run(2)
+    else:
+        layers = 8
+        run = oracle_port(layers, prompt_len)
+        t = run(decode)                      # probe (also warms BLAS threads)
+        while layers > 2 and t * (warmup + steps) > budget_s:
+            layers //= 2
+            run = oracle_port(layers, prompt_len)
+            t = run(decode)
     for _ in range(warmup):
-        hf_session(m, torch, prompt_len, decode)
-    ts = [hf_session(m, torch, prompt_len, decode) for _ in range(steps)]
-    return {"seconds": ts, "threads": torch.get_num_threads(), "prompt_len": prompt_len, "decode": decode, "layers": layers}
+        run(decode)
+    ts = [run(decode) for _ in range(steps)]
+    return {"seconds": ts, "threads": threads, "prompt_len": prompt_len, "decode": decode, "layers": layers, "impl": impl}
+
+
+def cpu_sample_text(r):
+    what = ("the numpy fp32 oracle port (oracle/llama_ref.py)" if r["impl"] == "oracle" else
+            "HF transformers LlamaForCausalLM fp32 on torch CPU")
+    return (f"{what}, {r['threads']} BLAS threads, Llama-3-8B shape truncated to {r['layers']}/32 layers, ONE session per step: "
+            f"{r['prompt_len']}-token prompt + {r['decode']} greedy decode tokens; value = tokens / (measured step time x "
+            f"{32 // r['layers']}); stand-in for the reference's llama.cpp CPU path (DEVELOPMENT_CPU_ONLY), which cannot run "
+            f"offline.  (HF transformers on torch CPU, the stand-in BASELINE.md names, measured 0.55 tokens/s on this box class "
+            f"— 245 s per 136-token session, profiles/r02c_reference_hf.json — so the faster port is the fairer baseline.)")
 
 
 def reference_arm(args, rank, world):
-    """--impl reference: the CPU stand-in, FULL 32-layer model, one session per step, K timed steps after W warm-ups; the
-    prompt is the workload's 2048 tokens unless the box's cores need a shorter one to finish in a few minutes (stated)."""
+    """--impl reference: K timed steps after W warm-ups of the CPU stand-in, one session per step, sized to finish in a
+    few minutes.  ms_per_step is the measured time of what ran; the depth extrapolation is a separate, stated factor."""
     if rank != 0:
         return
-    r = cpu_stand_in(32, args.seq, 8, args.steps, args.warmup, budget_s=240.0)
+    r = cpu_stand_in(args.cpu_impl, args.steps, args.warmup, budget_s=200.0)
     t = statistics.mean(r["seconds"])
+    factor = 32 / r["layers"]
     toks = r["prompt_len"] + r["decode"]
-    v = toks / t
-    sample = (f"HF transformers LlamaForCausalLM fp32 on torch CPU, {r['threads']} threads, full 32-layer Llama-3-8B shape "
-              f"(random init), ONE session per step: {r['prompt_len']}-token prompt + {r['decode']} greedy decode tokens through "
-              f"the KV cache; stand-in for the reference's llama.cpp CPU path (DEVELOPMENT_CPU_ONLY), which cannot run offline")
+    v = toks / (t * factor)
+    sample = cpu_sample_text(r)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "sample": sample, "tokens_per_step": toks},
+            "config": {"workload": workload_name(args), "sample": sample, "tokens_per_step": toks, "layers_run": r["layers"],
+                       "extrapolation_factor": factor},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample,
-                             "step_seconds": r["seconds"]},
+                             "measured_step_seconds": r["seconds"], "extrapolation_factor": factor},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_field(kind="llama"):
-    """Bounded (~10-30 s) CPU sample for the native line at N=1: 8 of the 32 identical layers, one 512+8-token session;
-    tokens/s for the full model = measured / (32/8) — the factor is reported, not hidden."""
-    r = cpu_stand_in(8, 512, 8, 1, 1)
+def cpu_baseline_field(impl="oracle"):
+    """Bounded CPU sample for the native line at N=1 (one probe + one timed session, <= ~30 s)."""
+    r = cpu_stand_in(impl, 1, 0, budget_s=25.0)
     t = r["seconds"][0]
-    factor = 32 / 8
-    return {"value": (512 + 8) / (t * factor), "unit": UNIT, "cores": r["threads"], "kind": "port", "measured_seconds": t,
-            "extrapolation_factor": factor,
-            "sample": f"HF transformers LlamaForCausalLM fp32 on torch CPU, {r['threads']} threads, Llama-3-8B shape truncated to 8/32 "
-                      f"layers (time x4), 1 session x 512-token prompt + 8 decode tokens; stand-in for the reference's llama.cpp CPU path"}
+    factor = 32 / r["layers"]
+    return {"value": (r["prompt_len"] + r["decode"]) / (t * factor), "unit": UNIT, "cores": r["threads"], "kind": "port",
+            "measured_seconds": t, "extrapolation_factor": factor, "sample": cpu_sample_text(r)}
 
 
 # ------------------------------------------------------------------ configs[2]: bge-base batch encode
@@ -323,29 +388,22 @@ def bench_bge(args):
     e.close()
 
 
-def bge_cpu_baseline(chunks=64):
-    threads = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(threads)
-    import torch
-    torch.set_num_threads(threads)
-    torch.set_grad_enabled(False)
-    from transformers import BertConfig, BertModel
-    cfg = BertConfig(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
-                     max_position_embeddings=512, attn_implementation="sdpa")
-    m = BertModel(cfg, add_pooling_layer=False).float().eval()
-    ids = torch.from_numpy(np.random.default_rng(3).integers(0, 30522, size=(chunks, 512))).long()
-
-    def run():
-        t0 = time.perf_counter()
-        for i in range(0, chunks, 16):
-            h = m(input_ids=ids[i:i + 16]).last_hidden_state[:, 0]
-            torch.nn.functional.normalize(h, dim=-1)
-        return time.perf_counter() - t0
-    run()
-    t = run()
-    return {"value": chunks / t, "unit": "chunks/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"HF transformers BertModel (bge-base-en shape, random init) fp32 on torch CPU, {torch.get_num_threads()} threads, "
-                      f"{chunks} chunks x 512 tokens in batches of 16, CLS + L2"}
+def bge_cpu_baseline(chunks=16):
+    """The numpy fp32 oracle (oracle/bert_ref.py) on all host threads over a bounded sample of the same workload."""
+    threads = host_threads()
+    from helix_b200 import configs
+    from oracle.bert_ref import bert_embed
+    from oracle import weights
+    d = configs.bge_base()
+    sd = weights.bert_state_dict(d, 2, 0.02)
+    seqs = [np.random.default_rng(30 + i).integers(0, d.vocab, size=512).astype(np.int32) for i in range(chunks)]
+    bert_embed(d, sd, seqs[:2])
+    t0 = time.perf_counter()
+    bert_embed(d, sd, seqs)
+    t = time.perf_counter() - t0
+    return {"value": chunks / t, "unit": "chunks/s", "cores": threads, "kind": "port", "measured_seconds": t,
+            "sample": f"numpy fp32 oracle port (oracle/bert_ref.py), {threads} BLAS threads, {chunks} chunks x 512 tokens, one chunk at a "
+                      f"time, CLS + L2 (HF BertModel on torch CPU measured 1.3 chunks/s on this box class)"}
 
 
 # ------------------------------------------------------------------ configs[3]: multi-model pack on one GPU
@@ -446,13 +504,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--sessions", type=int, default=32)
-    ap.add_argument("--seq", type=int, default=2048)
+    ap.add_argument("--seq", type=int, default=640)
     ap.add_argument("--decode", type=int, default=128)
     ap.add_argument("--max-seqs", type=int, default=256, help="--max-num-seqs of the slot (the reference's vLLM default)")
     ap.add_argument("--max-batched-tokens", type=int, default=16384)
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-impl", default="oracle", choices=["oracle", "hf"], help="CPU stand-in behind cpu_baseline / --impl reference")
     ap.add_argument("--no-fixed-total", action="store_true")
+    ap.add_argument("--mixed-step-tokens", type=int, default=640)
     ap.add_argument("--fixed-total-sessions", type=int, default=256)
     ap.add_argument("--layers", type=int, default=0, help="debug: truncate the model (INVALID as a bench number)")
     ap.add_argument("--workload", default="llama8b", choices=["llama8b", "bge", "pack"])
@@ -551,7 +611,16 @@ def main():
     prefill_steps = (s1["steps_prefill"] - s0["steps_prefill"]) / args.steps
 
     latency = serve_latency(e, hb, prompts, args.decode)
-    latency_spread = serve_latency(e, hb, prompts, args.decode, spread_s=1.0) if rank == 0 or world == 1 else None
+    latency_spread = latency_mixed = None
+    if rank == 0:
+        # arrivals spread over a second: with pure phases every later prompt's prefill step stalls the running streams;
+        # with mixed steps (what the runtime passes: decode_with_prefill, 2048-token steps) they keep decoding
+        latency_spread = serve_latency(e, hb, prompts, args.decode, spread_s=1.0)
+        e.set_mixed(1, args.mixed_step_tokens)
+        serve_once(e, hb, prompts[:4], 4)   # first use of the mixed path (paged prefill attention variants)
+        latency_mixed = serve_latency(e, hb, prompts, args.decode, spread_s=1.0)
+        latency_mixed["scheduler"] = f"decode_with_prefill=1, mixed_step_tokens={args.mixed_step_tokens}"
+        e.set_mixed(0, 0)
 
     # ---- BASELINE configs[4] framing: a FIXED total of sessions, routed by the scheduler's rule from rank 0
     fixed = None
@@ -661,9 +730,10 @@ def main():
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "hb_submit/hb_wait/hb_poll (C ABI, host buffers, step-loop thread)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "phases": phases,
-                "latency": latency, "latency_spread_arrivals": latency_spread, "fixed_total": fixed}
+                "latency": latency, "latency_spread_arrivals": latency_spread, "latency_spread_arrivals_mixed_steps": latency_mixed,
+                "fixed_total": fixed}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_field()
+            line["cpu_baseline"] = cpu_baseline_field(args.cpu_impl)
         print(json.dumps(line), flush=True)
     e.close()
     if world > 1:

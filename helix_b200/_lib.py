@@ -15,7 +15,7 @@ class EngineCfg(C.Structure):
                 ("max_ctx", C.c_int32), ("max_batched_tokens", C.c_int32), ("kv_page_size", C.c_int32),
                 ("use_cuda_graphs", C.c_int32), ("enable_prefix_cache", C.c_int32), ("sm_budget", C.c_int32),
                 ("sm_partition", C.c_int32), ("stream_priority", C.c_int32), ("decode_with_prefill", C.c_int32),
-                ("fused_decode", C.c_int32), ("reserved", C.c_int32 * 1)]
+                ("fused_decode", C.c_int32), ("mixed_step_tokens", C.c_int32)]
 
 
 class ModelDescC(C.Structure):
@@ -39,8 +39,8 @@ class StatsC(C.Structure):
                 ("running", C.c_int32), ("waiting", C.c_int32), ("steps_prefill", C.c_uint64),
                 ("steps_decode", C.c_uint64), ("tokens_prefill", C.c_uint64), ("tokens_decode", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("graph_launches", C.c_uint64), ("cuda_error", C.c_int32),
-                ("kv_pages_cached", C.c_int32), ("reserved0", C.c_int32), ("prefix_hit_tokens", C.c_uint64),
-                ("reserved", C.c_int32 * 3), ("gpu_ms_prefill", C.c_double), ("gpu_ms_decode", C.c_double),
+                ("kv_pages_cached", C.c_int32), ("preemptions", C.c_int32), ("prefix_hit_tokens", C.c_uint64),
+                ("steps_mixed", C.c_uint64), ("reserved", C.c_int32 * 1), ("gpu_ms_prefill", C.c_double), ("gpu_ms_decode", C.c_double),
                 ("prof_ms", C.c_double * 8), ("prof_work", C.c_double * 8), ("prof_launches", C.c_uint64 * 8)]
 
 
@@ -61,6 +61,7 @@ SIGNATURES = {
                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "hb_engine_start": (I, [P]),
     "hb_engine_stop": (I, [P]),
+    "hb_engine_set_mixed": (I, [P, C.c_int32, C.c_int32]),
     "hb_step": (I, [P, C.POINTER(I)]),
     "hb_submit": (I, [P, P, C.c_int32, C.POINTER(SamplingC), C.POINTER(C.c_uint64)]),
     "hb_poll": (I, [P, C.c_uint64, P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -65,6 +65,7 @@ int hb_memory_estimate(const hb_model_desc* d, const hb_engine_cfg* c, uint64_t*
 
 int hb_engine_start(hb_engine* e) { return e ? e->impl.start() : HB_ERR_INVALID; }
 int hb_engine_stop(hb_engine* e) { return e ? e->impl.stop() : HB_ERR_INVALID; }
+int hb_engine_set_mixed(hb_engine* e, int32_t on, int32_t tokens) { return e ? e->impl.set_mixed(on, tokens) : HB_ERR_INVALID; }
 int hb_step(hb_engine* e, int* did) { return e ? e->impl.step(did) : HB_ERR_INVALID; }
 int hb_submit(hb_engine* e, const int32_t* t, int32_t n, const hb_sampling* sp, uint64_t* id) {
   return e ? e->impl.submit(t, n, sp, id) : HB_ERR_INVALID;

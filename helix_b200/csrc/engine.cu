@@ -58,6 +58,7 @@ Engine::Engine(const hb_engine_cfg& cfg) : cfg_(cfg) {
   if (cfg_.max_ctx <= 0) cfg_.max_ctx = 8192;
   if (cfg_.max_batched_tokens <= 0) cfg_.max_batched_tokens = 16384;
   if (cfg_.kv_page_size <= 0) cfg_.kv_page_size = 64;
+  if (cfg_.mixed_step_tokens < 0) cfg_.mixed_step_tokens = 0;
   page_ = cfg_.kv_page_size;
 }
 
@@ -1157,7 +1158,7 @@ int Engine::collect_logprobs(Request* const* batch, int B, bool prefill) {
   for (int i = 0; i < B; ++i) {
     Request* r = batch[i];
     const int w = std::max(0, std::min(r->sp.logprobs, (int)HB_MAX_LOGPROBS));
-    if (w == 0 || (prefill && r->prefilled + r->chunk < (int)r->prompt.size())) continue;  // not the last chunk: nothing sampled
+    if (w == 0 || (prefill && r->prefilled + r->chunk < r->target)) continue;  // not the last chunk: nothing sampled
     r->lp_ids.insert(r->lp_ids.end(), h_lp_ids_ + (size_t)i * HB_MAX_LOGPROBS, h_lp_ids_ + (size_t)i * HB_MAX_LOGPROBS + w);
     r->lp_vals.insert(r->lp_vals.end(), h_lp_vals_ + (size_t)i * HB_MAX_LOGPROBS, h_lp_vals_ + (size_t)i * HB_MAX_LOGPROBS + w);
   }
@@ -1192,7 +1193,7 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   for (Request* r : batch) {  // this step covers prompt[prefilled, prefilled + chunk) of every request
     T += r->chunk;
     max_len = std::max(max_len, r->chunk);
-    want_all |= (r->sp.capture & HB_CAPTURE_PROMPT_LOGITS) != 0;
+    want_all |= (r->sp.capture & HB_CAPTURE_PROMPT_LOGITS) != 0 && r->prefilled + r->chunk <= (int)r->prompt.size();
     paged |= r->prefilled > 0;
   }
   if (want_all) {
@@ -1219,7 +1220,7 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
     cu[i] = t;
     const int end = r->prefilled + r->chunk;
     for (int j = r->prefilled; j < end; ++j, ++t) {
-      tok[t] = r->prompt[j];
+      tok[t] = token_at(r, j);  // generated tokens too: decode rows of a mixed step, resumed (preempted) sequences
       pos[t] = j;
       slot[t] = r->pages[j / page_] * page_ + j % page_;
     }
@@ -1257,12 +1258,12 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   // captures (test tap; synchronous copies are fine here)
   for (int i = 0; i < B; ++i) {
     Request* r = batch[i];
-    if (r->sp.capture & HB_CAPTURE_PROMPT_LOGITS) {
+    if ((r->sp.capture & HB_CAPTURE_PROMPT_LOGITS) && r->prefilled + r->chunk <= (int)r->prompt.size()) {
       r->prompt_logits.resize(r->prompt.size() * (size_t)d.vocab);
       CU(cudaMemcpy(r->prompt_logits.data() + (size_t)r->prefilled * d.vocab, all_logits_ + (size_t)cu[i] * d.vocab,
                     (size_t)r->chunk * d.vocab * 4, cudaMemcpyDeviceToHost));
     }
-    if ((r->sp.capture & HB_CAPTURE_STEP_LOGITS) && r->prefilled + r->chunk == (int)r->prompt.size()) {
+    if ((r->sp.capture & HB_CAPTURE_STEP_LOGITS) && r->prefilled + r->chunk == r->target) {
       const size_t o = r->step_logits.size();
       r->step_logits.resize(o + d.vocab);
       CU(cudaMemcpy(r->step_logits.data() + o, logits_ + (size_t)i * d.vocab, (size_t)d.vocab * 4, cudaMemcpyDeviceToHost));
@@ -1350,6 +1351,44 @@ int Engine::run_decode(std::vector<Request*>& batch) {
   return HB_OK;
 }
 
+// A running sequence loses its pages (they stay content-addressed in the prefix cache while unreferenced) and goes back
+// to the head of the queue; on re-admission prompt + generated tokens are prefilled again — vLLM's recompute preemption,
+// what `--max-num-seqs` implies in the backend the reference spawns (api/pkg/runner/vllm_runtime.go:705-762).  mu_ held.
+void Engine::preempt(Request* v) {
+  running_.erase(std::remove(running_.begin(), running_.end(), v), running_.end());
+  for (auto it = v->pages.rbegin(); it != v->pages.rend(); ++it) drop_page(*it);
+  v->pages.clear();
+  v->kv_len = v->prefilled = v->registered = 0;
+  v->chain_key = 0;
+  v->in_running = false;
+  v->preempted += 1;
+  v->state = ReqState::WAITING;
+  preemptions_++;
+  auto pos = waiting_.begin();
+  if (pos != waiting_.end() && !(*pos)->pages.empty()) ++pos;  // never in front of a prompt that is between its chunks
+  waiting_.insert(pos, v);
+}
+
+// Every running sequence owns the page its next position falls into; when the pool is empty the most recently admitted
+// running sequence is preempted (possibly the one that asked).  mu_ held.
+void Engine::ensure_decode_pages() {
+  for (size_t i = 0; i < running_.size();) {
+    Request* r = running_[i];
+    const int need_idx = r->kv_len / page_;
+    bool gone = false;
+    while ((int)r->pages.size() <= need_idx) {
+      if (pages_available() > 0) {
+        r->pages.push_back(take_page());
+      } else {
+        Request* v = running_.back();
+        preempt(v);
+        if (v == r) { gone = true; break; }
+      }
+    }
+    if (!gone) ++i;
+  }
+}
+
 int Engine::step(int* did_work) {
   if (did_work) *did_work = 0;
   if (!loaded_) return fail(HB_ERR_STATE, "hb_step before a model is loaded");
@@ -1365,6 +1404,7 @@ int Engine::step(int* did_work) {
     // retire cancelled sequences
     for (size_t i = 0; i < running_.size();) {
       if (running_[i]->cancel_flag) {
+        running_[i]->in_running = false;
         finish_request(running_[i], ReqState::CANCELLED);
         running_.erase(running_.begin() + i);
         cv_out_.notify_all();
@@ -1377,38 +1417,55 @@ int Engine::step(int* did_work) {
       waiting_.pop_front();
       cv_out_.notify_all();
     }
-    // admission: FIFO; pages for prompt + max_tokens reserved up front (no preemption).  Prompts are packed whole into
-    // the step's token budget; only a prompt LONGER than the budget is split, and then runs as budget-sized chunks of
-    // its own (chunks after the first attend to the already cached prefix through the paged pool).
+    // Token budget of this step.  With decode_with_prefill the running sequences ride along in prefill steps (one token
+    // each, attending to their cached context through the paged attention path — vLLM's mixed batches), and such steps
+    // are kept short (mixed_step_tokens) so that a long prompt is spread over several of them instead of stalling every
+    // running stream for the length of a full prefill step.
+    const bool mixed = cfg_.decode_with_prefill != 0 && !running_.empty();
+    const int mixed_cap = cfg_.mixed_step_tokens > 0 ? cfg_.mixed_step_tokens : 2048;
+    const int budget = mixed ? std::max(64, std::min(t_cap_, mixed_cap) - (int)running_.size()) : t_cap_;
+    // admission: FIFO.  A sequence takes pages for what it is about to prefill plus its first generated token; further
+    // pages are taken as it grows (ensure_decode_pages), so max_tokens does not hold memory it may never use.  Prompts are
+    // packed whole into the step's token budget; only a prompt LONGER than the budget is split, and then runs as
+    // budget-sized chunks (chunks after the first attend to the already cached prefix through the paged pool).
     int T = 0;
+    std::vector<int32_t> seq;
     while (!waiting_.empty()) {
       Request* r = waiting_.front();
-      const int n = (int)r->prompt.size();
       if (r->pages.empty()) {
+        // a preempted sequence resumes by prefilling prompt + everything it had generated
+        const int n = (int)(r->prompt.size() + r->out.size());
+        const int32_t* toks = r->prompt.data();
+        if (!r->out.empty()) {
+          seq.assign(r->prompt.begin(), r->prompt.end());
+          seq.insert(seq.end(), r->out.begin(), r->out.end());
+          toks = seq.data();
+        }
         // positions never reach max_ctx (generation stops there), so a sequence never needs more than a full context of pages
-        const int total = std::min((n + r->sp.max_tokens + page_ - 1) / page_, max_pages_per_seq_);
+        const int total = std::min((n + 1 + page_ - 1) / page_, max_pages_per_seq_);
         if ((int)(running_.size() + batch.size()) >= cfg_.max_seqs) break;
-        // leading full pages already in the pool (always leave >= 1 prompt token to run: its logits seed the decode)
+        // leading full pages already in the pool (always leave >= 1 token to run: its logits seed the decode)
         std::vector<int32_t> hit;
         uint64_t key = 0;
         int idle_hits = 0;
         if (cfg_.enable_prefix_cache) {
           for (int i = 0; (i + 1) * page_ <= n - 1; ++i) {
-            const uint64_t k2 = page_key(key, r->prompt.data() + (size_t)i * page_, page_);
+            const uint64_t k2 = page_key(key, toks + (size_t)i * page_, page_);
             auto it = cache_.find(k2);
             if (it == cache_.end()) break;
             const PageMeta& m = pmeta_[it->second];
-            if (m.parent != key || !std::equal(m.toks.begin(), m.toks.end(), r->prompt.begin() + (size_t)i * page_)) break;
+            if (m.parent != key || !std::equal(m.toks.begin(), m.toks.end(), toks + (size_t)i * page_)) break;
             hit.push_back(it->second);
             idle_hits += m.ref == 0;
             key = k2;
           }
         }
         const int need = total - (int)hit.size();
-        const int rest = n - (int)hit.size() * page_;  // prompt tokens still to prefill
-        if (pages_available() - idle_hits < need) break;
-        if (rest <= t_cap_ && T + rest > t_cap_) break;
-        if (rest > t_cap_ && T > 0) break;
+        const int rest = n - (int)hit.size() * page_;  // tokens still to prefill
+        // one spare page per running sequence stays free: admitting into the last pages would only force a preemption
+        if (pages_available() - idle_hits < need + (int)running_.size()) break;
+        if (rest <= budget && T + rest > budget) break;
+        if (rest > budget && T > 0) break;
         for (int32_t pg : hit) {
           PageMeta& m = pmeta_[pg];
           if (m.ref++ == 0) lru_.erase(m.tick);
@@ -1418,17 +1475,29 @@ int Engine::step(int* did_work) {
         r->prefilled = r->kv_len = (int)hit.size() * page_;
         r->registered = (int)hit.size();
         r->chain_key = key;
+        r->target = n;
         prefix_hit_tokens_ += (uint64_t)r->prefilled;
         r->state = ReqState::RUNNING;  // owns cache pages from here on: cancellation goes through cancel_flag
       }
-      r->chunk = std::min(n - r->prefilled, t_cap_ - T);
+      r->chunk = std::min(r->target - r->prefilled, budget - T);
+      if (r->chunk <= 0) break;
       batch.push_back(r);
       T += r->chunk;
-      if (r->prefilled + r->chunk < n) break;  // stays at the head of the queue until its last chunk
+      if (r->prefilled + r->chunk < r->target) break;  // stays at the head of the queue until its last chunk
       waiting_.pop_front();
     }
+    ensure_decode_pages();
     if (!batch.empty()) {
       prefill = true;
+      if (cfg_.decode_with_prefill) {
+        for (Request* r : running_) {  // decode rows: a one-token chunk at the end of the cached sequence
+          r->prefilled = r->kv_len;
+          r->chunk = 1;
+          r->target = r->kv_len + 1;
+          batch.push_back(r);
+        }
+        if (!running_.empty()) steps_mixed_++;
+      }
     } else {
       batch = running_;
     }
@@ -1439,8 +1508,9 @@ int Engine::step(int* did_work) {
     std::lock_guard<std::mutex> g(mu_);
     if (rc != HB_OK) {
       for (Request* r : batch) {
-        if (!prefill) running_.erase(std::remove(running_.begin(), running_.end(), r), running_.end());
+        running_.erase(std::remove(running_.begin(), running_.end(), r), running_.end());
         waiting_.erase(std::remove(waiting_.begin(), waiting_.end(), r), waiting_.end());  // a partly prefilled prompt
+        r->in_running = false;
         finish_request(r, ReqState::FAILED);
       }
       cv_out_.notify_all();
@@ -1453,8 +1523,11 @@ int Engine::step(int* did_work) {
         r->prefilled += r->chunk;
         r->kv_len = r->prefilled;
         register_full_pages(r);
-        if (r->prefilled < (int)r->prompt.size()) continue;  // more chunks to go: nothing sampled yet
-        running_.push_back(r);
+        if (r->prefilled < r->target) continue;  // more chunks to go: nothing sampled yet
+        if (!r->in_running) {
+          running_.push_back(r);
+          r->in_running = true;
+        }
       } else {
         r->kv_len += 1;
         register_full_pages(r);
@@ -1465,6 +1538,7 @@ int Engine::step(int* did_work) {
                         r->kv_len + 1 >= cfg_.max_ctx;
       if (done) {
         running_.erase(std::remove(running_.begin(), running_.end(), r), running_.end());
+        r->in_running = false;
         finish_request(r, ReqState::FINISHED);
       }
     }
@@ -1636,6 +1710,8 @@ int Engine::stats(hb_stats* s) {
   s->kv_pages_free = pages_available();
   s->kv_pages_cached = (int)lru_.size();
   s->prefix_hit_tokens = prefix_hit_tokens_;
+  s->preemptions = (int32_t)preemptions_;
+  s->steps_mixed = steps_mixed_;
   s->running = (int)running_.size();
   s->waiting = (int)waiting_.size();
   s->steps_prefill = steps_prefill_;

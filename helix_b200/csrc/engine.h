@@ -44,6 +44,8 @@ struct Request {
   std::vector<int32_t> lp_ids;       // [generated][sp.logprobs]
   std::vector<float> lp_vals;
   int preempted = 0;    // times this sequence was evicted and re-queued (pages reclaimed, KV recomputed on re-admission)
+  int target = 0;       // tokens that must have K/V before the next token is sampled (prompt [+ generated, after a preemption])
+  bool in_running = false;
 };
 
 struct StepLayout {
@@ -78,6 +80,12 @@ class Engine {
   int load_broadcast(const hb_model_desc& d, const void* id, int rank, int world, double* seconds);
   int stats(hb_stats* s);
   int set_profile(bool on);
+  int set_mixed(int on, int tokens) {
+    std::lock_guard<std::mutex> g(mu_);
+    cfg_.decode_with_prefill = on;
+    cfg_.mixed_step_tokens = tokens < 0 ? 0 : tokens;
+    return HB_OK;
+  }
   const char* last_error();
 
   static void estimate(const hb_model_desc& d, const hb_engine_cfg& c, uint64_t* w, uint64_t* kv, uint64_t* ws);
@@ -90,6 +98,8 @@ class Engine {
   void free_all();
   void loop();
   void finish_request(Request* r, ReqState st);
+  void preempt(Request* v);
+  void ensure_decode_pages();
   StepLayout layout(int T, int B, size_t pen_entries = 0) const;
   int forward_llama(int T, int B, bool prefill, int max_seqlen, const StepLayout& L, bool all_logits, bool paged = false,
                     float* pool_out = nullptr);
@@ -143,7 +153,7 @@ class Engine {
   std::vector<PageMeta> pmeta_;
   std::unordered_map<uint64_t, int32_t> cache_;   // content key -> page
   std::map<uint64_t, int32_t> lru_;               // tick -> unreferenced cached page (oldest first)
-  uint64_t tick_ = 0, prefix_hit_tokens_ = 0;
+  uint64_t tick_ = 0, prefix_hit_tokens_ = 0, preemptions_ = 0, steps_mixed_ = 0;
   int32_t take_page();                 // free list first, then evict the oldest unreferenced cached page
   void drop_page(int32_t pg);          // a sequence lets go of a page
   int pages_available() const { return (int)(free_pages_.size() + lru_.size()); }

@@ -37,11 +37,12 @@ class EngineConfig:
     stream_priority: int = 0      # 1: high-priority stream
     decode_with_prefill: int = 0  # 1: running sequences decode inside prefill steps (mixed batches)
     fused_decode: int = 0         # 1: decode GEMMs with tile finishers instead of separate row kernels (measured slower)
+    mixed_step_tokens: int = 0    # token budget of a step that carries decode rows (0 = 2048)
 
     def to_c(self):
         return EngineCfg(self.device, self.memory_budget_bytes, self.max_seqs, self.max_ctx, self.max_batched_tokens,
                          self.kv_page_size, self.use_cuda_graphs, self.enable_prefix_cache, self.sm_budget,
-                         self.sm_partition, self.stream_priority, self.decode_with_prefill, self.fused_decode)
+                         self.sm_partition, self.stream_priority, self.decode_with_prefill, self.fused_decode, self.mixed_step_tokens)
 
 
 @dataclass
@@ -173,6 +174,10 @@ class Engine:
 
     def stop(self):
         self._ck(self._l.hb_engine_stop(self._h))
+
+    def set_mixed(self, on, tokens=0):
+        """decode_with_prefill / mixed_step_tokens of a live engine (next step on)."""
+        self._ck(self._l.hb_engine_set_mixed(self._h, int(bool(on)), int(tokens)))
 
     def step(self):
         did = C.c_int()

@@ -153,7 +153,8 @@ class B200Runtime:
                                                              self.parsed.gpu_memory_utilization),
                            max_seqs=self.parsed.max_num_seqs, max_ctx=max_ctx, use_cuda_graphs=1,
                            max_batched_tokens=self.parsed.max_num_batched_tokens or 16384,
-                           enable_prefix_cache=int(self.parsed.enable_prefix_caching and not embed))
+                           enable_prefix_cache=int(self.parsed.enable_prefix_caching and not embed),
+                           decode_with_prefill=1)  # running streams keep decoding while long prompts are prefilled
         eng = (self.p.engine_factory or Engine)(cfg)
         try:
             if self.p.state_dict is not None:

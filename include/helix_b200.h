@@ -76,7 +76,8 @@ typedef struct hb_engine_cfg {
   int32_t fused_decode;         /* 1: decode GEMMs run with tile finishers (the last CTA of each stream-K tile applies RoPE+KV
                                    write / residual+norm statistics / SwiGLU itself: 5 kernels per layer instead of 9).
                                    Measured slower than the separate row kernels on B200, so off by default */
-  int32_t reserved[1];
+  int32_t mixed_step_tokens;    /* token budget of a step that carries decode rows (decode_with_prefill): a long prompt
+                                   is spread over steps of this size so inter-token latency stays bounded; 0 = 2048 */
 } hb_engine_cfg;
 
 typedef struct hb_model_desc {
@@ -128,9 +129,10 @@ typedef struct hb_stats {
   uint64_t graph_launches;
   int32_t cuda_error;         /* sticky cudaError_t, 0 = healthy */
   int32_t kv_pages_cached;    /* unreferenced pages kept for prefix reuse (counted in kv_pages_free: evictable) */
-  int32_t reserved0;
+  int32_t preemptions;        /* running sequences evicted for pages and re-queued (KV recomputed on re-admission) */
   uint64_t prefix_hit_tokens; /* prompt tokens served from cached pages instead of being prefilled */
-  int32_t reserved[3];
+  uint64_t steps_mixed;       /* prefill steps that also carried decode rows of running sequences */
+  int32_t reserved[1];
   /* device time of the forward passes (CUDA events on the engine stream: after the step's inputs are
      resident, before the sampled ids are copied back) */
   double gpu_ms_prefill, gpu_ms_decode;
@@ -176,6 +178,8 @@ int hb_memory_estimate(const hb_model_desc* desc, const hb_engine_cfg* cfg, uint
 /* ---- generation ---- */
 int hb_engine_start(hb_engine* e); /* spawn the step-loop thread (continuous batching) */
 int hb_engine_stop(hb_engine* e);
+/* change hb_engine_cfg.decode_with_prefill / mixed_step_tokens of a live engine (takes effect at the next step) */
+int hb_engine_set_mixed(hb_engine* e, int32_t decode_with_prefill, int32_t mixed_step_tokens);
 int hb_step(hb_engine* e, int* did_work); /* run ONE scheduler step on the caller's thread (no step-loop thread) */
 int hb_submit(hb_engine* e, const int32_t* tokens, int32_t n_tokens, const hb_sampling* sp, uint64_t* req_id);
 int hb_poll(hb_engine* e, uint64_t req_id, int32_t* out_tokens, int32_t cap, int32_t* n_out, int32_t* finished);
