@@ -32,8 +32,12 @@ st = e.stats()
 print(f"# decode steps {st['steps_decode']}, gpu_ms_decode {st['gpu_ms_decode']:.2f} -> {st['gpu_ms_decode'] / max(1, st['steps_decode']):.3f} ms/step, bank MB {os.environ.get('HB_DECODE_BANK_MB', '32')}")
 rows = [l.split() for l in open("/tmp/dec_trace.txt")]
 print("# layer kernel  entry ring_issued handover after_wait first_operands last_load last_mma epilogue_done   (us, relative to layer start)")
-for l in (0, 1, 15, 31):
-    sel = [r for r in rows if int(r[0]) == l]
+layers = sorted({int(r[0]) for r in rows})
+first = min(int(x) for r in rows for x in r[2:] if int(x) >= 0)
+last = max(int(x) for r in rows for x in r[2:])
+print(f"# whole step, first stamp -> last stamp: {(last - first) / 1000:.1f} us; the head row is the LM-head GEMM (then sum / sample kernels follow untraced)")
+for l in (0, 1, 15, 31, layers[-1]):
+    sel = [r for r in rows if int(r[0]) == l and (l != layers[-1] or r[1] == "head" or l in (0, 1, 15, 31))]
     base = min(int(x) for r in sel for x in r[2:] if int(x) >= 0)
     for r in sel:
         print(f"{r[0]:>3} {r[1]:<5} " + " ".join(f"{(int(x) - base) / 1000:8.2f}" if int(x) >= 0 else "       -" for x in r[2:]))
