@@ -33,6 +33,11 @@ class SamplingC(C.Structure):
                 ("presence_penalty", C.c_float), ("frequency_penalty", C.c_float), ("reserved2", C.c_int32 * 4)]
 
 
+class SlotInfoC(C.Structure):
+    _fields_ = [("model", C.c_char * 256), ("is_embed", C.c_int32), ("tensor_parallel_size", C.c_int32),
+                ("n_unknown_args", C.c_int32), ("gpu_memory_utilization", C.c_float)]
+
+
 class StatsC(C.Structure):
     _fields_ = [("weights_bytes", C.c_uint64), ("kv_bytes", C.c_uint64), ("workspace_bytes", C.c_uint64),
                 ("budget_bytes", C.c_uint64), ("kv_pages_total", C.c_int32), ("kv_pages_free", C.c_int32),
@@ -49,6 +54,7 @@ I = C.c_int
 # name -> (restype, argtypes): every symbol include/helix_b200.h and include/helix_b200_kernels.h declare
 SIGNATURES = {
     "hb_abi_version": (I, []),
+    "hb_slot_config": (I, [C.c_char_p, C.c_uint64, C.POINTER(EngineCfg), C.POINTER(SlotInfoC)]),
     "hb_engine_create": (I, [C.POINTER(EngineCfg), C.POINTER(P)]),
     "hb_engine_destroy": (None, [P]),
     "hb_last_error": (C.c_char_p, [P]),

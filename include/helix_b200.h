@@ -144,6 +144,22 @@ typedef struct hb_stats {
   uint64_t prof_launches[8];
 } hb_stats;
 
+/* ---- slot creation: the scheduler's JSON -> engine configuration.
+ * `json` is a types.CreateRunnerSlotRequest or its `attributes` object (api/pkg/types/runner.go:92-109) with
+ * runtime "vllm" (plug-in option A).  Follows Slot.Create (api/pkg/runner/slot.go:395-470: runtime_args.model
+ * overrides model; runtime_args.args as a string array, a mixed array or a {flag: value} map) and reads the flags the
+ * scheduler emits (api/pkg/scheduler/runner.go:1187-1259,1344-1397): --gpu-memory-utilization, --max-num-seqs (default 256),
+ * --max-model-len, --task embed, --max-num-batched-tokens, --[no-]enable-prefix-caching.  memory_budget_bytes is
+ * model_memory_requirement when present, else utilization x per_gpu_memory_bytes.  max_ctx 0 = the model's default. ---- */
+typedef struct hb_slot_info {
+  char model[256];
+  int32_t is_embed;             /* --task embed */
+  int32_t tensor_parallel_size; /* as sent; this runtime replicates instead of splitting */
+  int32_t n_unknown_args;       /* flags the engine has no use for (ignored, counted) */
+  float gpu_memory_utilization; /* as sent (0 = absent) */
+} hb_slot_info;
+int hb_slot_config(const char* json, uint64_t per_gpu_memory_bytes, hb_engine_cfg* cfg_out, hb_slot_info* info_out);
+
 /* ---- lifecycle ---- */
 int hb_abi_version(void);
 int hb_engine_create(const hb_engine_cfg* cfg, hb_engine** out);

@@ -54,14 +54,18 @@ int main(void) {
     fprintf(stderr, "ABI mismatch: header %d, library %d\n", HB_ABI_VERSION, hb_abi_version());
     return 1;
   }
+  /* the slot-creation message as the scheduler sends it (types.CreateRunnerSlotRequest) -> engine configuration */
+  static const char* create_slot =
+      "{\"id\": \"6f1c0e0e-0000-4000-8000-000000000001\", \"attributes\": {\"runtime\": \"vllm\", \"model\": \"tiny/llama\","
+      " \"context_length\": 256, \"gpu_index\": 0, \"tensor_parallel_size\": 1,"
+      " \"runtime_args\": {\"args\": [\"--max-num-seqs\", \"4\", \"--max-num-batched-tokens\", 256, \"--trust-remote-code\"]}}}";
   hb_engine_cfg cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.device = 0;
-  cfg.max_seqs = 4;
-  cfg.max_ctx = 256;
-  cfg.max_batched_tokens = 256;
-  cfg.kv_page_size = 64;
-  cfg.use_cuda_graphs = 1;
+  hb_slot_info slot;
+  if (hb_slot_config(create_slot, 0, &cfg, &slot) != HB_OK || strcmp(slot.model, "tiny/llama") || cfg.max_seqs != 4 ||
+      cfg.max_ctx != 256 || cfg.max_batched_tokens != 256 || slot.n_unknown_args != 1) {
+    fprintf(stderr, "hb_slot_config: unexpected decode\n");
+    return 1;
+  }
   if (hb_engine_create(&cfg, &eng) != HB_OK) {
     fprintf(stderr, "hb_engine_create: %s\n", hb_last_error(NULL));
     return 1;
