@@ -65,7 +65,7 @@ def test_greedy_ids_and_logprobs_agree_with_vllm(tmp_path, golden_dir):
         assert abs(float(lps[i, 0]) - v["logprobs"][i][str(a)] if isinstance(next(iter(v["logprobs"][i])), str) else
                    float(lps[i, 0]) - v["logprobs"][i][a]) <= 5e-2
     hf = g["greedy_tokens"].tolist()
-    print(f"\\n[vLLM second opinion] engine {outs[0]}\\n                      vLLM   {v['tokens']}\\n                      HF fp32 {hf}; "
+    print(f"\n[vLLM second opinion] engine  {outs[0]}\n                      vLLM    {v['tokens']}\n                      HF fp32 {hf}; "
           f"identical for the first {same}/8 steps; engine logprobs {lps[:same, 0].round(4).tolist()}")
     assert same >= 3
     if same < 8:   # after a disagreement: it must be a near-tie in the engine's own distribution
