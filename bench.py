@@ -504,7 +504,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--sessions", type=int, default=32)
-    ap.add_argument("--seq", type=int, default=640)
+    ap.add_argument("--seq", type=int, default=2048)
     ap.add_argument("--decode", type=int, default=128)
     ap.add_argument("--max-seqs", type=int, default=256, help="--max-num-seqs of the slot (the reference's vLLM default)")
     ap.add_argument("--max-batched-tokens", type=int, default=16384)
