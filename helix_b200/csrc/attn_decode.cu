@@ -59,7 +59,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
                    const int32_t* __restrict__ ctx_lens, float* __restrict__ ws, int Hkv, int num_splits,
                    float scale_log2, bf16* __restrict__ out_direct, int ldo, const int* sig_wait, int sig_wait_count,
                    int* sig_done, int bank_tiles, const bf16* __restrict__ k_cache, const bf16* __restrict__ v_cache,
-                   unsigned long long* trace) {
+                   unsigned long long* trace, const int* dep_wait, int dep_count, int* dep_done) {
   using C = DCfg<D>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -96,9 +96,19 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
   const int t_end = min(n_tiles_total, t_begin + tps);
   float* ws_base = ws + ((size_t)(b * Hkv + kvh) * num_splits + split) * G * (D + 2);
   if (t_begin >= t_end) {
-    pdl_wait();  // ws may still be read by an earlier launch's combine pass
+    if (dep_wait) {
+      if (threadIdx.x == 0) dep_wait_thread(dep_wait, dep_count);
+      __syncthreads();
+    } else {
+      pdl_wait();  // ws may still be read by an earlier launch's combine pass
+    }
     for (int i = threadIdx.x; i < G * (D + 2); i += kThreads) ws_base[i] = (i % (D + 2) == D) ? -INFINITY : 0.f;
-    if (threadIdx.x == 0) sig_add(sig_done);  // every CTA reports, also one without work
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {  // every CTA reports, also one without work
+      sig_add(sig_done);
+      dep_signal(dep_done);
+    }
     return;
   }
   const int n_tiles = t_end - t_begin;
@@ -138,7 +148,15 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
     {
       for (int j = 0; j < n_tiles; ++j) {
         const int pg0 = (t_begin + j) * 2;
-        if (t_begin + j == n_tiles_total - 1) pdl_wait();  // the tile with the step's new position
+        if (t_begin + j == n_tiles_total - 1) {  // the tile with the step's new position
+          if (dep_wait) {
+            if (elected) dep_wait_thread(dep_wait, dep_count);
+            __syncwarp();
+            if (elected) fence_proxy_async_all();
+          } else {
+            pdl_wait();
+          }
+        }
         // a tile's second page may not exist yet: re-load the first one (finite data, masked by the softmax)
         const int page_a = pt[pg0], page_b = pt[min(pg0 + 1, n_pages - 1)];
 #pragma unroll
@@ -232,7 +250,12 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
     }
     // ---- stage Q^T (G rows of D, rows G..15 zero) into the K-major swizzled B-operand layout; zero P
     if (t == 0) trace_ev(trace, 2);
-    pdl_wait();  // q is written by the predecessor; so is nothing else this role reads
+    if (dep_wait) {  // q is written by the predecessor; so is nothing else this role reads
+      if (t == 0) dep_wait_thread(dep_wait, dep_count);
+      bar_sync(1, 128);
+    } else {
+      pdl_wait();
+    }
     if (t == 0) trace_ev(trace, 3);
     {
       const bf16* qsrc = q + (size_t)b * ldq + (size_t)kvh * G * D;
@@ -359,6 +382,11 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
       }
     }
   }
+  if (dep_done && warp >= 2) {  // the 128 softmax threads have stored this CTA's output rows: report to the next kernel
+    __threadfence();
+    bar_sync(1, 128);
+    if (threadIdx.x == 64) dep_signal(dep_done);
+  }
   if (threadIdx.x == 64) trace_ev(trace, 7);
   tc_fence_before();
   __syncthreads();
@@ -413,7 +441,7 @@ cudaError_t launch(cudaStream_t stream, const AttnDecodeArgs& a) {
   cudaError_t e = launch_k(attn_decode_kernel<D, G>, grid, dim3(kThreads), DCfg<D>::SMEM, stream, true, mk, mv, a.q, a.ldq,
                            a.page_table, a.max_pages, a.ctx_lens, a.workspace, a.Hkv, a.num_splits,
                            a.scale * 1.4426950408889634f, direct, a.ldo, a.sig.wait, a.sig.wait_count, a.sig.done, bank_tiles,
-                           a.k_cache, a.v_cache, a.sig.trace);
+                           a.k_cache, a.v_cache, a.sig.trace, a.sig.dep.wait, a.sig.dep.wait_count, a.sig.dep.done);
   if (e != cudaSuccess || direct) return e;
   return launch_k(attn_decode_combine_kernel<D>, dim3(a.Hq, a.B), dim3(D / 2), 0, stream, true,
                   (const float*)a.workspace, a.out, a.ldo, a.Hq, a.Hkv, G, a.num_splits);

@@ -5,6 +5,7 @@
 
 #include "kernels.h"
 #include "launch.h"
+#include "ptx.cuh"
 
 namespace hb {
 namespace {
@@ -15,6 +16,22 @@ __device__ __forceinline__ float slab_sum(const float* __restrict__ ws, const ui
   float acc = 0.f;
   for (int s = 0; s < ns; ++s) acc += ws[((size_t)s * M + m) * N + n];
   return acc;
+}
+// block-wide entry / exit of a kernel in the decode chain (ptx.cuh dep_*)
+__device__ __forceinline__ void block_dep_wait(const int* wait, int count) {
+  if (wait) {
+    if (threadIdx.x == 0) dep_wait_thread(wait, count);
+    __syncthreads();
+  } else {
+    pdl_wait();
+  }
+}
+__device__ __forceinline__ void block_dep_done(int* done) {
+  if (done) {
+    __threadfence();   // this thread's stores are visible device-wide ...
+    __syncthreads();   // ... for every thread of the block before the block reports
+    if (threadIdx.x == 0) dep_signal(done);
+  }
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 __device__ __forceinline__ float warp_sum(float v) {
@@ -38,12 +55,11 @@ __global__ void __launch_bounds__(64)
 qkv_rope_kvwrite_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf16* __restrict__ qkv_out,
                         const int32_t* __restrict__ positions, const int32_t* __restrict__ slot_mapping,
                         const float* __restrict__ inv_freq, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
-                        int M, int Hq, int Hkv, int D, int page_size) {
+                        int M, int Hq, int Hkv, int D, int page_size, const int* dep_wait, int dep_count, int* dep_done) {
   pdl_launch_dependents();
-  pdl_wait();
+  block_dep_wait(dep_wait, dep_count);
   const int h = blockIdx.x, m = blockIdx.y, j = threadIdx.x;
-  const int half = D / 2;
-  if (j >= half) return;
+  const int half = D / 2;  // == blockDim.x
   const int N = (Hq + 2 * Hkv) * D;
   // GEMM output is rounded to bf16 first (same as the prefill epilogue); RoPE is evaluated in fp32 on top
   const float a = bf16_round(slab_sum(ws, segs, M, N, m, h * D + j));
@@ -68,6 +84,7 @@ qkv_rope_kvwrite_kernel(const float* __restrict__ ws, const uint8_t* __restrict_
     v_cache[dst + j] = __float2bfloat16(a);
     v_cache[dst + half + j] = __float2bfloat16(b);
   }
+  block_dep_done(dep_done);
 }
 
 constexpr int kRT = 512;
@@ -94,10 +111,11 @@ __device__ __forceinline__ float4 slab_sum4(const float* __restrict__ ws, const 
 // one block per row: x = bf16(x + sum of slabs); xn = x * rsqrt(mean(x^2)+eps) * w
 __global__ void __launch_bounds__(kRT)
 resid_rmsnorm_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf16* __restrict__ x,
-                     const bf16* __restrict__ w, bf16* __restrict__ xn, int M, int H, float eps) {
+                     const bf16* __restrict__ w, bf16* __restrict__ xn, int M, int H, float eps, const int* dep_wait,
+                     int dep_count, int* dep_done) {
   __shared__ float red[kRT / 32];
   pdl_launch_dependents();
-  pdl_wait();
+  block_dep_wait(dep_wait, dep_count);
   const int m = blockIdx.x;
   bf16* xr = x + (size_t)m * H;
   float4 cache[kRMaxVec];
@@ -121,7 +139,10 @@ resid_rmsnorm_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ s
       ss += r01.x * r01.x + r01.y * r01.y + r23.x * r23.x + r23.y * r23.y;
     }
   }
-  if (!w) return;
+  if (!w) {
+    block_dep_done(dep_done);
+    return;
+  }
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
@@ -143,15 +164,17 @@ resid_rmsnorm_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ s
       *reinterpret_cast<uint2*>(xn + (size_t)m * H + n) = ob;
     }
   }
+  block_dep_done(dep_done);
 }
 
 __global__ void __launch_bounds__(256)
-swiglu_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf16* __restrict__ h, int M, int F) {
+swiglu_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf16* __restrict__ h, int M, int F,
+              const int* dep_wait, int dep_count, int* dep_done) {
   pdl_launch_dependents();
-  pdl_wait();
+  block_dep_wait(dep_wait, dep_count);
   const int m = blockIdx.y;
   const int j = (blockIdx.x * 256 + threadIdx.x) * 4;  // 4 consecutive outputs: never straddles a 128-column tile
-  if (j >= F) return;
+  if (j < F) {
   const int t = j >> 7, r = j & 127;
   const float4 g = slab_sum4(ws, segs, M, 2 * F, m, t * 256 + r);
   const float4 u = slab_sum4(ws, segs, M, 2 * F, m, t * 256 + 128 + r);
@@ -161,6 +184,8 @@ swiglu_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf
   ob.x = *reinterpret_cast<uint32_t*>(&o01);
   ob.y = *reinterpret_cast<uint32_t*>(&o23);
   *reinterpret_cast<uint2*>(h + (size_t)m * F + j) = ob;
+  }
+  block_dep_done(dep_done);
 }
 
 // one block (128 threads) per row: x = table[token]; xg = bf16(x * gain); ss_out[tile][m] = sum of x^2 over the tile
@@ -201,18 +226,30 @@ cudaError_t dec_sum_slabs(cudaStream_t s, const float* ws, const SkinnyPlan& p, 
 }
 cudaError_t dec_qkv_rope_kvwrite(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* qkv_out,
                                  const int32_t* positions, const int32_t* slot_mapping, const float* inv_freq,
-                                 bf16* k_cache, bf16* v_cache, int M, int Hq, int Hkv, int D, int page_size) {
+                                 bf16* k_cache, bf16* v_cache, int M, int Hq, int Hkv, int D, int page_size,
+                                 const DepSig* dep) {
+  const DepSig none{};
+  if (!dep) dep = &none;
   return launch_k(qkv_rope_kvwrite_kernel, dim3(Hq + 2 * Hkv, M), dim3(D / 2), 0, s, true, ws, p.seg_count, qkv_out,
-                  positions, slot_mapping, inv_freq, k_cache, v_cache, M, Hq, Hkv, D, page_size);
+                  positions, slot_mapping, inv_freq, k_cache, v_cache, M, Hq, Hkv, D, page_size, dep->wait, dep->wait_count,
+                  dep->done);
 }
+int dec_qkv_rope_ctas(int M, int Hq, int Hkv) { return (Hq + 2 * Hkv) * M; }
+int dec_swiglu_ctas(int M, int F) { return ((F / 4 + 255) / 256) * M; }
 cudaError_t dec_resid_rmsnorm(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* x, const bf16* w, bf16* xn,
-                              int M, int H, float eps) {
+                              int M, int H, float eps, const DepSig* dep) {
   if (H > kRT * kRMaxVec * 4 || (H % 4)) return cudaErrorInvalidValue;
-  return launch_k(resid_rmsnorm_kernel, dim3(M), dim3(kRT), 0, s, true, ws, p.seg_count, x, w, xn, M, H, eps);
+  const DepSig none{};
+  if (!dep) dep = &none;
+  return launch_k(resid_rmsnorm_kernel, dim3(M), dim3(kRT), 0, s, true, ws, p.seg_count, x, w, xn, M, H, eps, dep->wait,
+                  dep->wait_count, dep->done);
 }
-cudaError_t dec_swiglu(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* h, int M, int F) {
+cudaError_t dec_swiglu(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* h, int M, int F, const DepSig* dep) {
   if (F % 4) return cudaErrorInvalidValue;
-  return launch_k(swiglu_kernel, dim3((F / 4 + 255) / 256, M), dim3(256), 0, s, true, ws, p.seg_count, h, M, F);
+  const DepSig none{};
+  if (!dep) dep = &none;
+  return launch_k(swiglu_kernel, dim3((F / 4 + 255) / 256, M), dim3(256), 0, s, true, ws, p.seg_count, h, M, F, dep->wait,
+                  dep->wait_count, dep->done);
 }
 
 }  // namespace hb

@@ -188,7 +188,7 @@ size_t Engine::workspace_bytes() const {
     b += al256((size_t)cfg_.max_seqs * 4);                    // sampled
     b += al256(sample_scratch_bytes(cfg_.max_seqs, d.vocab)); // argmax partials
     b += 2 * al256((size_t)cfg_.max_seqs * HB_MAX_LOGPROBS * 4);  // log-probability records of one step
-    b += al256((size_t)(5 * d.layers + 1) * sizeof(int));         // HBM hand-over counters of the decode step
+    b += al256((size_t)(5 * d.layers + 1 + 9 * d.layers + 2) * sizeof(int));  // hand-over counters + dependency flags of the decode step
     b += al256(fused_counter_ints(d) * sizeof(int));              // tile arrival counters of the fused decode GEMMs
     b += al256((size_t)((d.hidden + 127) / 128) * kSkinnySsStride * sizeof(float));  // RMSNorm per-tile partials
     b += al256(skinny_ws_bytes(148));                         // decode GEMM partial slabs
@@ -325,7 +325,8 @@ int Engine::alloc_runtime() {
     dec_ws_ = (float*)take(attn_decode_workspace_floats(cfg_.max_seqs, d.heads, d.head_dim, 16) * 4);
     sampled_ = (int32_t*)take((size_t)cfg_.max_seqs * 4);
     sample_ws_ = take(sample_scratch_bytes(cfg_.max_seqs, d.vocab));
-    sig_ = (int*)take((size_t)(5 * d.layers + 1) * sizeof(int));
+    sig_ = (int*)take((size_t)(5 * d.layers + 1 + 9 * d.layers + 2) * sizeof(int));
+    dep_ = sig_ + (5 * d.layers + 1);  // dependency flags of the decode chain follow the hand-over counters (one memset)
     {
       int* cnt = (int*)take(fused_counter_ints(d) * sizeof(int));
       CU(cudaMemset(cnt, 0, fused_counter_ints(d) * sizeof(int)));
@@ -705,10 +706,29 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
     return (size_t)(e ? atoi(e) : 0) << 20;  // measured: no gain on the headline workload, off by default
   }();
   const bool handover = sig_ != nullptr && !profile_ && (bank_bytes > 0 || dec_trace_);
-  if (handover) CU(cudaMemsetAsync(sig_, 0, (size_t)(5 * d.layers + 1) * sizeof(int), stream_));
+  // Dependency flags (kernels.h DepSig): inside a layer chain every kernel waits for its predecessor's release/acquire
+  // counter instead of griddepcontrol.wait; the step's first kernels and the sampler keep the PDL wait.
+  static const int flags_env = [] { const char* e = getenv("HB_DECODE_FLAGS"); return e ? atoi(e) : -1; }();
+  const int splits = decode_splits(B);
+  const bool flags = dep_ != nullptr && flags_env > 0 && splits == 1;  // measured slower than griddepcontrol.wait: opt-in
+  const size_t n_sig = (size_t)(5 * d.layers + 1), n_dep = (size_t)(9 * d.layers + 2);
+  if (handover || flags) CU(cudaMemsetAsync(sig_, 0, (n_sig + n_dep) * sizeof(int), stream_));  // dep_ follows sig_
   int prev_idx = -1, prev_count = 0;
+  int dep_next = 0, dep_prev_count = 0;
+  const int* dep_prev = nullptr;
+  auto next_dep = [&](int my_ctas) {  // this kernel waits for the previous kernel of the chain and owns the next counter
+    DepSig dp{};
+    if (!flags) return dp;
+    dp.wait = dep_prev;
+    dp.wait_count = dep_prev_count;
+    dp.done = dep_ + dep_next++;
+    dep_prev = dp.done;
+    dep_prev_count = my_ctas;
+    return dp;
+  };
   auto next_sig = [&](int idx, int my_ctas) {
     StreamSig sg{};
+    sg.dep = next_dep(my_ctas);
     if (!handover) return sg;
     if (prev_idx >= 0) { sg.wait = sig_ + prev_idx; sg.wait_count = prev_count; }
     sg.done = sig_ + idx;
@@ -718,7 +738,6 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
     prev_count = my_ctas;
     return sg;
   };
-  const int splits = decode_splits(B);
 
   SPAN(3, rowb, embed_gather(stream_, tokens, model_.embed, x_, B, H));
   SPAN(3, rowb, rmsnorm(stream_, x_, model_.ll[0].attn_norm, xn_, nullptr, B, H, d.norm_eps));
@@ -727,11 +746,14 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
     bf16* kc = kv_ + (size_t)l * 2 * layer_kv;
     bf16* vc = kc + layer_kv;
     {
-      const StreamSig sg = next_sig(5 * l + 0, plan_qkv_.grid);
+      const StreamSig sg = next_sig(5 * l + 0, plan_qkv_.grid);  // layer 0: no predecessor counter -> griddepcontrol.wait
       SPAN(4, wbytes(QKV, H), gemm_skinny(stream_, plan_qkv_, xn_, H, w.wqkv, H, skinny_ws_, B, QKV, H, &sg));
     }
-    SPAN(3, 8.0 * B * QKV, dec_qkv_rope_kvwrite(stream_, skinny_ws_, plan_qkv_, qkv_, positions, slots, model_.inv_freq,
-                                                 kc, vc, B, d.heads, d.kv_heads, D, page_));
+    {
+      const DepSig dp = next_dep(dec_qkv_rope_ctas(B, d.heads, d.kv_heads));
+      SPAN(3, 8.0 * B * QKV, dec_qkv_rope_kvwrite(stream_, skinny_ws_, plan_qkv_, qkv_, positions, slots, model_.inv_freq,
+                                                   kc, vc, B, d.heads, d.kv_heads, D, page_, &dp));
+    }
     {
       AttnDecodeArgs a{};
       a.q = qkv_; a.ldq = QKV;
@@ -752,24 +774,33 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
       const StreamSig sg = next_sig(5 * l + 2, plan_o_.grid);
       SPAN(4, wbytes(H, QD), gemm_skinny(stream_, plan_o_, attn_, QD, w.wo, QD, skinny_ws_, B, H, QD, &sg));
     }
-    SPAN(3, 3 * rowb, dec_resid_rmsnorm(stream_, skinny_ws_, plan_o_, x_, w.mlp_norm, xn_, B, H, d.norm_eps));
+    {
+      const DepSig dp = next_dep(B);
+      SPAN(3, 3 * rowb, dec_resid_rmsnorm(stream_, skinny_ws_, plan_o_, x_, w.mlp_norm, xn_, B, H, d.norm_eps, &dp));
+    }
     {
       const StreamSig sg = next_sig(5 * l + 3, plan_gu_.grid);
       SPAN(4, wbytes(2.0 * F, H), gemm_skinny(stream_, plan_gu_, xn_, H, w.wgu, H, skinny_ws_, B, 2 * F, H, &sg));
     }
-    SPAN(3, 10.0 * B * F, dec_swiglu(stream_, skinny_ws_, plan_gu_, h_, B, F));
+    {
+      const DepSig dp = next_dep(dec_swiglu_ctas(B, F));
+      SPAN(3, 10.0 * B * F, dec_swiglu(stream_, skinny_ws_, plan_gu_, h_, B, F, &dp));
+    }
     {
       const StreamSig sg = next_sig(5 * l + 4, plan_down_.grid);
       SPAN(4, wbytes(H, F), gemm_skinny(stream_, plan_down_, h_, F, w.wdown, F, skinny_ws_, B, H, F, &sg));
     }
     const bf16* next_norm = (l + 1 < d.layers) ? model_.ll[l + 1].attn_norm : model_.final_norm;
-    SPAN(3, 3 * rowb, dec_resid_rmsnorm(stream_, skinny_ws_, plan_down_, x_, next_norm, xn_, B, H, d.norm_eps));
+    {
+      const DepSig dp = next_dep(B);
+      SPAN(3, 3 * rowb, dec_resid_rmsnorm(stream_, skinny_ws_, plan_down_, x_, next_norm, xn_, B, H, d.norm_eps, &dp));
+    }
   }
   {
     const StreamSig sg = next_sig(5 * d.layers, plan_head_.grid);
     SPAN(4, wbytes(d.vocab, H), gemm_skinny(stream_, plan_head_, xn_, H, model_.lm_head, H, skinny_ws_, B, d.vocab, H, &sg));
   }
-  SPAN(3, 8.0 * B * d.vocab, dec_sum_slabs(stream_, skinny_ws_, plan_head_, logits_, d.vocab, B, d.vocab));
+  SPAN(3, 8.0 * B * d.vocab, dec_sum_slabs(stream_, skinny_ws_, plan_head_, logits_, d.vocab, B, d.vocab));  // PDL wait: head GEMM complete
   return sample_step(B, L);
 }
 

@@ -176,6 +176,7 @@ class Engine {
   unsigned long long* dec_trace_ = nullptr;  // HB_DEC_TRACE timeline buffer (debug)
   int *cnt_qkv_ = nullptr, *cnt_o_ = nullptr, *cnt_gu_ = nullptr, *cnt_down_ = nullptr, *cnt_head_ = nullptr;  // tile arrival counters
   float* ss_ = nullptr;         // [hidden/128][256] per-tile sums of x^2 (RMSNorm statistics carried between finishers)
+  int* dep_ = nullptr;          // [9 * layers + 2] release/acquire dependency flags of the decode chain (kernels.h DepSig)
   int* sig_ = nullptr;          // [5 * layers + 1] HBM hand-over counters of the decode step (kernels.h StreamSig)
   int32_t* lp_ids_ = nullptr;   // [b_cap][HB_MAX_LOGPROBS]
   float* lp_vals_ = nullptr;

@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(kThreads, (MPAD <= 64 ? 2 : 1))
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                    float* __restrict__ ws, int M, int N, int K, const int* sig_wait, int sig_wait_count, int* sig_done,
                    int bank_units, const bf16* __restrict__ Wp, int ldw, unsigned long long* trace,
-                   const __grid_constant__ SkinnyEpi epi, const uint8_t* __restrict__ segs) {
+                   const __grid_constant__ SkinnyEpi epi, const uint8_t* __restrict__ segs, const int* dep_wait, int dep_count,
+                   int* dep_done) {
   using C = SCfg<MPAD>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -250,7 +251,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       }
       if (pre_end >= u1 && elected) sig_add(sig_done);  // the whole range fitted into the ring
       if (elected) trace_ev(trace, 1);
-      pdl_wait();
+      if (dep_wait) {  // the activations are ready when every CTA of the previous kernel has reported (ptx.cuh dep_*)
+        if (elected) dep_wait_thread(dep_wait, dep_count);
+        __syncwarp();
+        if (elected) fence_proxy_async_all();  // their generic-proxy stores, read below through TMA
+      } else {
+        pdl_wait();
+      }
       if (elected) trace_ev(trace, 3);
       for (long long u = u0; u < pre_end; ++u) {
         const int s = (int)(u - u0);
@@ -328,7 +335,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         if (wrow < N) prefetch_l2_line(Wp + wrow * ldw + (ub % KB) * BLOCK_K);
       }
     }
-    pdl_wait();  // ws is an activation buffer: never written before the predecessors are done
+    if (dep_wait) {  // ws is an activation buffer: never written before the previous kernel has finished reading it
+      if (lane == 0) dep_wait_thread(dep_wait, dep_count);
+      __syncwarp();
+    } else {
+      pdl_wait();
+    }
     if (epi.mode != SK_SLABS && epi.ss_in) {
       // RMSNorm row factors of the GEMM's input rows, from the previous finisher's per-tile partials, summed in tile
       // order (deterministic).  Computed once per CTA while the first accumulator is still being produced; 8 partials
@@ -396,6 +408,11 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
       u = seg_end;
       ++it;
     }
+    if (dep_done) {  // every slab (and finisher output) of this CTA is stored: report to the next kernel
+      __threadfence();
+      bar_sync(2, 128);
+      if (threadIdx.x == 64) dep_signal(dep_done);
+    }
     if (warp == 2 && lane == 0) trace_ev(trace, 7);
   }
   tc_fence_before();
@@ -434,7 +451,8 @@ cudaError_t launch(cudaStream_t stream, const SkinnyPlan& plan, const bf16* X, i
   if (!make_tmap_2d(&mw, W, TM_BF16, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, BLOCK_K, BLOCK_N)) return cudaErrorInvalidValue;
   if (!make_tmap_2d(&mx, X, TM_BF16, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, BLOCK_K, MPAD)) return cudaErrorInvalidValue;
   return launch_k(gemm_skinny_kernel<MPAD>, dim3(plan.grid), dim3(kThreads), C::SMEM, stream, true, mw, mx, ws, M, N, K,
-                  sig->wait, sig->wait_count, sig->done, bank_units, W, ldw, sig->trace, *epi, plan.seg_count);
+                  sig->wait, sig->wait_count, sig->done, bank_units, W, ldw, sig->trace, *epi, plan.seg_count, sig->dep.wait,
+                  sig->dep.wait_count, sig->dep.done);
 }
 
 template <int MPAD>

@@ -109,12 +109,21 @@ cudaError_t attn_naive_check(cudaStream_t stream, const AttnPrefillArgs& a, floa
 // the PREVIOUS streaming kernel bumps once per CTA when its last load is issued (`wait_count` = its CTA count), `done`
 // is this kernel's own counter, `bank_bytes` how much of its own stream the kernel may prefetch into L2 once the
 // predecessor's loads have ended.  All-zero = feature off.
+// Data dependency of a decode-step kernel on its predecessor as a release/acquire counter (ptx.cuh dep_*): `wait` is the
+// predecessor's counter, `wait_count` how many of its CTAs report, `done` this kernel's own counter.  wait == nullptr:
+// the kernel uses griddepcontrol.wait (every standalone / prefill use).
+struct DepSig {
+  const int* wait = nullptr;
+  int wait_count = 0;
+  int* done = nullptr;
+};
 struct StreamSig {
   const int* wait = nullptr;
   int wait_count = 0;
   int* done = nullptr;
   size_t bank_bytes = 0;
   unsigned long long* trace = nullptr;  // 16 event slots of this launch (HB_DEC_TRACE), written by CTA 0
+  DepSig dep;                           // data dependency on the previous kernel of the step (optional)
 };
 
 // ---- K6: paged-KV decode attention (one query token per sequence), split-KV + combine ----
@@ -181,13 +190,17 @@ cudaError_t gemm_skinny(cudaStream_t stream, const SkinnyPlan& plan, const bf16*
                         float* ws, int M, int N, int K, const StreamSig* sig = nullptr, const SkinnyEpi* epi = nullptr);
 // consumers of the slabs (each sums the slabs in fixed order, then applies its fused epilogue)
 cudaError_t dec_sum_slabs(cudaStream_t s, const float* ws, const SkinnyPlan& p, float* out, int ldo, int M, int N);
+// the dec_* kernels below take an optional DepSig; *ctas (when given) receives the number of CTAs that will report
 cudaError_t dec_qkv_rope_kvwrite(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* qkv_out,
                                  const int32_t* positions, const int32_t* slot_mapping, const float* inv_freq,
-                                 bf16* k_cache, bf16* v_cache, int M, int Hq, int Hkv, int D, int page_size);
+                                 bf16* k_cache, bf16* v_cache, int M, int Hq, int Hkv, int D, int page_size,
+                                 const DepSig* dep = nullptr);
+int dec_qkv_rope_ctas(int M, int Hq, int Hkv);
+int dec_swiglu_ctas(int M, int F);
 // x = bf16(x + sum); xn = rmsnorm(x) * w (w may be null: residual update only)
 cudaError_t dec_resid_rmsnorm(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* x, const bf16* w, bf16* xn,
-                              int M, int H, float eps);
+                              int M, int H, float eps, const DepSig* dep = nullptr);
 // h[m, t*128+j] = silu(sum[m, t*256+j]) * sum[m, t*256+128+j]
-cudaError_t dec_swiglu(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* h, int M, int F);
+cudaError_t dec_swiglu(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* h, int M, int F, const DepSig* dep = nullptr);
 
 }  // namespace hb

@@ -125,6 +125,29 @@ __device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0,
 // One 128-byte line into L2 through the load/store path: unlike UTMAPF it does not queue in front of the CTA's TMA loads
 // (the TMA unit works in order: a burst of tensor prefetches delayed the operand loads issued after it by microseconds)
 __device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// ---- Dependency flags of the decode step (kernels.h DepSig): the data dependency between two consecutive kernels of the
+// step is a counter in global memory instead of griddepcontrol.wait.  Producer CTA: all its global stores, then
+// __threadfence() + a barrier over the storing threads, then ONE red.release; consumer: ONE thread polls with ld.acquire
+// until every producer CTA has reported, then a barrier releases the other threads (and a proxy fence precedes TMA reads of
+// the data).  The successor is already resident (PDL launch), so the hand-over costs two L2 round trips instead of grid
+// completion + flush + release (measured 2-4 us per boundary, profiles/r02_decode_timeline.txt).  Every CTA waits before it
+// signals, so "kernel K done" implies "kernel K-1 done" transitively, exactly like stream order.
+__device__ __forceinline__ void dep_signal(int* p) {
+  if (p) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ bool dep_poll(const int* p, int n) {  // one thread; true when all n producers have reported
+  int v;
+  for (long long spin = 0; spin < (1ll << 24); ++spin) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v >= n) return true;
+    __nanosleep(64);
+  }
+  return false;  // > 1 s: a producer never reported
+}
+__device__ __forceinline__ void dep_wait_thread(const int* p, int n) {
+  if (!dep_poll(p, n)) asm volatile("trap;");  // fail loudly (sticky launch failure) instead of hanging the GPU
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // Optional timeline of the decode step (HB_DEC_TRACE=1): event `ev` of this kernel -> trace[ev] = %globaltimer (ns)
 __device__ __forceinline__ void trace_ev(unsigned long long* trace, int ev) {
   if (trace) {
