@@ -79,6 +79,13 @@ SIGNATURES = {
     "hb_replica_unique_id": (I, [P]),
     "hb_model_load_broadcast": (I, [P, C.POINTER(ModelDescC), P, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "hb_embed": (I, [P, P, P, C.c_int32, P]),
+    "hb_tok_load": (I, [C.c_char_p, C.POINTER(P)]),
+    "hb_tok_free": (None, [P]),
+    "hb_tok_vocab_size": (C.c_int32, [P]),
+    "hb_tok_token_id": (C.c_int32, [P, C.c_char_p]),
+    "hb_tok_encode": (I, [P, C.c_char_p, C.c_int32, P, C.c_int32, C.POINTER(C.c_int32)]),
+    "hb_tok_decode": (I, [P, P, C.c_int32, C.c_int32, P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "hb_tok_chat_llama3": (I, [P, P, P, C.c_int32, P, C.c_int32, C.POINTER(C.c_int32)]),
     "hb_get_stats": (I, [P, C.POINTER(StatsC)]),
     "hb_set_profile": (I, [P, C.c_int32]),
     # kernel-level ABI

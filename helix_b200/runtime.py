@@ -120,7 +120,7 @@ class B200RuntimeParams:
     state_dict: Optional[dict] = None        # HF-named tensors; None -> random init
     seed: int = 0
     serve_http: bool = True
-    tokenizer: Optional[object] = None
+    tokenizer: Optional[object] = None        # a tokenizer object, or the path of a HF tokenizer.json (loaded natively: hb_tok_*)
     engine_factory: Optional[Callable] = None  # EngineConfig -> engine; default: the CUDA engine (tests inject a stand-in)
 
 
@@ -167,7 +167,11 @@ class B200Runtime:
             self.is_embed = embed or desc.arch == configs.BERT
             if self.p.serve_http:
                 from .server import OpenAIServer
-                self.server = OpenAIServer(self, self.p.tokenizer)
+                tok = self.p.tokenizer
+                if isinstance(tok, (str, bytes)) or hasattr(tok, "__fspath__"):  # path of a HF tokenizer.json: native tokenizer
+                    from .tokenizer import NativeTokenizer
+                    tok = NativeTokenizer(tok)
+                self.server = OpenAIServer(self, tok)
                 self._url = self.server.start()
             self._status = "running"
         except Exception:

@@ -352,7 +352,8 @@ def test_runtime_lifecycle_and_openai_http_front():
     from helix_b200.runtime import B200Runtime, B200RuntimeParams
 
     d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000)
-    rt = B200Runtime(B200RuntimeParams(model="tiny", desc=d, state_dict=weights.llama_state_dict(d, 0, 0.02),
+    sd_rt = weights.llama_state_dict(d, 0, 0.02)
+    rt = B200Runtime(B200RuntimeParams(model="tiny", desc=d, state_dict=sd_rt,
                                        args=["--max-num-seqs", "4", "--max-model-len", "256"]))
     assert rt.status() == ""
     rt.start()
@@ -371,6 +372,22 @@ def test_runtime_lifecycle_and_openai_http_front():
         assert r["object"] == "chat.completion" and r["choices"][0]["finish_reason"] in ("stop", "length")
         assert r["usage"]["completion_tokens"] == 6 and r["usage"]["prompt_tokens"] > 0
         assert r["usage"]["total_tokens"] == r["usage"]["prompt_tokens"] + 6
+        # what came over HTTP is the ORACLE's greedy continuation of the templated prompt, with the oracle's log-probabilities
+        from helix_b200.server import ByteTokenizer
+        from oracle import sampling_ref
+        tk = ByteTokenizer()
+        ids_in = tk.chat([{"role": "user", "content": "hello"}])
+        o = LlamaOracle(d, sd_rt)
+        want, rows = o.greedy(np.array(ids_in, np.int32), 6)
+        assert r["choices"][0]["message"]["content"] == tk.decode([t for t in want if t != tk.EOS])
+        rl = json.load(post("/v1/chat/completions", {"model": "tiny", "messages": [{"role": "user", "content": "hello"}],
+                                                      "max_tokens": 6, "logprobs": True, "top_logprobs": 3, "n": 2, "seed": 3}))
+        assert [c["message"]["content"] for c in rl["choices"]] == [r["choices"][0]["message"]["content"]] * 2  # greedy: both choices equal
+        lp = rl["choices"][1]["logprobs"]["content"]
+        for i, t in enumerate(want):
+            _, ref_lp = sampling_ref.logprob_record(rows[i], t, 1)
+            assert abs(lp[i]["logprob"] - ref_lp[0]) < 5e-2 and len(lp[i]["top_logprobs"]) == 3
+            assert lp[i]["top_logprobs"][0]["logprob"] >= lp[i]["top_logprobs"][1]["logprob"] >= lp[i]["top_logprobs"][2]["logprob"]
         # `stop`: the byte tokenizer's output is arbitrary text; take a piece of it as the stop string of a rerun
         full = r["choices"][0]["message"]["content"]
         if len(full) >= 3:
@@ -393,7 +410,8 @@ def test_runtime_lifecycle_and_openai_http_front():
     assert rt.status() == ""
     # encoder runtime (--task embed)
     b = configs.tiny_bert(layers=2, vocab=1000)
-    rt = B200Runtime(B200RuntimeParams(model="tiny-embed", desc=b, state_dict=weights.bert_state_dict(b, 5, 0.05),
+    sd_b = weights.bert_state_dict(b, 5, 0.05)
+    rt = B200Runtime(B200RuntimeParams(model="tiny-embed", desc=b, state_dict=sd_b,
                                        args=["--task", "embed", "--max-model-len", "512"]))
     rt.start()
     try:
@@ -404,6 +422,16 @@ def test_runtime_lifecycle_and_openai_http_front():
         assert len(out["data"]) == 2 and len(out["data"][0]["embedding"]) == b.hidden
         v = np.array(out["data"][1]["embedding"])
         assert abs(np.linalg.norm(v) - 1.0) < 1e-3
+        # the vectors that came over HTTP are the oracle's embeddings of the tokenised inputs (all three input forms)
+        from helix_b200.server import ByteTokenizer
+        tk = ByteTokenizer()
+        ref = bert_embed(b, sd_b, [np.array(tk.encode(t), np.int32) for t in ("abc", "defgh")])
+        got = np.array([x["embedding"] for x in out["data"]], np.float32)
+        assert np.abs(got - ref).max() <= 1e-2 and float((got * ref).sum(-1).min()) >= 0.9999
+        req = urllib.request.Request(rt.url() + "/v1/embeddings", json.dumps({"input": [tk.encode("defgh")], "model": "tiny-embed"}).encode(),
+                                     {"Content-Type": "application/json"})
+        ids_form = json.load(urllib.request.urlopen(req, timeout=60))
+        assert np.allclose(np.array(ids_form["data"][0]["embedding"], np.float32), got[1], atol=1e-6)
     finally:
         rt.stop()
 
