@@ -24,7 +24,7 @@ class ModelDescC(C.Structure):
                 ("max_pos", C.c_int32), ("type_vocab", C.c_int32), ("tie_embeddings", C.c_int32),
                 ("norm_eps", C.c_float), ("rope_theta", C.c_float), ("rope_factor", C.c_float),
                 ("rope_low_freq_factor", C.c_float), ("rope_high_freq_factor", C.c_float),
-                ("rope_orig_max_pos", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("rope_orig_max_pos", C.c_int32), ("qkv_bias", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class SamplingC(C.Structure):

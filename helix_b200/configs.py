@@ -29,6 +29,19 @@ def tiny_llama(layers=2, head_dim=64, vocab=1000, rope_scaling=False):
                      rope_orig_max_pos=256 if rope_scaling else 0)
 
 
+def dse_qwen2_2b():
+    """Text backbone shape of MrLight/dse-qwen2-2b-mrl-v1 (Qwen2-VL-2B), the reference's default embedding model served
+    with `--task embed` (api/pkg/model/models.go:421-433): q/k/v biases, GQA 12/2, tied embeddings, last-token pooling."""
+    return ModelDesc(arch=LLAMA, hidden=1536, layers=28, heads=12, kv_heads=2, head_dim=128, ffn=8960, vocab=151936,
+                     max_pos=32768, tie_embeddings=1, norm_eps=1e-6, rope_theta=1000000.0, qkv_bias=1)
+
+
+def tiny_qwen2(layers=2, vocab=1000):
+    """Qwen2-style decoder in miniature: q/k/v biases, GQA group 6 (12 q heads over 2 kv heads), tied embeddings."""
+    return ModelDesc(arch=LLAMA, hidden=768, layers=layers, heads=12, kv_heads=2, head_dim=64, ffn=512, vocab=vocab,
+                     max_pos=4096, tie_embeddings=1, norm_eps=1e-6, rope_theta=1000000.0, qkv_bias=1)
+
+
 def tiny_bert(layers=2, vocab=1000):
     return ModelDesc(arch=BERT, hidden=256, layers=layers, heads=4, kv_heads=4, head_dim=64, ffn=512, vocab=vocab,
                      max_pos=512, type_vocab=2, norm_eps=1e-12)

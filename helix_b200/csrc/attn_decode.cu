@@ -453,11 +453,15 @@ cudaError_t attn_decode_init() {
   cudaError_t e;
   if ((e = set_attr<128, 1>()) != cudaSuccess) return e;
   if ((e = set_attr<128, 2>()) != cudaSuccess) return e;
+  if ((e = set_attr<128, 3>()) != cudaSuccess) return e;
   if ((e = set_attr<128, 4>()) != cudaSuccess) return e;
+  if ((e = set_attr<128, 6>()) != cudaSuccess) return e;
   if ((e = set_attr<128, 8>()) != cudaSuccess) return e;
   if ((e = set_attr<64, 1>()) != cudaSuccess) return e;
   if ((e = set_attr<64, 2>()) != cudaSuccess) return e;
+  if ((e = set_attr<64, 3>()) != cudaSuccess) return e;
   if ((e = set_attr<64, 4>()) != cudaSuccess) return e;
+  if ((e = set_attr<64, 6>()) != cudaSuccess) return e;
   return set_attr<64, 8>();
 }
 
@@ -473,7 +477,9 @@ cudaError_t attn_decode(cudaStream_t stream, const AttnDecodeArgs& a) {
     switch (G) {
       case 1: return launch<128, 1>(stream, a);
       case 2: return launch<128, 2>(stream, a);
+      case 3: return launch<128, 3>(stream, a);
       case 4: return launch<128, 4>(stream, a);
+      case 6: return launch<128, 6>(stream, a);
       case 8: return launch<128, 8>(stream, a);
       default: return cudaErrorInvalidValue;
     }
@@ -482,7 +488,9 @@ cudaError_t attn_decode(cudaStream_t stream, const AttnDecodeArgs& a) {
     switch (G) {
       case 1: return launch<64, 1>(stream, a);
       case 2: return launch<64, 2>(stream, a);
+      case 3: return launch<64, 3>(stream, a);
       case 4: return launch<64, 4>(stream, a);
+      case 6: return launch<64, 6>(stream, a);
       case 8: return launch<64, 8>(stream, a);
       default: return cudaErrorInvalidValue;
     }

@@ -55,15 +55,17 @@ __global__ void __launch_bounds__(64)
 qkv_rope_kvwrite_kernel(const float* __restrict__ ws, const uint8_t* __restrict__ segs, bf16* __restrict__ qkv_out,
                         const int32_t* __restrict__ positions, const int32_t* __restrict__ slot_mapping,
                         const float* __restrict__ inv_freq, bf16* __restrict__ k_cache, bf16* __restrict__ v_cache,
-                        int M, int Hq, int Hkv, int D, int page_size, const int* dep_wait, int dep_count, int* dep_done) {
+                        int M, int Hq, int Hkv, int D, int page_size, const int* dep_wait, int dep_count, int* dep_done,
+                        const bf16* __restrict__ bias) {
   pdl_launch_dependents();
   block_dep_wait(dep_wait, dep_count);
   const int h = blockIdx.x, m = blockIdx.y, j = threadIdx.x;
   const int half = D / 2;  // == blockDim.x
   const int N = (Hq + 2 * Hkv) * D;
   // GEMM output is rounded to bf16 first (same as the prefill epilogue); RoPE is evaluated in fp32 on top
-  const float a = bf16_round(slab_sum(ws, segs, M, N, m, h * D + j));
-  const float b = bf16_round(slab_sum(ws, segs, M, N, m, h * D + half + j));
+  const float ba = bias ? __bfloat162float(bias[h * D + j]) : 0.f, bb = bias ? __bfloat162float(bias[h * D + half + j]) : 0.f;
+  const float a = bf16_round(slab_sum(ws, segs, M, N, m, h * D + j) + ba);
+  const float b = bf16_round(slab_sum(ws, segs, M, N, m, h * D + half + j) + bb);
   const int slot = slot_mapping[m];
   const int page = slot >= 0 ? slot / page_size : 0, off = slot >= 0 ? slot % page_size : 0;
   if (h < Hq + Hkv) {
@@ -227,12 +229,12 @@ cudaError_t dec_sum_slabs(cudaStream_t s, const float* ws, const SkinnyPlan& p, 
 cudaError_t dec_qkv_rope_kvwrite(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* qkv_out,
                                  const int32_t* positions, const int32_t* slot_mapping, const float* inv_freq,
                                  bf16* k_cache, bf16* v_cache, int M, int Hq, int Hkv, int D, int page_size,
-                                 const DepSig* dep) {
+                                 const DepSig* dep, const bf16* bias) {
   const DepSig none{};
   if (!dep) dep = &none;
   return launch_k(qkv_rope_kvwrite_kernel, dim3(Hq + 2 * Hkv, M), dim3(D / 2), 0, s, true, ws, p.seg_count, qkv_out,
                   positions, slot_mapping, inv_freq, k_cache, v_cache, M, Hq, Hkv, D, page_size, dep->wait, dep->wait_count,
-                  dep->done);
+                  dep->done, bias);
 }
 int dec_qkv_rope_ctas(int M, int Hq, int Hkv) { return (Hq + 2 * Hkv) * M; }
 int dec_swiglu_ctas(int M, int F) { return ((F / 4 + 255) / 256) * M; }

@@ -595,7 +595,7 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
     bf16* vc = kc + layer_kv;
     SPAN(3, row_bytes, rmsnorm(stream_, x_, w.attn_norm, xn_, nullptr, T, H, d.norm_eps));
     {
-      GemmArgs g{xn_, H, w.wqkv, H, qkv_, QKV, nullptr, 0, nullptr, T, QKV, H, EPI_NONE, 0};
+      GemmArgs g{xn_, H, w.wqkv, H, qkv_, QKV, nullptr, 0, w.bqkv, T, QKV, H, w.bqkv ? EPI_BIAS : EPI_NONE, 0};
       SPAN(gcat, gwork(T, QKV, H), gemm_bf16_tn(stream_, g));
     }
     SPAN(3, 2.0 * T * (QD + 2.0 * KD) * 2, rope_kv_write(stream_, qkv_, positions, slots, model_.inv_freq, kc, vc, T, d.heads, d.kv_heads, D, page_));
@@ -752,7 +752,7 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
     {
       const DepSig dp = next_dep(dec_qkv_rope_ctas(B, d.heads, d.kv_heads));
       SPAN(3, 8.0 * B * QKV, dec_qkv_rope_kvwrite(stream_, skinny_ws_, plan_qkv_, qkv_, positions, slots, model_.inv_freq,
-                                                   kc, vc, B, d.heads, d.kv_heads, D, page_, &dp));
+                                                   kc, vc, B, d.heads, d.kv_heads, D, page_, &dp, w.bqkv));
     }
     {
       AttnDecodeArgs a{};
@@ -812,7 +812,7 @@ bool Engine::fused_decode_ok() const {
   static const int env = [] { const char* e = getenv("HB_DECODE_FUSED"); return e ? atoi(e) : -1; }();  // A/B override
   const hb_model_desc& d = model_.d;
   const bool on = env >= 0 ? env != 0 : cfg_.fused_decode != 0;
-  return on && cnt_qkv_ && (d.head_dim == 64 || d.head_dim == 128) && (d.heads * d.head_dim) % 128 == 0 &&
+  return on && cnt_qkv_ && !d.qkv_bias && (d.head_dim == 64 || d.head_dim == 128) && (d.heads * d.head_dim) % 128 == 0 &&
          (d.kv_heads * d.head_dim) % 128 == 0 && d.hidden % 128 == 0 && (2 * d.ffn) % 256 == 0;
 }
 

@@ -194,7 +194,7 @@ cudaError_t dec_sum_slabs(cudaStream_t s, const float* ws, const SkinnyPlan& p, 
 cudaError_t dec_qkv_rope_kvwrite(cudaStream_t s, const float* ws, const SkinnyPlan& p, bf16* qkv_out,
                                  const int32_t* positions, const int32_t* slot_mapping, const float* inv_freq,
                                  bf16* k_cache, bf16* v_cache, int M, int Hq, int Hkv, int D, int page_size,
-                                 const DepSig* dep = nullptr);
+                                 const DepSig* dep = nullptr, const bf16* qkv_bias = nullptr);
 int dec_qkv_rope_ctas(int M, int Hq, int Hkv);
 int dec_swiglu_ctas(int M, int F);
 // x = bf16(x + sum); xn = rmsnorm(x) * w (w may be null: residual update only)

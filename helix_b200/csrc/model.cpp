@@ -30,7 +30,7 @@ std::string validate_desc(const hb_model_desc& d) {
   if (d.arch == HB_ARCH_LLAMA) {
     if (d.kv_heads <= 0 || d.heads % d.kv_heads) return "heads must be a multiple of kv_heads";
     const int g = d.heads / d.kv_heads;
-    if (g != 1 && g != 2 && g != 4) return "GQA group (heads/kv_heads) must be 1, 2 or 4";
+    if (g != 1 && g != 2 && g != 3 && g != 4 && g != 6 && g != 8) return "GQA group (heads/kv_heads) must be 1, 2, 3, 4, 6 or 8";
     if (d.ffn % 128) return "ffn must be a multiple of 128 (SwiGLU tile packing)";
     if (d.rope_theta <= 0.f) return "rope_theta must be positive";
     if (d.vocab % 4) return "vocab must be a multiple of 4 (16-byte rows of the fp32 logits)";
@@ -72,6 +72,7 @@ static size_t carve(Model* m, const hb_model_desc& d, uint8_t* base) {
       LlamaLayerW w;
       w.attn_norm = c.take(H);
       w.wqkv = c.take((QD + 2 * KD) * H);
+      if (d.qkv_bias) w.bqkv = c.take(QD + 2 * KD);
       w.wo = c.take(H * QD);
       w.mlp_norm = c.take(H);
       w.wgu = c.take(2 * F * H);
@@ -80,6 +81,11 @@ static size_t carve(Model* m, const hb_model_desc& d, uint8_t* base) {
       put(p + "self_attn.q_proj.weight", w.wqkv, QD, H);
       put(p + "self_attn.k_proj.weight", w.wqkv ? w.wqkv + QD * H : nullptr, KD, H);
       put(p + "self_attn.v_proj.weight", w.wqkv ? w.wqkv + (QD + KD) * H : nullptr, KD, H);
+      if (d.qkv_bias) {
+        put(p + "self_attn.q_proj.bias", w.bqkv, QD, 1, 0, false, true);
+        put(p + "self_attn.k_proj.bias", w.bqkv ? w.bqkv + QD : nullptr, KD, 1, 0, false, true);
+        put(p + "self_attn.v_proj.bias", w.bqkv ? w.bqkv + QD + KD : nullptr, KD, 1, 0, false, true);
+      }
       put(p + "self_attn.o_proj.weight", w.wo, H, QD);
       put(p + "post_attention_layernorm.weight", w.mlp_norm, H, 1, 0, true);
       put(p + "mlp.gate_proj.weight", w.wgu, F, H, 1);

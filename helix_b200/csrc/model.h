@@ -15,6 +15,7 @@ namespace hb {
 
 struct LlamaLayerW {
   bf16 *attn_norm, *wqkv, *wo, *mlp_norm, *wgu, *wdown;
+  bf16* bqkv = nullptr;  // [q;k;v] projection biases (hb_model_desc.qkv_bias), else null
 };
 struct BertLayerW {
   bf16 *wqkv, *bqkv, *wo, *bo, *ln1_g, *ln1_b, *w1, *b1, *w2, *b2, *ln2_g, *ln2_b;

@@ -64,12 +64,13 @@ class ModelDesc:
     rope_low_freq_factor: float = 1.0
     rope_high_freq_factor: float = 4.0
     rope_orig_max_pos: int = 0
+    qkv_bias: int = 0     # Qwen2-family decoders: biases on the q/k/v projections
 
     def to_c(self):
         return ModelDescC(self.arch, self.hidden, self.layers, self.heads, self.kv_heads, self.head_dim, self.ffn,
                           self.vocab, self.max_pos, self.type_vocab, self.tie_embeddings, self.norm_eps,
                           self.rope_theta, self.rope_factor, self.rope_low_freq_factor, self.rope_high_freq_factor,
-                          self.rope_orig_max_pos)
+                          self.rope_orig_max_pos, self.qkv_bias)
 
 
 @dataclass

@@ -69,6 +69,8 @@ MODEL_CATALOGUE = {
     "meta-llama/Meta-Llama-3-8B-Instruct": (configs.llama3_8b, False),
     "meta-llama/Llama-3.2-1B-Instruct": (configs.llama32_1b, False),
     "BAAI/bge-base-en-v1.5": (configs.bge_base, True),
+    # the reference's default embedding model (api/pkg/model/models.go:421-433): text backbone, last-token pooling
+    "MrLight/dse-qwen2-2b-mrl-v1": (configs.dse_qwen2_2b, True),
 }
 
 

@@ -14,7 +14,7 @@ import numpy as np
 from .engine import ModelDesc, bf16_bits
 
 _DT = {"BF16": (np.uint16, 2), "F16": (np.float16, 2), "F32": (np.float32, 4)}
-_IGNORED = ("pooler.", "embeddings.position_ids", "rotary_emb.inv_freq", "cls.")
+_IGNORED = ("pooler.", "embeddings.position_ids", "rotary_emb.inv_freq", "cls.", "visual.")  # visual.: the VL tower (not served)
 
 
 def read_safetensors(path):
@@ -81,19 +81,23 @@ def load_safetensors(engine, desc: ModelDesc, paths):
 
 
 def desc_from_hf_config(cfg):
-    """HF config.json (dict or path) -> ModelDesc for the two supported families."""
+    """HF config.json (dict or path) -> ModelDesc: Llama- and Qwen2-family decoders, BERT-family encoders."""
     if not isinstance(cfg, dict):
         with open(cfg) as f:
             cfg = json.load(f)
     mt = cfg.get("model_type", "")
-    if mt == "llama":
+    if mt in ("qwen2", "qwen2_vl") and "text_config" in cfg:  # VL checkpoints nest the language model's configuration
+        cfg = dict(cfg["text_config"], model_type="qwen2")
+        mt = "qwen2"
+    if mt in ("llama", "qwen2"):
         heads = cfg["num_attention_heads"]
         rope = cfg.get("rope_parameters") or cfg.get("rope_scaling") or {}
         d = ModelDesc(arch=0, hidden=cfg["hidden_size"], layers=cfg["num_hidden_layers"], heads=heads,
                       kv_heads=cfg.get("num_key_value_heads", heads), head_dim=cfg.get("head_dim") or cfg["hidden_size"] // heads,
                       ffn=cfg["intermediate_size"], vocab=cfg["vocab_size"], max_pos=cfg.get("max_position_embeddings", 8192),
                       tie_embeddings=int(bool(cfg.get("tie_word_embeddings", False))), norm_eps=cfg.get("rms_norm_eps", 1e-5),
-                      rope_theta=float(rope.get("rope_theta", cfg.get("rope_theta", 10000.0))))
+                      rope_theta=float(rope.get("rope_theta", cfg.get("rope_theta", 10000.0))),
+                      qkv_bias=int(mt == "qwen2"))  # Qwen2: biases on q/k/v, otherwise the Llama layer
         if (rope.get("rope_type") or rope.get("type")) == "llama3":
             d.rope_factor = float(rope["factor"])
             d.rope_low_freq_factor = float(rope["low_freq_factor"])

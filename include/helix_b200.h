@@ -91,7 +91,9 @@ typedef struct hb_model_desc {
   float rope_factor;   /* llama3 rope scaling; <= 0 disables */
   float rope_low_freq_factor, rope_high_freq_factor;
   int32_t rope_orig_max_pos;
-  int32_t reserved[8];
+  int32_t qkv_bias;    /* 1: q/k/v projections carry biases (Qwen2-family decoders, e.g. the reference's default embedding
+                          model MrLight/dse-qwen2-2b-mrl-v1, api/pkg/model/models.go:421-433); everything else as Llama */
+  int32_t reserved[7];
 } hb_model_desc;
 
 typedef struct hb_sampling {

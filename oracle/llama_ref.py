@@ -69,9 +69,12 @@ class LlamaOracle:
         for i in range(d.layers):
             p = f"model.layers.{i}."
             xn = rmsnorm(x, sd[p + "input_layernorm.weight"], d.norm_eps)
-            q = (xn @ sd[p + "self_attn.q_proj.weight"].T).reshape(n, d.heads, d.head_dim)
-            k = (xn @ sd[p + "self_attn.k_proj.weight"].T).reshape(n, d.kv_heads, d.head_dim)
-            v = (xn @ sd[p + "self_attn.v_proj.weight"].T).reshape(n, d.kv_heads, d.head_dim)
+            q, k, v = (xn @ sd[p + f"self_attn.{t}_proj.weight"].T for t in "qkv")
+            if p + "self_attn.q_proj.bias" in sd:  # Qwen2-family decoders (HF modeling_qwen2.py: bias on q/k/v only)
+                q, k, v = (y + sd[p + f"self_attn.{t}_proj.bias"] for y, t in zip((q, k, v), "qkv"))
+            q = q.reshape(n, d.heads, d.head_dim)
+            k = k.reshape(n, d.kv_heads, d.head_dim)
+            v = v.reshape(n, d.kv_heads, d.head_dim)
             q = apply_rope(q, pos, self.inv_freq)
             k = apply_rope(k, pos, self.inv_freq)
             self.k[i] = k if self.k[i] is None else np.concatenate([self.k[i], k], 0)

@@ -34,6 +34,10 @@ def llama_state_dict(d, seed=0, std=0.02):
         sd[p + "self_attn.q_proj.weight"] = _t(seed, p + "q", (d.heads * D, H), std)
         sd[p + "self_attn.k_proj.weight"] = _t(seed, p + "k", (d.kv_heads * D, H), std)
         sd[p + "self_attn.v_proj.weight"] = _t(seed, p + "v", (d.kv_heads * D, H), std)
+        if getattr(d, "qkv_bias", 0):
+            sd[p + "self_attn.q_proj.bias"] = _t(seed, p + "qb", (d.heads * D,), 0.1)
+            sd[p + "self_attn.k_proj.bias"] = _t(seed, p + "kb", (d.kv_heads * D,), 0.1)
+            sd[p + "self_attn.v_proj.bias"] = _t(seed, p + "vb", (d.kv_heads * D,), 0.1)
         sd[p + "self_attn.o_proj.weight"] = _t(seed, p + "o", (H, d.heads * D), std)
         sd[p + "post_attention_layernorm.weight"] = _t(seed, p + "ln2", (H,), 0.05, 1.0)
         sd[p + "mlp.gate_proj.weight"] = _t(seed, p + "gate", (F, H), std)

@@ -40,6 +40,45 @@ def hf_llama(d, sd):
     return m
 
 
+def hf_qwen2(d, sd):
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    cfg = Qwen2Config(vocab_size=d.vocab, hidden_size=d.hidden, intermediate_size=d.ffn, num_hidden_layers=d.layers,
+                      num_attention_heads=d.heads, num_key_value_heads=d.kv_heads, max_position_embeddings=d.max_pos,
+                      rms_norm_eps=d.norm_eps, tie_word_embeddings=bool(d.tie_embeddings), use_sliding_window=False,
+                      rope_parameters={"rope_theta": d.rope_theta, "rope_type": "default"}, attn_implementation="eager")
+    assert cfg.hidden_size // cfg.num_attention_heads == d.head_dim
+    m = Qwen2ForCausalLM(cfg).float().eval()
+    missing, unexpected = m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not unexpected, unexpected
+    assert all("rotary" in k or (d.tie_embeddings and k == "lm_head.weight") for k in missing), missing
+    return m
+
+
+def gen_qwen2(name, d, seed, n_prompt, n_decode, std=0.05):
+    """Qwen2-family decoder (q/k/v biases, GQA group 6, tied embeddings): prompt logits, greedy decode and the last-token
+    embedding (final-norm hidden state of the last position, L2-normalised: the `--task embed` pooling)."""
+    sd = weights.llama_state_dict(d, seed, std)
+    m = hf_qwen2(d, sd)
+    prompt = weights.random_tokens(seed + 1, n_prompt, d.vocab)
+    ids = torch.from_numpy(prompt.astype(np.int64))[None]
+    out = m(ids, use_cache=True, output_hidden_states=True)
+    prompt_logits = out.logits[0].numpy()
+    h = out.hidden_states[-1][0, -1]          # HF applies the final norm before appending the last hidden state
+    emb = (h / h.norm().clamp_min(1e-12)).numpy()
+    past, logits = out.past_key_values, out.logits[0, -1]
+    toks, rows = [], []
+    for _ in range(n_decode):
+        rows.append(logits.numpy().copy())
+        t = int(torch.argmax(logits))
+        toks.append(t)
+        o = m(torch.tensor([[t]]), past_key_values=past, use_cache=True)
+        past, logits = o.past_key_values, o.logits[0, -1]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed=seed, std=std, prompt=prompt,
+                        prompt_logits=prompt_logits.astype(np.float32), greedy_tokens=np.array(toks, np.int32),
+                        step_logits=np.stack(rows).astype(np.float32), embedding=emb.astype(np.float32))
+    print(name, "greedy", toks[:8])
+
+
 def hf_bert(d, sd):
     from transformers import BertConfig, BertModel
     cfg = BertConfig(vocab_size=d.vocab, hidden_size=d.hidden, num_hidden_layers=d.layers, num_attention_heads=d.heads,
@@ -141,6 +180,9 @@ if __name__ == "__main__":
         d8 = configs.llama3_8b()
         d8.layers = 2
         gen_llama_fullshape("llama3_8b_2layer", d8, 4, 512, 8)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "qwen2":
+        gen_qwen2("qwen2_tiny", configs.tiny_qwen2(layers=2, vocab=1000), 6, 70, 10)
         sys.exit(0)
     gen_llama("llama_tiny_d64", configs.tiny_llama(layers=2, head_dim=64, vocab=1000), 0, 48, 12, 0.02)
     gen_llama("llama_tiny_d64_s05", configs.tiny_llama(layers=2, head_dim=64, vocab=1000), 0, 48, 12, 0.05)

@@ -87,6 +87,34 @@ def test_decoder_embedder_last_token_pooling_vs_oracle():
     assert st["kv_pages_free"] == st["kv_pages_total"]            # embeds never take pages
 
 
+def test_qwen2_style_decoder_generation_and_embedding(golden_dir):
+    """Qwen2-family decoder (hb_model_desc.qkv_bias: q/k/v biases; GQA group 6; tied embeddings) through the engine: prompt
+    logits and greedy decode (bias in the prefill GEMM epilogue and in the decode RoPE kernel) vs the HF fixture and the
+    oracle, and `--task embed` pooling vs HF's last-token hidden state."""
+    g = np.load(os.path.join(golden_dir, "qwen2_tiny.npz"))
+    d = configs.tiny_qwen2(layers=2, vocab=1000)
+    sd = weights.llama_state_dict(d, int(g["seed"]), float(g["std"]))
+    prompt, n_dec = g["prompt"], len(g["greedy_tokens"])
+    from helix_b200.engine import CAPTURE_PROMPT_LOGITS
+    with hb.Engine(hb.EngineConfig(max_seqs=4, max_ctx=256, max_batched_tokens=256, use_cuda_graphs=1)) as e:
+        e.load_state_dict(d, sd)
+        rids, outs = e.generate([prompt], hb.Sampling(max_tokens=n_dec, capture=CAPTURE_PROMPT_LOGITS | CAPTURE_STEP_LOGITS))
+        pl = e.captured_logits(rids[0], CAPTURE_PROMPT_LOGITS)
+        sl = e.captured_logits(rids[0], CAPTURE_STEP_LOGITS)
+        emb = e.embed([prompt, prompt[:5]])
+    assert np.abs(pl - g["prompt_logits"]).max() <= tol(g["prompt_logits"])
+    o = LlamaOracle(d, sd)
+    logits = o.forward(prompt)[-1]
+    for i, t in enumerate(outs[0]):
+        assert np.abs(sl[i] - logits).max() <= tol(logits), i
+        best = int(np.argmax(logits))
+        assert t == best or logits[best] - logits[t] <= 2 * tol(logits)
+        logits = o.forward([t])[-1]
+    assert outs[0][:4] == g["greedy_tokens"].tolist()[:4]
+    assert np.abs(emb[0] - g["embedding"]).max() <= 1e-2 and float(emb[0] @ g["embedding"]) >= 0.9999
+    assert np.abs(emb[1] - o.embed(prompt[:5])).max() <= 1e-2
+
+
 def _free_bytes():
     import torch
     return torch.cuda.mem_get_info(0)[0]

@@ -79,3 +79,16 @@ def test_llama_oracle_matches_hf_at_the_llama3_8b_shape(golden_dir):
     toks, srows = o.greedy(prompt, len(g["greedy_tokens"]))
     assert toks == g["greedy_tokens"].tolist()
     assert np.abs(srows[:, cols] - g["step_logits"]).max() < 5e-4
+
+
+def test_qwen2_style_decoder_oracle_matches_hf(golden_dir):
+    """Qwen2-family decoder (q/k/v biases, GQA group 6, tied embeddings — the architecture of the reference's default
+    embedding model, api/pkg/model/models.go:421-433): logits, greedy ids and the last-token embedding vs HF Qwen2ForCausalLM."""
+    g = np.load(os.path.join(golden_dir, "qwen2_tiny.npz"))
+    d = configs.tiny_qwen2(layers=2, vocab=1000)
+    o = LlamaOracle(d, weights.llama_state_dict(d, int(g["seed"]), float(g["std"])))
+    prompt = g["prompt"]
+    assert np.abs(o.forward(prompt) - g["prompt_logits"]).max() < 2e-4
+    toks, rows = o.greedy(prompt, len(g["greedy_tokens"]))
+    assert toks == g["greedy_tokens"].tolist() and np.abs(rows - g["step_logits"]).max() < 2e-4
+    assert np.abs(o.embed(prompt) - g["embedding"]).max() < 2e-5

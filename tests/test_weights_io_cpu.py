@@ -41,3 +41,16 @@ def test_desc_from_hf_config_matches_catalogue():
                                           "max_position_embeddings": 512, "type_vocab_size": 2, "layer_norm_eps": 1e-12})
     assert bge == configs.bge_base()
     assert weights_io.canonical_name("bert.encoder.layer.0.output.dense.weight", 1) == "encoder.layer.0.output.dense.weight"
+
+
+def test_qwen2_config_maps_to_a_biased_llama_layer():
+    from helix_b200.weights_io import desc_from_hf_config
+    d = desc_from_hf_config({"model_type": "qwen2", "hidden_size": 1536, "num_hidden_layers": 28, "num_attention_heads": 12,
+                             "num_key_value_heads": 2, "intermediate_size": 8960, "vocab_size": 151936, "rms_norm_eps": 1e-6,
+                             "rope_theta": 1000000.0, "tie_word_embeddings": True, "max_position_embeddings": 32768})
+    from helix_b200 import configs
+    want = configs.dse_qwen2_2b()
+    assert (d.qkv_bias, d.heads, d.kv_heads, d.head_dim, d.hidden, d.ffn, d.vocab, d.tie_embeddings) == \
+           (1, want.heads, want.kv_heads, want.head_dim, want.hidden, want.ffn, want.vocab, 1)
+    assert desc_from_hf_config({"model_type": "llama", "hidden_size": 256, "num_hidden_layers": 2, "num_attention_heads": 4,
+                                "intermediate_size": 512, "vocab_size": 1000}).qkv_bias == 0
