@@ -123,6 +123,84 @@ size_t scan_pretoken(const std::vector<Cp>& t, size_t i, size_t n) {
   return i + 1;  // unreachable for valid input: every character class is covered above
 }
 
+
+// ---- BERT WordPiece pipeline (HF tokenizers BertNormalizer + BertPreTokenizer + WordPiece) ----
+const uint32_t* seq_lookup(const uint32_t (*rows)[3], int n, const uint32_t* pool, uint32_t cp, int* len) {
+  int lo = 0, hi = n - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cp < rows[mid][0]) hi = mid - 1;
+    else if (cp > rows[mid][0]) lo = mid + 1;
+    else { *len = (int)rows[mid][2]; return pool + rows[mid][1]; }
+  }
+  *len = 0;
+  return nullptr;
+}
+bool is_chinese(uint32_t c) {
+  return (c >= 0x4E00 && c <= 0x9FFF) || (c >= 0x3400 && c <= 0x4DBF) || (c >= 0x20000 && c <= 0x2A6DF) || (c >= 0x2A700 && c <= 0x2B73F) ||
+         (c >= 0x2B740 && c <= 0x2B81F) || (c >= 0x2B920 && c <= 0x2CEAF) || (c >= 0xF900 && c <= 0xFAFF) || (c >= 0x2F800 && c <= 0x2FA1F);
+}
+bool bert_is_whitespace(uint32_t c) { return c == '\t' || c == '\n' || c == '\r' || is_space(c); }
+bool bert_is_control(uint32_t c) {
+  if (c == '\t' || c == '\n' || c == '\r') return false;
+  return c < 128 ? (c < 32 || c == 127) : in_ranges(kUniOther, kUniOther_n, c);
+}
+bool bert_is_punct(uint32_t c) {
+  if (c < 128) return (c >= 33 && c <= 47) || (c >= 58 && c <= 64) || (c >= 91 && c <= 96) || (c >= 123 && c <= 126);
+  return in_ranges(kUniPunct, kUniPunct_n, c);
+}
+void nfd_append(std::vector<uint32_t>& out, uint32_t c) {
+  if (c >= 0xAC00 && c <= 0xD7A3) {  // Hangul syllable: algorithmic decomposition
+    const uint32_t s = c - 0xAC00, l = 0x1100 + s / 588, v = 0x1161 + (s % 588) / 28, t = 0x11A7 + s % 28;
+    out.push_back(l);
+    out.push_back(v);
+    if (t != 0x11A7) out.push_back(t);
+    return;
+  }
+  int n = 0;
+  const uint32_t* d = c < 0xC0 ? nullptr : seq_lookup(kUniNfd, kUniNfd_n, kUniNfd_pool, c, &n);
+  if (d) out.insert(out.end(), d, d + n); else out.push_back(c);
+}
+// BertNormalizer(clean_text, handle_chinese_chars, strip_accents, lowercase) in the library's order
+std::vector<uint32_t> bert_normalize(const std::vector<Cp>& t, size_t n, bool clean, bool chinese, bool strip, bool lower) {
+  std::vector<uint32_t> a, b;
+  a.reserve(n + 8);
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t c = t[i].cp;
+    if (clean) {
+      if (c == 0 || c == 0xFFFD || bert_is_control(c)) continue;
+      a.push_back(bert_is_whitespace(c) ? ' ' : c);
+    } else {
+      a.push_back(c);
+    }
+  }
+  if (chinese) {
+    b.clear();
+    for (uint32_t c : a) {
+      if (is_chinese(c)) { b.push_back(' '); b.push_back(c); b.push_back(' '); } else b.push_back(c);
+    }
+    a.swap(b);
+  }
+  if (strip) {
+    b.clear();
+    for (uint32_t c : a) nfd_append(b, c);
+    a.clear();
+    for (uint32_t c : b)
+      if (!(c >= 0x300 && in_ranges(kUniMarkNonspacing, kUniMarkNonspacing_n, c))) a.push_back(c);
+  }
+  if (lower) {
+    b.clear();
+    for (uint32_t c : a) {
+      if (c < 128) { b.push_back((c >= 'A' && c <= 'Z') ? c + 32 : c); continue; }
+      int ln = 0;
+      const uint32_t* d = seq_lookup(kUniLower, kUniLower_n, kUniLower_pool, c, &ln);
+      if (d) b.insert(b.end(), d, d + ln); else b.push_back(c);
+    }
+    a.swap(b);
+  }
+  return a;
+}
+
 }  // namespace
 
 struct hb_tokenizer {
@@ -132,6 +210,11 @@ struct hb_tokenizer {
   struct Added { std::string content; int32_t id; bool special; };
   std::vector<Added> added;  // longest content first
   bool ignore_merges = false;
+  // WordPiece (BERT-family encoders)
+  bool wordpiece = false, bn_clean = true, bn_chinese = true, bn_strip = true, bn_lower = true;
+  std::string wp_prefix = "##", unk_token = "[UNK]";
+  int32_t unk_id = -1, cls_id = -1, sep_id = -1;
+  size_t wp_max_chars = 100;
   std::string byte_char[256];                       // ByteLevel: byte -> UTF-8 of its stand-in character
   std::unordered_map<uint32_t, uint8_t> char_byte;  // stand-in code point -> byte
   std::string error;
@@ -153,7 +236,9 @@ struct hb_tokenizer {
     if (!hbjson::parse(json_text.data(), json_text.size(), &root) || root.kind != JVal::OBJ) { error = "tokenizer.json: not a JSON object"; return false; }
     const JVal* model = root.get("model");
     const JVal* type = model ? model->get("type") : nullptr;
-    if (!model || model->kind != JVal::OBJ || (type && type->kind == JVal::STR && type->raw != "BPE")) { error = "tokenizer.json: model.type must be BPE"; return false; }
+    if (!model || model->kind != JVal::OBJ) { error = "tokenizer.json: model missing"; return false; }
+    if (type && type->kind == JVal::STR && type->raw == "WordPiece") wordpiece = true;
+    else if (type && type->kind == JVal::STR && type->raw != "BPE") { error = "tokenizer.json: model.type must be BPE or WordPiece"; return false; }
     const JVal* v = model->get("vocab");
     if (!v || v->kind != JVal::OBJ) { error = "tokenizer.json: model.vocab missing"; return false; }
     size_t max_id = 0;
@@ -186,6 +271,25 @@ struct hb_tokenizer {
     for (const auto& kv : vocab) id_to_token[kv.second] = kv.first;
     for (const Added& a : added) id_to_token[a.id] = a.content;
     init_bytes();
+    if (wordpiece) {
+      if (const JVal* p = model->get("continuing_subword_prefix"); p && p->kind == JVal::STR) wp_prefix = p->raw;
+      if (const JVal* u = model->get("unk_token"); u && u->kind == JVal::STR) unk_token = u->raw;
+      if (const JVal* mx = model->get("max_input_chars_per_word"); mx && mx->kind == JVal::NUM) wp_max_chars = (size_t)mx->num;
+      unk_id = added_id(unk_token);
+      cls_id = added_id("[CLS]");
+      sep_id = added_id("[SEP]");
+      if (const JVal* nz = root.get("normalizer"); nz && nz->kind == JVal::OBJ) {
+        auto flag = [&](const char* k, bool dflt) {
+          const JVal* v = nz->get(k);
+          return (v && v->kind == JVal::BOOL) ? v->b : dflt;
+        };
+        bn_clean = flag("clean_text", true);
+        bn_chinese = flag("handle_chinese_chars", true);
+        bn_lower = flag("lowercase", true);
+        const JVal* sa = nz->get("strip_accents");
+        bn_strip = (sa && sa->kind == JVal::BOOL) ? sa->b : bn_lower;  // null: follows lowercase
+      }
+    }
     return true;
   }
 
@@ -238,8 +342,47 @@ struct hb_tokenizer {
     }
   }
 
+  // WordPiece: normalise, split on whitespace / punctuation, greedy longest-match-first with the continuing prefix
+  void encode_wordpiece(const std::string& text, std::vector<int32_t>& out) const {
+    std::vector<Cp> t;
+    decode_utf8(text, t);
+    const std::vector<uint32_t> nrm = bert_normalize(t, t.size() - 1, bn_clean, bn_chinese, bn_strip, bn_lower);
+    std::vector<std::string> chars;  // the current word, one UTF-8 string per code point
+    auto flush = [&]() {
+      if (chars.empty()) return;
+      if (chars.size() > wp_max_chars) { out.push_back(unk_id); chars.clear(); return; }
+      std::vector<int32_t> pieces;
+      size_t start = 0;
+      bool bad = false;
+      while (start < chars.size()) {
+        size_t end = chars.size();
+        int32_t found = -1;
+        for (; end > start; --end) {
+          std::string sub = start ? wp_prefix : std::string();
+          for (size_t k = start; k < end; ++k) sub += chars[k];
+          auto it = vocab.find(sub);
+          if (it != vocab.end()) { found = it->second; break; }
+        }
+        if (found < 0) { bad = true; break; }
+        pieces.push_back(found);
+        start = end;
+      }
+      if (bad) out.push_back(unk_id); else out.insert(out.end(), pieces.begin(), pieces.end());
+      chars.clear();
+    };
+    for (uint32_t c : nrm) {
+      if (bert_is_whitespace(c)) { flush(); continue; }
+      std::string u;
+      append_utf8(u, c);
+      if (bert_is_punct(c)) { flush(); chars.push_back(u); flush(); continue; }
+      chars.push_back(u);
+    }
+    flush();
+  }
+
   void encode_plain(const std::string& text, std::vector<int32_t>& out) const {
     if (text.empty()) return;
+    if (wordpiece) { encode_wordpiece(text, out); return; }
     std::vector<Cp> t;
     decode_utf8(text, t);
     const size_t n = t.size() - 1;
@@ -275,6 +418,23 @@ struct hb_tokenizer {
   }
 
   std::string decode(const int32_t* ids, int n, bool skip_special) const {
+    if (wordpiece) {  // WordPiece decoder: pieces joined by spaces, continuing pieces glued on (cleanup off)
+      std::string s;
+      bool first = true;
+      for (int k = 0; k < n; ++k) {
+        const int32_t id = ids[k];
+        if (id < 0 || (size_t)id >= id_to_token.size()) continue;
+        bool special = false;
+        for (const Added& a : added)
+          if (a.id == id) { special = a.special; break; }
+        if (special && skip_special) continue;
+        const std::string& tok = id_to_token[id];
+        if (!first && tok.compare(0, wp_prefix.size(), wp_prefix) == 0) { s += tok.substr(wp_prefix.size()); }
+        else { if (!first) s += ' '; s += tok; }
+        first = false;
+      }
+      return s;
+    }
     std::string bytes;
     for (int k = 0; k < n; ++k) {
       const int32_t id = ids[k];
@@ -322,7 +482,15 @@ int32_t hb_tok_token_id(hb_tokenizer* t, const char* token) { return (t && token
 int hb_tok_encode(hb_tokenizer* t, const char* utf8, int32_t parse_special, int32_t* out, int32_t cap, int32_t* n) {
   if (!t || !utf8 || !n) return HB_ERR_INVALID;
   std::vector<int32_t> ids;
+  if (parse_special == 2) {  // the model's own framing, what HF's encode(add_special_tokens=True) adds
+    if (t->wordpiece && t->cls_id >= 0) ids.push_back(t->cls_id);
+    if (!t->wordpiece) {
+      const int32_t bot = t->added_id("<|begin_of_text|>");
+      if (bot >= 0) ids.push_back(bot);
+    }
+  }
   t->encode(utf8, parse_special != 0, ids);
+  if (parse_special == 2 && t->wordpiece && t->sep_id >= 0) ids.push_back(t->sep_id);
   *n = (int32_t)ids.size();
   if ((int32_t)ids.size() > cap || (!out && !ids.empty())) return HB_ERR_BUSY;  // *n tells the needed capacity
   if (!ids.empty()) memcpy(out, ids.data(), ids.size() * 4);

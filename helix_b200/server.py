@@ -202,12 +202,13 @@ class OpenAIServer:
 
     def embeddings(self, body):
         inp = body.get("input")
+        enc = getattr(self.tok, "encode_for_embedding", self.tok.encode)  # [CLS] ... [SEP] framing where the model has one
         if isinstance(inp, str):
-            seqs = [self.tok.encode(inp)]
+            seqs = [enc(inp)]
         elif isinstance(inp, list) and inp and isinstance(inp[0], int):
             seqs = [inp]
         elif isinstance(inp, list):
-            seqs = [self.tok.encode(x) if isinstance(x, str) else list(x) for x in inp]
+            seqs = [enc(x) if isinstance(x, str) else list(x) for x in inp]
         else:
             raise ValueError("input must be a string, a list of strings or token arrays")
         vocab = self.rt.engine.desc.vocab

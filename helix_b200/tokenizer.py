@@ -32,9 +32,14 @@ class NativeTokenizer:
     def token_id(self, token):
         return self._l.hb_tok_token_id(self._h, token.encode())
 
+    def encode_for_embedding(self, text):
+        """The model's own framing around the text ([CLS] ... [SEP] for WordPiece encoders): what the backend's tokenizer
+        adds before an embedding forward pass."""
+        return self.encode(text, parse_special=2)
+
     def encode(self, text, parse_special=False):
         raw = text.encode("utf-8")
-        cap = max(16, len(raw) + 8)
+        cap = max(16, len(raw) * 2 + 8)  # WordPiece: Chinese characters are isolated, accents may decompose
         n = C.c_int32()
         buf = np.empty(cap, np.int32)
         rc = self._l.hb_tok_encode(self._h, raw, int(parse_special), buf.ctypes.data, cap, C.byref(n))

@@ -220,14 +220,17 @@ int hb_logprobs(hb_engine* e, uint64_t req_id, int32_t first_row, int32_t max_ro
  *      (api/pkg/model/models.go:421-433); needs an engine that is not running generations concurrently. ---- */
 int hb_embed(hb_engine* e, const int32_t* tokens, const int32_t* offsets, int32_t nseq, float* out);
 
-/* ---- tokenizer (scope row F2): a HF tokenizer.json (byte-level BPE: the Llama-3 family) loaded natively, bit-exact with
- *      `tokenizers` 0.22 on that pipeline; what the backends do inside their child process before the first kernel runs.
+/* ---- tokenizer (scope row F2): a HF tokenizer.json loaded natively — byte-level BPE with the Llama-3 pre-tokenizer
+ *      (decoders) or BERT WordPiece with BertNormalizer / BertPreTokenizer (encoders such as bge) — bit-exact with
+ *      `tokenizers` 0.22 on those pipelines; what the backends do inside their child process before the first kernel runs.
  *      encode/decode/chat return HB_ERR_BUSY with the needed size in *n / *len when the caller's buffer is too small. ---- */
 typedef struct hb_tokenizer hb_tokenizer;
 int hb_tok_load(const char* tokenizer_json_path, hb_tokenizer** out);
 void hb_tok_free(hb_tokenizer* t);
 int32_t hb_tok_vocab_size(hb_tokenizer* t);
 int32_t hb_tok_token_id(hb_tokenizer* t, const char* token); /* -1 if absent; special tokens included */
+/* parse_special: 0 = plain text; 1 = special-token strings inside the text become their ids; 2 = 1 + the model's framing
+ * ([CLS] ... [SEP] for WordPiece encoders, <|begin_of_text|> for Llama-3 BPE): HF's encode(add_special_tokens=True) */
 int hb_tok_encode(hb_tokenizer* t, const char* utf8, int32_t parse_special, int32_t* out, int32_t cap, int32_t* n);
 int hb_tok_decode(hb_tokenizer* t, const int32_t* ids, int32_t n_ids, int32_t skip_special, char* out, size_t cap, size_t* len);
 /* Llama-3 instruct template over (role, content) pairs, ending with the assistant header */

@@ -8,7 +8,7 @@ import random
 
 import pytest
 from hypothesis import given, settings, strategies as st
-from tokenizers import Regex, Tokenizer, decoders, models, pre_tokenizers, trainers
+from tokenizers import Regex, Tokenizer, decoders, models, normalizers, pre_tokenizers, processors, trainers
 
 from helix_b200.server import HFTokenizer
 from helix_b200.tokenizer import NativeTokenizer
@@ -99,3 +99,47 @@ def test_llama3_chat_template_matches_the_python_mirror(tmp_path):
     ids = nt.chat(convo)
     assert ids[0] == nt.token_id("<|begin_of_text|>") and ids.count(nt.EOS) == len(convo)
     assert nt.decode(ids, skip_special=True) == py.decode(ids)
+
+
+def train_wordpiece(tmp_path, lowercase, seed):
+    tok = Tokenizer(models.WordPiece(unk_token="[UNK]", max_input_chars_per_word=100))
+    tok.normalizer = normalizers.BertNormalizer(clean_text=True, handle_chinese_chars=True, strip_accents=None, lowercase=lowercase)
+    tok.pre_tokenizer = pre_tokenizers.BertPreTokenizer()
+    tok.decoder = decoders.WordPiece(prefix="##", cleanup=False)
+    trainer = trainers.WordPieceTrainer(vocab_size=900, special_tokens=["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"], show_progress=False)
+    tok.train_from_iterator(corpus(seed), trainer)
+    tok.post_processor = processors.TemplateProcessing(single="[CLS] $A [SEP]", pair="[CLS] $A [SEP] $B:1 [SEP]:1",
+                                                       special_tokens=[("[CLS]", tok.token_to_id("[CLS]")), ("[SEP]", tok.token_to_id("[SEP]"))])
+    path = tmp_path / f"wordpiece_{int(lowercase)}.json"
+    tok.save(str(path))
+    return tok, path
+
+
+@pytest.mark.parametrize("lowercase", [True, False])
+def test_wordpiece_ids_match_hf_tokenizers(tmp_path, lowercase):
+    """BERT-family encoders (bge): BertNormalizer (clean text, isolate CJK, NFD + strip Mn marks, per-character lowercase)
+    -> BertPreTokenizer (whitespace, punctuation isolated) -> WordPiece greedy longest match — ids bit-exact vs HF, with and
+    without the [CLS] ... [SEP] framing the embedding path uses."""
+    hf, path = train_wordpiece(tmp_path, lowercase, 7)
+    nt = NativeTokenizer(path, eos_token="[SEP]")
+
+    def same(text):
+        want = hf.encode(text, add_special_tokens=False).ids
+        got = nt.encode(text, parse_special=True)
+        assert got == want, (text, got[:24], want[:24])
+        assert nt.encode_for_embedding(text) == hf.encode(text, add_special_tokens=True).ids
+        assert nt.decode(got, skip_special=True) == hf.decode(want, skip_special_tokens=True)
+    edge = ["", "  ", "Hello, World!", "naïve café Über STRASSE İstanbul", "日本語のテキスト mixed中文words", "don't stop-believing... 3.14 $9.99 (x) [y] {z}",
+            "x" * 101 + " ok", "zzzzqqqqjjjj unknownword", "tab\tsep\nnew\r\nline", "ＦＵＬＬｗｉｄｔｈ １２３", "Ångström Å Å ﬁ ǅ", "한국어 텍스트 가각",
+            "[CLS] literal [SEP] [MASK] inside", "emoji 😀 👍🏽 ok", "«quoted» “double” ‘single’ – dash — em", "a\u200bb\u00adc\ufeffd"]
+    edge = [e.encode().decode("unicode_escape") if "\\u" in e or "\\t" in e else e for e in edge]
+    for t in edge + corpus(107, 300):
+        same(t)
+    alphabet = st.sampled_from(list("abcXYZ 019'\n\t-_.,!?()") + ["é", "É", "ß", "Ω", "Σ", "я", "Я", "日", "本", "한", "ע", "😀", "\u00a0", "\u2003", "…", "—",
+                                                                   "the", "ing", "##", "İ", "ǅ", "ﬁ", "Å", "ü", "Ü", "\u0301", "\u200b"])
+
+    @settings(max_examples=1200, deadline=None)
+    @given(st.lists(alphabet, max_size=40))
+    def prop(parts):
+        same("".join(parts))
+    prop()
