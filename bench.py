@@ -512,7 +512,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-impl", default="oracle", choices=["oracle", "hf"], help="CPU stand-in behind cpu_baseline / --impl reference")
     ap.add_argument("--no-fixed-total", action="store_true")
-    ap.add_argument("--mixed-step-tokens", type=int, default=640)
+    ap.add_argument("--mixed-step-tokens", type=int, default=512)
     ap.add_argument("--fixed-total-sessions", type=int, default=256)
     ap.add_argument("--layers", type=int, default=0, help="debug: truncate the model (INVALID as a bench number)")
     ap.add_argument("--workload", default="llama8b", choices=["llama8b", "bge", "pack"])

@@ -599,14 +599,15 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
       SPAN(gcat, gwork(T, QKV, H), gemm_bf16_tn(stream_, g));
     }
     SPAN(3, 2.0 * T * (QD + 2.0 * KD) * 2, rope_kv_write(stream_, qkv_, positions, slots, model_.inv_freq, kc, vc, T, d.heads, d.kv_heads, D, page_));
-    if (prefill) {
+    const int Bd = prefill ? step_decode_rows_ : 0, Bpf = B - Bd, Tpf = T - Bd;  // mixed step: decode rows trail the batch
+    if (prefill && Bpf > 0) {
       AttnPrefillArgs a{};
       a.q = qkv_; a.ldq = QKV;
       a.k = qkv_ + QD; a.ldk = QKV;
       a.v = qkv_ + QD + KD; a.ldv = QKV;
       a.out = attn_; a.ldo = QD;
       a.cu_seqlens = cu;
-      a.B = B; a.T = T; a.max_seqlen = max_seqlen;
+      a.B = Bpf; a.T = Tpf; a.max_seqlen = max_seqlen;
       a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D;
       a.causal = 1;
       a.scale = 1.0f / sqrtf((float)D);
@@ -617,16 +618,20 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
         a.num_pages = num_pages_; a.page_size = page_;
       }
       SPAN(1, attn_flops_, attn_prefill(stream_, a));
-    } else {
+    }
+    if (!prefill || Bd > 0) {
+      // decode rows (a whole decode step on this generic path, or the running sequences riding in a mixed step): one query
+      // token per sequence over its paged context — the HBM-bound decode-attention kernel, not a 128-row prefill q tile each
+      const int b0 = prefill ? Bpf : 0, t0 = prefill ? Tpf : 0, nb = prefill ? Bd : B;
       AttnDecodeArgs a{};
-      a.q = qkv_; a.ldq = QKV;
+      a.q = qkv_ + (size_t)t0 * QKV; a.ldq = QKV;
       a.k_cache = kc; a.v_cache = vc;
-      a.page_table = pt; a.max_pages = max_pages_per_seq_;
-      a.ctx_lens = ctx;
-      a.out = attn_; a.ldo = QD;
+      a.page_table = pt + (size_t)b0 * max_pages_per_seq_; a.max_pages = max_pages_per_seq_;
+      a.ctx_lens = ctx + b0;
+      a.out = attn_ + (size_t)t0 * QD; a.ldo = QD;
       a.workspace = dec_ws_;
-      a.B = B; a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D; a.page_size = page_;
-      a.num_splits = decode_splits(B);
+      a.B = nb; a.Hq = d.heads; a.Hkv = d.kv_heads; a.D = D; a.page_size = page_;
+      a.num_splits = decode_splits(nb);
       a.scale = 1.0f / sqrtf((float)D);
       a.num_pages = num_pages_;
       SPAN(2, attn_bytes_, attn_decode(stream_, a));
@@ -1221,11 +1226,13 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
   const int B = (int)batch.size();
   int T = 0, max_len = 0;
   bool want_all = false, paged = false;
-  for (Request* r : batch) {  // this step covers prompt[prefilled, prefilled + chunk) of every request
+  const int Bp = B - step_decode_rows_;  // the trailing step_decode_rows_ entries are decode rows of a mixed step
+  for (int i = 0; i < B; ++i) {  // this step covers tokens [prefilled, prefilled + chunk) of every request
+    Request* r = batch[i];
     T += r->chunk;
     max_len = std::max(max_len, r->chunk);
     want_all |= (r->sp.capture & HB_CAPTURE_PROMPT_LOGITS) != 0 && r->prefilled + r->chunk <= (int)r->prompt.size();
-    paged |= r->prefilled > 0;
+    if (i < Bp) paged |= r->prefilled > 0;
   }
   if (want_all) {
     if (T > 4096) return fail(HB_ERR_INVALID, "HB_CAPTURE_PROMPT_LOGITS limited to 4096 prompt tokens per step");
@@ -1257,7 +1264,7 @@ int Engine::run_prefill(std::vector<Request*>& batch) {
     }
     last[i] = t - 1;
     ctx[i] = end;
-    if (paged) {
+    if (paged || i >= Bp) {
       const int np = (end + page_ - 1) / page_;
       for (int j = 0; j < np; ++j) pt[(size_t)i * max_pages_per_seq_ + j] = r->pages[j];
     }
@@ -1518,9 +1525,11 @@ int Engine::step(int* did_work) {
       waiting_.pop_front();
     }
     ensure_decode_pages();
+    step_decode_rows_ = 0;
     if (!batch.empty()) {
       prefill = true;
       if (cfg_.decode_with_prefill) {
+        step_decode_rows_ = (int)running_.size();
         for (Request* r : running_) {  // decode rows: a one-token chunk at the end of the cached sequence
           r->prefilled = r->kv_len;
           r->chunk = 1;
@@ -1652,6 +1661,7 @@ int Engine::embed(const int32_t* toks, const int32_t* offsets, int nseq, float* 
   std::lock_guard<std::mutex> gg(gpu_mu_);
   CU(cudaSetDevice(cfg_.device));
   SmLimitScope sm_scope(cfg_.sm_budget);
+  step_decode_rows_ = 0;  // an embedding pass has no decode rows (the field belongs to the last scheduler step)
   const int bmax = dec ? cfg_.max_seqs : b_cap_;
   int s0 = 0;
   while (s0 < nseq) {

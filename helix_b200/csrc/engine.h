@@ -171,6 +171,7 @@ class Engine {
   int skinny_max_b_ = 0;
   int32_t* sampled_ = nullptr;
   void* sample_ws_ = nullptr;
+  int step_decode_rows_ = 0;    // mixed step: the last N batch entries are decode rows (attention through the decode kernel)
   int step_flags_ = 0;          // StepFlags of the current step: top-k/top-p filter, penalties, log-probabilities
   size_t pen_cap_ = 0;          // penalty entries the step block can hold
   unsigned long long* dec_trace_ = nullptr;  // HB_DEC_TRACE timeline buffer (debug)
