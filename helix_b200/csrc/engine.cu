@@ -1210,7 +1210,8 @@ int Engine::logprobs(uint64_t id, int first_row, int max_rows, int32_t* ids, flo
   if (width) *width = w;
   int have = w ? (int)(r->lp_ids.size() / w) : 0;
   have = std::min(have, (int)r->out.size());  // rows become visible together with their token
-  int n = std::max(0, std::min(max_rows, have - std::max(0, first_row)));
+  if (first_row < 0) first_row = 0;
+  int n = std::max(0, std::min(max_rows, have - first_row));
   if (n > 0 && ids && lps) {
     memcpy(ids, r->lp_ids.data() + (size_t)first_row * w, (size_t)n * w * 4);
     memcpy(lps, r->lp_vals.data() + (size_t)first_row * w, (size_t)n * w * 4);
