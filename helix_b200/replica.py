@@ -1,7 +1,8 @@
 """Host-side logic of the multi-GPU path: replicas only, one process per GPU.
 
-* one broadcast of rank 0's weight arena fills every replica (NCCL over NVLink on GPUs; the same code
-  path runs over gloo on CPU tensors in the tests);
+* one broadcast of rank 0's weight arena fills every replica: on GPUs that is `hb_model_load_broadcast` (ncclBroadcast
+  issued inside libhelixb200.so, engine.Engine.load_broadcast); `broadcast_buffer` below is the same step over a
+  torch.distributed group and only serves the CPU (gloo) test of the host logic;
 * sessions are routed to replicas the way the scheduler routes requests to warm slots
   (api/pkg/scheduler/scheduler.go:1958-2009: fewest active requests first, ties by lowest load, then order);
 * throughput of the job = all units processed / max-over-ranks time.
