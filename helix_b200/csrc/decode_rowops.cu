@@ -13,16 +13,8 @@ namespace {
 __device__ __forceinline__ float slab_sum(const float* __restrict__ ws, const uint8_t* __restrict__ segs, int M, int N,
                                           int m, int n) {
   const int ns = segs[n >> 7];
-  // all slab loads are issued before the first add (a load-add loop over a runtime count pays one L2 round trip per
-  // slab); the sum itself stays in slab order 0..ns-1
-  float v[8];
-#pragma unroll
-  for (int s = 0; s < 8; ++s) v[s] = (s < ns) ? ws[((size_t)s * M + m) * N + n] : 0.f;
   float acc = 0.f;
-#pragma unroll
-  for (int s = 0; s < 8; ++s)
-    if (s < ns) acc += v[s];
-  for (int s = 8; s < ns; ++s) acc += ws[((size_t)s * M + m) * N + n];
+  for (int s = 0; s < ns; ++s) acc += ws[((size_t)s * M + m) * N + n];
   return acc;
 }
 // block-wide entry / exit of a kernel in the decode chain (ptx.cuh dep_*)
