@@ -62,6 +62,9 @@ SIGNATURES = {
     "hb_model_tensor_set": (I, [P, C.c_char_p, P, C.c_size_t]),
     "hb_model_load_finish": (I, [P]),
     "hb_model_load_random": (I, [P, C.POINTER(ModelDescC), C.c_uint64]),
+    "hb_gguf_describe": (I, [C.c_char_p, C.POINTER(ModelDescC)]),
+    "hb_model_load_gguf": (I, [P, C.c_char_p]),
+    "hb_gguf_read_tensor": (I, [C.c_char_p, C.c_char_p, P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "hb_model_weights_arena": (I, [P, C.POINTER(P), C.POINTER(C.c_size_t)]),
     "hb_memory_estimate": (I, [C.POINTER(ModelDescC), C.POINTER(EngineCfg), C.POINTER(C.c_uint64),
                                C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

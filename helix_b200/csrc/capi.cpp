@@ -6,6 +6,7 @@
 #include "../../include/helix_b200.h"
 #include "../../include/helix_b200_kernels.h"
 #include "engine.h"
+#include "gguf.h"
 #include "tma_host.h"
 
 using hb::Engine;
@@ -54,6 +55,39 @@ int hb_model_tensor_set(hb_engine* e, const char* name, const void* host, size_t
 int hb_model_load_finish(hb_engine* e) { return e ? e->impl.load_finish() : HB_ERR_INVALID; }
 int hb_model_load_random(hb_engine* e, const hb_model_desc* d, uint64_t seed) {
   return (e && d) ? e->impl.load_random(*d, seed) : HB_ERR_INVALID;
+}
+int hb_model_load_gguf(hb_engine* e, const char* path) { return e ? e->impl.load_gguf(path) : HB_ERR_INVALID; }
+int hb_gguf_describe(const char* path, hb_model_desc* desc) {
+  if (!path || !desc) return HB_ERR_INVALID;
+  hb::GgufFile g;
+  std::string err;
+  if (!g.open(path, &err) || !g.describe(desc, &err)) {
+    g_last_create_error = "gguf: " + err;
+    return HB_ERR_INVALID;
+  }
+  return HB_OK;
+}
+int hb_gguf_read_tensor(const char* path, const char* hf_name, float* out, size_t cap, size_t* rows, size_t* cols) {
+  if (!path || !hf_name || !rows || !cols) return HB_ERR_INVALID;
+  hb::GgufFile g;
+  std::string err;
+  hb_model_desc d;
+  if (!g.open(path, &err) || !g.describe(&d, &err)) {
+    g_last_create_error = "gguf: " + err;
+    return HB_ERR_INVALID;
+  }
+  for (const auto& kv : g.tensors()) {
+    if (hb::gguf_to_hf_name(kv.first) != hf_name) continue;
+    std::vector<float> f;
+    if (!g.read_f32(kv.first, &f, rows, cols)) return HB_ERR_INVALID;
+    const bool permute = g.str("general.architecture") == "llama";
+    if (permute && strstr(hf_name, "self_attn.q_proj.weight")) hb::gguf_unpermute_rows(f, *rows, *cols, d.heads);
+    if (permute && strstr(hf_name, "self_attn.k_proj.weight")) hb::gguf_unpermute_rows(f, *rows, *cols, d.kv_heads);
+    if (!out || cap < f.size()) return HB_ERR_BUSY;  // *rows x *cols floats needed
+    memcpy(out, f.data(), f.size() * 4);
+    return HB_OK;
+  }
+  return HB_ERR_NOT_FOUND;
 }
 int hb_model_weights_arena(hb_engine* e, void** p, size_t* b) { return e ? e->impl.weights_arena(p, b) : HB_ERR_INVALID; }
 int hb_memory_estimate(const hb_model_desc* d, const hb_engine_cfg* c, uint64_t* w, uint64_t* kv, uint64_t* ws) {

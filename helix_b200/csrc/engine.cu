@@ -1,5 +1,6 @@
 #include "engine.h"
 
+#include "gguf.h"
 #include "launch.h"
 #include "nccl_dl.h"
 #include "tma_host.h"
@@ -443,6 +444,33 @@ int Engine::load_random(const hb_model_desc& d, uint64_t seed) {
   load_open_ = false;
   loaded_ = true;
   return HB_OK;
+}
+
+// GGUF checkpoint -> arena: metadata gives the description, every tensor is dequantised to bf16 on the host and uploaded
+// under its HF name (gguf.cpp); q/k projections of llama-architecture files are un-permuted to the rotate-half row order.
+int Engine::load_gguf(const char* path) {
+  GgufFile g;
+  std::string err;
+  if (!path || !g.open(path, &err)) return fail(HB_ERR_INVALID, "gguf: " + (path ? err : std::string("null path")));
+  hb_model_desc d;
+  if (!g.describe(&d, &err)) return fail(HB_ERR_INVALID, "gguf: " + err);
+  int rc = load_begin(d);
+  if (rc != HB_OK) return rc;
+  const bool permute = g.str("general.architecture") == "llama";
+  std::vector<float> f;
+  std::vector<uint16_t> bits;
+  for (const auto& kv : g.tensors()) {
+    const std::string hf = gguf_to_hf_name(kv.first);
+    if (hf.empty()) continue;  // tensors the engine has no use for
+    size_t rows = 0, cols = 0;
+    if (!g.read_f32(kv.first, &f, &rows, &cols)) return fail(HB_ERR_INVALID, "gguf: cannot read " + kv.first);
+    if (permute && hf.find("self_attn.q_proj.weight") != std::string::npos) gguf_unpermute_rows(f, rows, cols, d.heads);
+    if (permute && hf.find("self_attn.k_proj.weight") != std::string::npos) gguf_unpermute_rows(f, rows, cols, d.kv_heads);
+    gguf_to_bf16(f, &bits);
+    rc = tensor_set(hf.c_str(), bits.data(), bits.size());
+    if (rc != HB_OK) return rc;
+  }
+  return load_finish();
 }
 
 int Engine::weights_arena(void** p, size_t* bytes) {

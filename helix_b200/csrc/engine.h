@@ -63,6 +63,7 @@ class Engine {
   int tensor_set(const char* name, const void* host_bf16, size_t n);
   int load_finish();
   int load_random(const hb_model_desc& d, uint64_t seed);
+  int load_gguf(const char* path);
   int weights_arena(void** p, size_t* bytes);
 
   int start();

@@ -107,6 +107,28 @@ def replica_unique_id() -> bytes:
     return buf.raw
 
 
+def gguf_describe(path) -> ModelDesc:
+    d = ModelDescC()
+    rc = _lib.lib().hb_gguf_describe(str(path).encode(), C.byref(d))
+    if rc != 0:
+        raise HBError(rc, (_lib.lib().hb_last_error(None) or b"").decode())
+    return ModelDesc(**{k: getattr(d, k) for k, _ in ModelDescC._fields_ if not k.startswith("reserved")})
+
+
+def gguf_read_tensor(path, hf_name):
+    """One tensor of a GGUF file as fp32 [rows, cols] in the HF layout (dequantised, q/k rows un-permuted)."""
+    l = _lib.lib()
+    rows, cols = C.c_size_t(), C.c_size_t()
+    rc = l.hb_gguf_read_tensor(str(path).encode(), hf_name.encode(), None, 0, C.byref(rows), C.byref(cols))
+    if rc not in (0, -6):
+        raise HBError(rc, (l.hb_last_error(None) or b"").decode() or f"tensor {hf_name} not in {path}")
+    out = np.empty((rows.value, cols.value), np.float32)
+    rc = l.hb_gguf_read_tensor(str(path).encode(), hf_name.encode(), out.ctypes.data, out.size, C.byref(rows), C.byref(cols))
+    if rc != 0:
+        raise HBError(rc, "hb_gguf_read_tensor failed")
+    return out
+
+
 def memory_estimate(desc: ModelDesc, cfg: EngineConfig):
     l = _lib.lib()
     w, kv, ws = C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -155,6 +177,11 @@ class Engine:
             self._ck(self._l.hb_model_tensor_set(self._h, name.encode(), bits.ctypes.data, bits.size))
         self._ck(self._l.hb_model_load_finish(self._h))
         self.desc = desc
+
+    def load_gguf(self, path):
+        """A llama.cpp / Ollama GGUF blob: description from its metadata, tensors dequantised to bf16 (hb_model_load_gguf)."""
+        self.desc = gguf_describe(path)
+        self._ck(self._l.hb_model_load_gguf(self._h, str(path).encode()))
 
     def load_broadcast(self, desc: ModelDesc, uid: bytes, rank: int, world: int):
         """Replica load (hb_model_load_broadcast): rank 0 sends its loaded arena, the others receive it. Returns seconds."""

@@ -174,6 +174,13 @@ int hb_model_load_begin(hb_engine* e, const hb_model_desc* desc);
 int hb_model_tensor_set(hb_engine* e, const char* name, const void* host_bf16, size_t n_elems);
 int hb_model_load_finish(hb_engine* e);
 int hb_model_load_random(hb_engine* e, const hb_model_desc* desc, uint64_t seed);
+/* ---- GGUF (llama.cpp / Ollama blobs, the format of the reference's default catalogue, e.g. "llama3:instruct" = 8B Q4_0:
+ *      api/pkg/model/models.go:259-266): metadata -> description, tensors dequantised to bf16 (F32 F16 BF16 Q8_0 Q4_0 Q4_1
+ *      Q5_0 Q5_1 Q4_K Q5_K Q6_K), llama.cpp's q/k row permutation undone.  hb_gguf_read_tensor returns one tensor as fp32 in
+ *      the HF layout (tests, tooling); HB_ERR_BUSY with *rows / *cols set when `cap` floats are not enough. ---- */
+int hb_gguf_describe(const char* path, hb_model_desc* desc_out);
+int hb_model_load_gguf(hb_engine* e, const char* path);
+int hb_gguf_read_tensor(const char* path, const char* hf_name, float* out, size_t cap_floats, size_t* rows, size_t* cols);
 /* device address/size of the contiguous weight arena: replicas receive it by one NCCL broadcast */
 int hb_model_weights_arena(hb_engine* e, void** dev_ptr, size_t* bytes);
 /* ---- replicas: one engine per GPU, weights loaded on rank 0 and copied to the others by ONE

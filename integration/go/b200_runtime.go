@@ -34,7 +34,7 @@ type B200RuntimeParams struct {
 	ContextLength          int64    // optional
 	Args                   []string // vLLM-style args from the scheduler (scheduler/runner.go:1187-1259,1344-1397)
 	Desc                   C.hb_model_desc
-	CheckpointDir          string // HF checkpoint directory (*.safetensors); empty = random init from Seed (benchmarks)
+	CheckpointDir          string // HF checkpoint directory (*.safetensors) or a llama.cpp / Ollama *.gguf blob; empty = random init from Seed (benchmarks)
 	Seed                   uint64
 	Tokenizer              Tokenizer // see b200_front.go
 	// Replica load (SURVEY.md §8e): when World > 1, rank 0 loads the checkpoint and every rank calls
@@ -137,6 +137,17 @@ func (r *B200Runtime) loadWeights() error {
 	}
 	if r.p.CheckpointDir == "" {
 		if rc := C.hb_model_load_random(r.eng, &r.p.Desc, C.uint64_t(r.p.Seed)); rc != C.HB_OK {
+			return r.lastError()
+		}
+	} else if strings.HasSuffix(r.p.CheckpointDir, ".gguf") {
+		// an Ollama blob (the reference's default catalogue format): description from the file's metadata, tensors
+		// dequantised to bf16 inside the library
+		cpath := C.CString(r.p.CheckpointDir)
+		defer C.free(unsafe.Pointer(cpath))
+		if rc := C.hb_gguf_describe(cpath, &r.p.Desc); rc != C.HB_OK {
+			return fmt.Errorf("helix-b200: %s", C.GoString(C.hb_last_error(nil)))
+		}
+		if rc := C.hb_model_load_gguf(r.eng, cpath); rc != C.HB_OK {
 			return r.lastError()
 		}
 	} else {

@@ -125,6 +125,37 @@ def test_qwen2_style_decoder_generation_and_embedding(golden_dir):
     assert np.abs(emb[1] - o.embed(prompt[:5])).max() <= 1e-2
 
 
+@pytest.mark.parametrize("arch", ["llama", "qwen2"])
+def test_gguf_checkpoint_loads_and_generates_like_the_oracle(tmp_path, arch):
+    """hb_model_load_gguf: a llama.cpp-format file with the tensor types Ollama's blobs use (Q4_0 / Q4_K / Q5_K / Q6_K / Q8_0 /
+    F32 norms; q/k rows in llama.cpp's permuted order) is dequantised into the arena; greedy generation then matches the
+    fp32 oracle run on the (bf16-rounded) dequantised weights."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gguf_ref import llama_gguf
+    d = configs.tiny_llama(layers=2, head_dim=64, vocab=1000) if arch == "llama" else configs.tiny_qwen2(layers=2, vocab=1000)
+    if arch == "llama":
+        d.hidden, d.heads, d.kv_heads, d.ffn = 512, 8, 2, 1024     # rows of 512 / 1024: whole K-quant super-blocks
+    rng = np.random.default_rng(11)
+    path = tmp_path / f"{arch}.gguf"
+    sd = llama_gguf(path, d, rng, {"embd": "Q8_0", "attn": "Q4_0", "v": "Q6_K", "ffn": "Q4_K", "down": "Q5_K", "output": "Q6_K"}, arch=arch)
+    sd = {k: weights.to_bf16_f32(v) for k, v in sd.items()}   # what the arena holds: one bf16 rounding of the dequantised value
+    prompt = weights.random_tokens(12, 40, d.vocab)
+    with hb.Engine(hb.EngineConfig(max_seqs=2, max_ctx=256, max_batched_tokens=256, use_cuda_graphs=1)) as e:
+        e.load_gguf(path)
+        assert e.desc.hidden == d.hidden and e.desc.qkv_bias == d.qkv_bias
+        rids, outs = e.generate([prompt], hb.Sampling(max_tokens=8, capture=CAPTURE_STEP_LOGITS))
+        sl = e.captured_logits(rids[0], CAPTURE_STEP_LOGITS)
+    o = LlamaOracle(e.desc, sd)
+    logits = o.forward(prompt)[-1]
+    for i, t in enumerate(outs[0]):
+        bound = 1.5 * tol(logits)
+        assert np.abs(sl[i] - logits).max() <= bound, (i, float(np.abs(sl[i] - logits).max()), bound)
+        best = int(np.argmax(logits))
+        assert t == best or logits[best] - logits[t] <= 2 * bound
+        logits = o.forward([t])[-1]
+
+
 def _free_bytes():
     import torch
     return torch.cuda.mem_get_info(0)[0]
