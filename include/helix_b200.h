@@ -19,6 +19,17 @@
  *        <- Runtime.Status (slot.go:46-57): non-empty status == running (scheduler/scheduler.go:940).
  *   hb_memory_estimate
  *        <- POST /api/v1/memory-estimate (api/pkg/runner/memory_estimation_handlers.go:36-327).
+ *   hb_slot_config
+ *        <- Slot.Create's decoding of CreateRunnerSlotAttributes / runtime_args (api/pkg/runner/slot.go:395-470).
+ *   hb_logprobs, hb_sampling.{logprobs, presence_penalty, frequency_penalty}
+ *        <- request fields the runner forwards untouched (openai.ChatCompletionRequest, openai_chat_handlers.go:100-175).
+ *   hb_replica_unique_id / hb_model_load_broadcast
+ *        <- the backend's own NCCL when a model spans the box's GPUs (api/pkg/runner/vllm_runtime.go:748-754); here:
+ *           replicas, weights copied by one broadcast.
+ *   hb_model_load_gguf / hb_gguf_describe
+ *        <- llama.cpp's GGUF load inside `ollama serve` (api/pkg/runner/ollama_runtime.go:546-697).
+ *   hb_tok_*
+ *        <- the tokenizer + chat template the backends apply inside their child process (Dockerfile.runner:61-74,188-191).
  *
  * Conventions: 0 = ok, negative = hb_status error; caller owns every host buffer; the engine owns all
  * device memory and (after hb_engine_start) one step-loop thread; all entry points are thread-safe; no
