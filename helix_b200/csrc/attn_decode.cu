@@ -59,7 +59,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
                    const int32_t* __restrict__ ctx_lens, float* __restrict__ ws, int Hkv, int num_splits,
                    float scale_log2, bf16* __restrict__ out_direct, int ldo, const int* sig_wait, int sig_wait_count,
                    int* sig_done, int bank_tiles, const bf16* __restrict__ k_cache, const bf16* __restrict__ v_cache,
-                   unsigned long long* trace, const int* dep_wait, int dep_count, int* dep_done) {
+                   unsigned long long* trace, const int* dep_wait, int dep_count, int* dep_done,
+                   const __grid_constant__ DecodeRope rope) {
   using C = DCfg<D>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -76,7 +77,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
   uint64_t* q_ready = bars + 2 * STAGES + 4;
   uint64_t* p_full = bars + 2 * STAGES + 5;
   uint64_t* pv_done = bars + 2 * STAGES + 6;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 7);
+  uint64_t* kv_ready = bars + 2 * STAGES + 7;  // fused RoPE prologue: this CTA's new K/V row is in the cache
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
   // Programmatic dependent launch: only two things here depend on the kernel before this one (RoPE + KV write of the
   // step's new token): q, and the LAST kv tile (it holds the new position).  Everything else — page table, context
@@ -128,6 +130,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
     mbar_init(q_ready, 4);
     mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
+    mbar_init(kv_ready, 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -149,7 +152,9 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
       for (int j = 0; j < n_tiles; ++j) {
         const int pg0 = (t_begin + j) * 2;
         if (t_begin + j == n_tiles_total - 1) {  // the tile with the step's new position
-          if (dep_wait) {
+          if (rope.ws) {  // written by this CTA's own softmax warps (fused prologue), fenced for the async proxy
+            mbar_wait(kv_ready, 0);
+          } else if (dep_wait) {
             if (elected) dep_wait_thread(dep_wait, dep_count);
             __syncwarp();
             if (elected) fence_proxy_async_all();
@@ -257,7 +262,58 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
       pdl_wait();
     }
     if (t == 0) trace_ev(trace, 3);
-    {
+    if (rope.ws) {
+      // fused prologue: q heads of this group, and the sequence's new K / V row, from the QKV GEMM's slabs
+      constexpr int HALF = D / 2;
+      const int Hq = Hkv * G;
+      const int slot = rope.slots[b], pos = rope.positions[b];
+      const int page = slot >= 0 ? slot / PAGE : 0, off = slot >= 0 ? slot % PAGE : 0;
+      for (int i = t; i < C::Q_BYTES / 16; i += 128) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0, 0, 0, 0);  // rows G..15 stay zero
+      for (int i = t; i < C::P_BYTES / 16; i += 128) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0, 0, 0, 0);
+      bar_sync(1, 128);
+      auto slab = [&](int n) {  // fixed slab order, as in decode_rowops.cu
+        const int ns = rope.segs[n >> 7];
+        float acc = 0.f;
+        for (int sgi = 0; sgi < ns; ++sgi) acc += rope.ws[((size_t)sgi * rope.M + b) * rope.N + n];
+        return acc;
+      };
+      auto q_elem = [&](int g, int e) {  // address of element e of q row g in the K-major swizzled B-operand layout
+        const int c = e >> 3;
+        return reinterpret_cast<bf16*>(sQ + (c >> 3) * (NQ * 128) + g * 128 + (((c & 7) ^ (g & 7)) << 4) + (e & 7) * 2);
+      };
+      for (int pp = t; pp < (G + 2) * HALF; pp += 128) {
+        const int hl = pp / HALF, j = pp % HALF;
+        const int head = hl < G ? kvh * G + hl : (hl == G ? Hq + kvh : Hq + Hkv + kvh);
+        const int n0 = head * D + j, n1 = n0 + HALF;
+        const float b0 = rope.bias ? __bfloat162float(rope.bias[n0]) : 0.f, b1 = rope.bias ? __bfloat162float(rope.bias[n1]) : 0.f;
+        // the projection output is rounded to bf16 first (as in the prefill epilogue); RoPE is evaluated in fp32 on top
+        const float a = __bfloat162float(__float2bfloat16(slab(n0) + b0)), bb = __bfloat162float(__float2bfloat16(slab(n1) + b1));
+        if (hl <= G) {
+          float sn, cs;
+          sincosf((float)pos * rope.inv_freq[j], &sn, &cs);
+          const bf16 lo = __float2bfloat16(a * cs - bb * sn), hi = __float2bfloat16(bb * cs + a * sn);
+          if (hl < G) {
+            *q_elem(hl, j) = lo;
+            *q_elem(hl, HALF + j) = hi;
+          } else if (slot >= 0) {
+            const size_t dst = (((size_t)page * Hkv + kvh) * PAGE + off) * D;
+            rope.k_cache[dst + j] = lo;
+            rope.k_cache[dst + HALF + j] = hi;
+          }
+        } else if (slot >= 0) {
+          const size_t dst = (((size_t)page * Hkv + kvh) * PAGE + off) * D;
+          rope.v_cache[dst + j] = __float2bfloat16(a);
+          rope.v_cache[dst + HALF + j] = __float2bfloat16(bb);
+        }
+      }
+      fence_proxy_async_smem();   // q in shared memory -> tcgen05 reads
+      fence_proxy_async_all();    // K / V row in global memory -> this CTA's own TMA load of the last tile
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(q_ready);
+        mbar_arrive(kv_ready);
+      }
+    } else {
       const bf16* qsrc = q + (size_t)b * ldq + (size_t)kvh * G * D;
       constexpr int CH = D / 8;  // 16-byte chunks per row
       for (int i = t; i < NQ * CH; i += 128) {
@@ -441,7 +497,8 @@ cudaError_t launch(cudaStream_t stream, const AttnDecodeArgs& a) {
   cudaError_t e = launch_k(attn_decode_kernel<D, G>, grid, dim3(kThreads), DCfg<D>::SMEM, stream, true, mk, mv, a.q, a.ldq,
                            a.page_table, a.max_pages, a.ctx_lens, a.workspace, a.Hkv, a.num_splits,
                            a.scale * 1.4426950408889634f, direct, a.ldo, a.sig.wait, a.sig.wait_count, a.sig.done, bank_tiles,
-                           a.k_cache, a.v_cache, a.sig.trace, a.sig.dep.wait, a.sig.dep.wait_count, a.sig.dep.done);
+                           a.k_cache, a.v_cache, a.sig.trace, a.sig.dep.wait, a.sig.dep.wait_count, a.sig.dep.done,
+                           a.num_splits == 1 ? a.rope : DecodeRope{});
   if (e != cudaSuccess || direct) return e;
   return launch_k(attn_decode_combine_kernel<D>, dim3(a.Hq, a.B), dim3(D / 2), 0, stream, true,
                   (const float*)a.workspace, a.out, a.ldo, a.Hq, a.Hkv, G, a.num_splits);

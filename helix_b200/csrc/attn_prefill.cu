@@ -70,8 +70,13 @@ template <int D>
 struct ACfg {
   static constexpr int Q_BYTES = BQ * D * 2;    // one q tile
   static constexpr int KV_BYTES = BKV * D * 2;
-  static constexpr int STAGES = 4;              // K ring and V ring depth (16 KB tiles at D = 128)
-  static constexpr int SMEM = 2 * Q_BYTES + 2 * STAGES * KV_BYTES + 1024 + 512;
+  static constexpr int STAGES = D == 128 ? 3 : 4;  // K ring and V ring depth (16 KB tiles at D = 128)
+  // D = 64 (encoder; short sequences, an item's output write-back is a large part of its time) stages O in shared
+  // memory and writes it with TMA: one 32-row x 128 B swizzled box per softmax warp.  At D = 128 the K/V rings leave no room.
+  static constexpr bool STAGE_O = true;
+  static constexpr int O_STAGE_BYTES = 32 * D * 2;  // per softmax warp
+  static constexpr int BAR_BYTES = 1024;            // barriers + TMEM pointer, padded so the staging area stays 1024-aligned
+  static constexpr int SMEM = 2 * Q_BYTES + 2 * STAGES * KV_BYTES + 1024 + BAR_BYTES + (STAGE_O ? 8 * O_STAGE_BYTES : 0);
   static constexpr int SUB = D / 64;  // 64-column swizzle sub-tiles per row
 };
 
@@ -99,7 +104,8 @@ struct ACfg {
 template <int D, bool PAGED, int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                    const __grid_constant__ CUtensorMap map_v, bf16* __restrict__ out, int ldo,
+                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
+                    bf16* __restrict__ out, int ldo,
                     const int32_t* __restrict__ cu_seqlens, int B, int Hq, int group, int causal, float scale_log2,
                     int max_q_pairs, const int32_t* __restrict__ kv_lens, const int32_t* __restrict__ page_table,
                     int max_pages, int Hkv) {
@@ -123,6 +129,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint64_t* v_full = k_empty + KST;
   uint64_t* v_empty = v_full + KST;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(v_empty + KST);
+  uint8_t* sO = reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES;  // [8 softmax warps][32 rows][D] (STAGE_O only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = max_q_pairs * B * Hq;
@@ -158,6 +165,7 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
+    if constexpr (C::STAGE_O) tma_prefetch_desc(&map_o);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 2);  // both issuers
     for (int i = 0; i < 4; ++i) {
@@ -451,28 +459,72 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       mbar_wait(&pv_done[t * 2 + ((jt + nt - 1) & 1)], ((jt + nt - 1) >> 1) & 1);
       tc_fence_after();
       const float inv_l = l > 0.f ? 1.0f / l : 0.f;
-      bf16* orow = out + (size_t)(it.seq0 + qrow) * ldo + it.h * D;
+      bool staged = false;
+      if constexpr (C::STAGE_O) {
+        // Every thread writing its own 128-byte row straight to global is 32 distinct lines per store instruction: ncu
+        // showed the warps spending about as long draining those stores (LSU queue, then the next TMEM load and even a
+        // stack reload stuck behind them) as waiting for the last PV.  Full 32-row chunks go through a swizzled staging
+        // buffer and ONE bulk tensor store per warp; the ragged last chunk of a sequence keeps the direct path.
+        staged = it.q0 + t * BQ + qd * 32 + 32 <= it.len;  // warp-uniform
+        if (staged) {
+          uint8_t* stage = sO + (warp - 3) * C::O_STAGE_BYTES;
+          if (lane == 0) tma_store_wait_read<0>();  // this warp's previous store has finished reading the buffer
+          __syncwarp();
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tO + c * 32, o);
-        tmem_ld_wait();
-        if (qrow < it.len) {
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tO + c * 32, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-            w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-            w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-            w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = w;
+            for (int i = 0; i < 4; ++i) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+              w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+              w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+              w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+              // 128B swizzle of the box: 16-byte chunk index ^ (row & 7); the box base is 1024-aligned and lane == row
+              *reinterpret_cast<uint4*>(stage + (c >> 1) * (32 * 128) + lane * 128 + ((((c & 1) * 4 + i) ^ (lane & 7)) << 4)) = w;
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < C::SUB; ++c)
+              tma_store_2d(&map_o, stage + c * (32 * 128), it.h * D + c * 64, it.seq0 + it.q0 + t * BQ + qd * 32);
+            tma_store_commit();
+            mbar_arrive(&o_free[t]);
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[t]);
+      if (!staged) {
+        bf16* orow = out + (size_t)(it.seq0 + qrow) * ldo + it.h * D;
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tO + c * 32, o);
+          tmem_ld_wait();
+          if (qrow < it.len) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+              w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+              w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+              w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = w;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[t]);
+      }
       jt += nt;
+    }
+    if constexpr (C::STAGE_O) {
+      if (lane == 0) tma_store_wait_all<0>();  // the bulk stores read this CTA's shared memory: finish them before exit
     }
   }
 
@@ -487,7 +539,8 @@ attn_prefill_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 template <int D, bool PAGED, int POLY>
 cudaError_t launch_p(cudaStream_t stream, const AttnPrefillArgs& a) {
   using C = ACfg<D>;
-  CUtensorMap mq, mk, mv;
+  CUtensorMap mq, mk, mv, mo;
+  if (!make_tmap_2d(&mo, a.out, TM_BF16, (uint64_t)a.Hq * D, (uint64_t)a.T, (uint64_t)a.ldo * 2, 64, 32)) return cudaErrorInvalidValue;
   if (!make_tmap_2d(&mq, a.q, TM_BF16, (uint64_t)a.Hq * D, (uint64_t)a.T, (uint64_t)a.ldq * 2, 64, BQ)) return cudaErrorInvalidValue;
   if (PAGED) {
     // pool plane = [page][kv head][64 positions][D]: one 3-D block per (page, kv head), as in the decode kernel
@@ -509,7 +562,7 @@ cudaError_t launch_p(cudaStream_t stream, const AttnPrefillArgs& a) {
   const long long items = (long long)max_q_pairs * a.B * a.Hq;
   const int grid = (int)std::min<long long>(items, effective_sms(num_sms));  // hb_engine_cfg.sm_budget
   const float scale_log2 = a.scale * 1.4426950408889634f;
-  kern<<<grid, kThreads, C::SMEM, stream>>>(mq, mk, mv, a.out, a.ldo, a.cu_seqlens, a.B, a.Hq, a.Hq / a.Hkv, a.causal,
+  kern<<<grid, kThreads, C::SMEM, stream>>>(mq, mk, mv, mo, a.out, a.ldo, a.cu_seqlens, a.B, a.Hq, a.Hq / a.Hkv, a.causal,
                                             scale_log2, max_q_pairs, a.kv_lens, a.page_table, a.max_pages, a.Hkv);
   return cudaGetLastError();
 }

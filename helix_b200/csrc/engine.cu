@@ -744,6 +744,9 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
   static const int flags_env = [] { const char* e = getenv("HB_DECODE_FLAGS"); return e ? atoi(e) : -1; }();
   const int splits = decode_splits(B);
   const bool flags = dep_ != nullptr && flags_env > 0 && splits == 1;  // measured slower than griddepcontrol.wait: opt-in
+  // RoPE + KV write inside the attention kernel's prologue (one kernel and one boundary fewer per layer); needs one split
+  static const int fuse_env = [] { const char* e = getenv("HB_DECODE_FUSE_ROPE"); return e ? atoi(e) : -1; }();
+  const bool fuse_rope = (fuse_env > 0) && splits == 1 && !flags && page_ == 64;
   const size_t n_sig = (size_t)(5 * d.layers + 1), n_dep = (size_t)(9 * d.layers + 2);
   if (handover || flags) CU(cudaMemsetAsync(sig_, 0, (n_sig + n_dep) * sizeof(int), stream_));  // dep_ follows sig_
   int prev_idx = -1, prev_count = 0;
@@ -782,7 +785,7 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
       const StreamSig sg = next_sig(5 * l + 0, plan_qkv_.grid);  // layer 0: no predecessor counter -> griddepcontrol.wait
       SPAN(4, wbytes(QKV, H), gemm_skinny(stream_, plan_qkv_, xn_, H, w.wqkv, H, skinny_ws_, B, QKV, H, &sg));
     }
-    {
+    if (!fuse_rope) {
       const DepSig dp = next_dep(dec_qkv_rope_ctas(B, d.heads, d.kv_heads));
       SPAN(3, 8.0 * B * QKV, dec_qkv_rope_kvwrite(stream_, skinny_ws_, plan_qkv_, qkv_, positions, slots, model_.inv_freq,
                                                    kc, vc, B, d.heads, d.kv_heads, D, page_, &dp, w.bqkv));
@@ -799,6 +802,11 @@ int Engine::forward_llama_decode(int B, const StepLayout& L) {
       a.num_splits = splits;
       a.scale = 1.0f / sqrtf((float)D);
       a.num_pages = num_pages_;
+      if (fuse_rope) {  // the attention CTAs build q / K / V from the QKV slabs themselves (kernels.h DecodeRope)
+        a.rope.ws = skinny_ws_; a.rope.segs = plan_qkv_.seg_count; a.rope.M = B; a.rope.N = QKV; a.rope.bias = w.bqkv;
+        a.rope.positions = positions; a.rope.slots = slots; a.rope.inv_freq = model_.inv_freq;
+        a.rope.k_cache = kc; a.rope.v_cache = vc;
+      }
       a.sig = next_sig(5 * l + 1, splits * d.kv_heads * B);
       SPAN(2, attn_bytes_, attn_decode(stream_, a));
       if (a.num_splits > 1) launches_.fetch_add(1, std::memory_order_relaxed);  // combine kernel

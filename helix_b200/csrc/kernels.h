@@ -127,6 +127,21 @@ struct StreamSig {
 };
 
 // ---- K6: paged-KV decode attention (one query token per sequence), split-KV + combine ----
+// Optional prologue of the decode-attention kernel (one split only): each CTA (sequence b, kv head) is the ONLY consumer of
+// that sequence's q heads of the group and of its new K/V row, so it builds them itself from the QKV GEMM's slabs — slab sum
+// (+ bias), bf16 rounding, RoPE, K/V written into the paged cache, q staged straight into shared memory — and the separate
+// RoPE / KV-write kernel (and its kernel boundary) disappears from the layer.  Same arithmetic as dec_qkv_rope_kvwrite.
+struct DecodeRope {
+  const float* ws = nullptr;        // QKV GEMM slabs [seg][M][N]; nullptr = q is read from AttnDecodeArgs::q as usual
+  const uint8_t* segs = nullptr;    // slabs per 128-column tile
+  int M = 0, N = 0;                 // batch rows, (Hq + 2 Hkv) * D
+  const bf16* bias = nullptr;       // [N] or null
+  const int32_t* positions = nullptr;
+  const int32_t* slots = nullptr;
+  const float* inv_freq = nullptr;
+  bf16* k_cache = nullptr;          // writable views of the layer's planes
+  bf16* v_cache = nullptr;
+};
 struct AttnDecodeArgs {
   const bf16* q; int ldq;          // [B, >=Hq*D] (post-RoPE)
   const bf16* k_cache;             // [num_pages][Hkv][page_size][D]
@@ -140,6 +155,7 @@ struct AttnDecodeArgs {
   float scale;
   int num_pages;                   // pages in the pool (TMA tensor-map extent)
   StreamSig sig;                   // HBM hand-over with the neighbouring streaming kernels (optional)
+  DecodeRope rope;                 // build q / K / V from the QKV GEMM's slabs inside the kernel (num_splits == 1 only)
 };
 cudaError_t attn_decode(cudaStream_t stream, const AttnDecodeArgs& a);
 size_t attn_decode_workspace_floats(int B, int Hq, int D, int num_splits);
