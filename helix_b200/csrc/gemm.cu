@@ -170,12 +170,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     const bool elected = elect_one_sync();
+    // L2 policy follows the tile order: the grouped operand's slice is what the rasterisation keeps resident (evict-last),
+    // the swept operand streams past it (evict-first).  Bit 1 of tile_group_n switches the hints on.
+    const bool hints = (tile_group_n & 2) != 0;
+    const uint64_t hint_a = !hints ? kEvictNormal : ((tile_group_n & 1) ? kEvictFirst : kEvictLast);
+    const uint64_t hint_b = !hints ? kEvictNormal : ((tile_group_n & 1) ? kEvictLast : kEvictFirst);
     {
       int s = 0;
       uint32_t phase = 0;
       for (int t = tile_worker; t < num_tiles; t += tile_workers) {
         int mi, ni;
-        tile_coords(t, num_m, num_n, tile_grp, tile_group_n, mi, ni);
+        tile_coords(t, num_m, num_n, tile_grp, tile_group_n & 1, mi, ni);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
           if (elected) {
@@ -184,13 +189,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               if (is_leader) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
               else mbar_arrive_cluster(&full_bar[s], 0);
               tma_load_2d_2sm(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K,
-                              mi * TILE_M + (int)cta_rank * BLOCK_M, kEvictNormal);
+                              mi * TILE_M + (int)cta_rank * BLOCK_M, hint_a);
               tma_load_2d_2sm(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K,
-                              ni * BN + (int)cta_rank * (BN / 2), kEvictNormal);
+                              ni * BN + (int)cta_rank * (BN / 2), hint_b);
             } else {
               mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-              tma_load_2d(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, mi * BLOCK_M, kEvictNormal);
-              tma_load_2d(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K, ni * BN, kEvictNormal);
+              tma_load_2d(smem_a + s * C::A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, mi * BLOCK_M, hint_a);
+              tma_load_2d(smem_b + s * C::B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K, ni * BN, hint_b);
             }
           }
           if (++s == STAGES) { s = 0; phase ^= 1; }
@@ -248,7 +253,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int it = 0;
     for (int t = tile_worker; t < num_tiles; t += tile_workers, ++it) {
       int mi, ni;
-      tile_coords(t, num_m, num_n, tile_grp, tile_group_n, mi, ni);
+      tile_coords(t, num_m, num_n, tile_grp, tile_group_n & 1, mi, ni);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = mi * TILE_M + (int)cta_rank * BLOCK_M;
@@ -428,7 +433,8 @@ cudaError_t launch_cfg(cudaStream_t stream, const GemmArgs& g, int num_sms) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (CG > 1) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mr, g.bias, g.M, g.N, g.K, grp, group_n);
+  static const int l2_hints = [] { const char* e = getenv("HB_GEMM_L2HINTS"); return e ? atoi(e) : 0; }();  // A/B knob
+  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mr, g.bias, g.M, g.N, g.K, grp, group_n | (l2_hints ? 2 : 0));
 }
 
 bool use_pair() {  // HB_GEMM_2CTA=0 falls back to single-CTA tiles (A/B measurements)
