@@ -103,6 +103,7 @@ SIGNATURES = {
     "hbk_rmsnorm": (I, [P, P, P, P, I, I, C.c_float]),
     "hbk_layernorm": (I, [P, P, P, P, I, I, C.c_float]),
     "hbk_rope_kv_write": (I, [P, P, P, P, P, P, I, I, I, I, I]),
+    "hbk_gemm_qkv_rope": (I, [P, I, P, I, P, P, P, P, P, P, P, I, I, I, I, I, I]),
     "hbk_sample": (I, [P, I, P, P, P, I, I]),
     "hbk_sample_filtered": (I, [P, I, P, P, P, P, P, I, I]),
     "hbk_apply_penalties": (I, [P, I, P, P, I, I]),

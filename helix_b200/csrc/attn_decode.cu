@@ -291,7 +291,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_const
         if (hl <= G) {
           float sn, cs;
           sincosf((float)pos * rope.inv_freq[j], &sn, &cs);
-          const bf16 lo = __float2bfloat16(a * cs - bb * sn), hi = __float2bfloat16(bb * cs + a * sn);
+          const bf16 lo = __float2bfloat16(rope_lo(a, bb, cs, sn)), hi = __float2bfloat16(rope_hi(a, bb, cs, sn));
           if (hl < G) {
             *q_elem(hl, j) = lo;
             *q_elem(hl, HALF + j) = hi;

@@ -194,6 +194,25 @@ int hbk_rope_kv_write(void* qkv, const int32_t* positions, const int32_t* slot_m
   return kret(hb::rope_kv_write(0, (hb::bf16*)qkv, positions, slot_mapping, inv_freq, (hb::bf16*)k_cache,
                                 (hb::bf16*)v_cache, T, Hq, Hkv, D, page_size));
 }
+int hbk_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, void* qkv, const void* bias, const int32_t* positions,
+                      const int32_t* slot_mapping, const float* inv_freq, void* k_cache, void* v_cache, int T, int K,
+                      int Hq, int Hkv, int D, int page_size) {
+  const int N = (Hq + 2 * Hkv) * D;
+  float* cs = nullptr;
+  cudaError_t e = cudaMalloc(&cs, (size_t)T * D * 4);
+  if (e != cudaSuccess) return kret(e);
+  e = hb::rope_table(0, positions, inv_freq, cs, T, D);
+  if (e == cudaSuccess) {
+    hb::GemmArgs g{(const hb::bf16*)A, lda, (const hb::bf16*)W, ldw, qkv, N, nullptr, 0, (const hb::bf16*)bias, T, N, K, hb::EPI_ROPE, 0};
+    g.rope.out = (hb::bf16*)qkv; g.rope.ldc = N; g.rope.cs = cs; g.rope.slots = slot_mapping;
+    g.rope.k_cache = (hb::bf16*)k_cache; g.rope.v_cache = (hb::bf16*)v_cache;
+    g.rope.Hq = Hq; g.rope.Hkv = Hkv; g.rope.D = D; g.rope.page_size = page_size;
+    e = hb::gemm_bf16_tn(0, g);
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaFree(cs);
+  return kret(e);
+}
 static int sample_impl(const float* logits, int ldl, const float* temperature, const uint64_t* seed, const int32_t* top_k,
                        const float* top_p, int32_t* out, int B, int V) {
   void* scratch = nullptr;

@@ -71,7 +71,7 @@ qkv_rope_kvwrite_kernel(const float* __restrict__ ws, const uint8_t* __restrict_
   if (h < Hq + Hkv) {
     float sn, cs;
     sincosf((float)positions[m] * inv_freq[j], &sn, &cs);
-    const bf16 lo = __float2bfloat16(a * cs - b * sn), hi = __float2bfloat16(b * cs + a * sn);
+    const bf16 lo = __float2bfloat16(rope_lo(a, b, cs, sn)), hi = __float2bfloat16(rope_hi(a, b, cs, sn));
     if (h < Hq) {
       bf16* qrow = qkv_out + (size_t)m * N + h * D;
       qrow[j] = lo;

@@ -193,6 +193,7 @@ size_t Engine::workspace_bytes() const {
     b += al256(fused_counter_ints(d) * sizeof(int));              // tile arrival counters of the fused decode GEMMs
     b += al256((size_t)((d.hidden + 127) / 128) * kSkinnySsStride * sizeof(float));  // RMSNorm per-tile partials
     b += al256(skinny_ws_bytes(148));                         // decode GEMM partial slabs
+    b += al256(T * (size_t)d.head_dim * 4);                   // cos/sin table of a step (QKV epilogue)
   }
   return b;
 }
@@ -348,6 +349,7 @@ int Engine::alloc_runtime() {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg_.device);
     skinny_ws_ = (float*)take(skinny_ws_bytes(148));
+    rope_cs_ = (float*)take(T * (size_t)d.head_dim * 4);
     if (skinny_ws_bytes(sms) > skinny_ws_bytes(148)) return fail(HB_ERR_INVALID, "unexpected SM count for the decode workspace");
     skinny_max_b_ = std::min(cfg_.max_seqs, 256);
     const int QD = d.heads * d.head_dim, QKV = model_.qkv_cols();
@@ -617,6 +619,11 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
   auto gwork = [&](double M, double N, double K) { return prefill ? 2.0 * M * N * K : 2.0 * (N * K + M * K + M * N); };
   const double row_bytes = 2.0 * T * H * 2;
   SPAN(3, 2.0 * T * H, embed_gather(stream_, tokens, model_.embed, x_, T, H));
+  // RoPE + KV scatter ride in the QKV projection's epilogue (EPI_ROPE) when its 256-column tiles hold whole heads; the
+  // step's cos/sin table is built once here and read by every layer.  HB_PREFILL_FUSE_ROPE=0 keeps the separate row kernel.
+  static const bool fuse_env = [] { const char* e = getenv("HB_PREFILL_FUSE_ROPE"); return !(e && atoi(e) == 0); }();
+  const bool fuse_rope = fuse_env && QKV % 256 == 0 && (D == 64 || D == 128);
+  if (fuse_rope) SPAN(3, 1.0 * T * D * 4, rope_table(stream_, positions, model_.inv_freq, rope_cs_, T, D));
   for (int l = 0; l < d.layers; ++l) {
     const LlamaLayerW& w = model_.ll[l];
     bf16* kc = kv_ + (size_t)l * 2 * layer_kv;
@@ -624,9 +631,16 @@ int Engine::forward_llama(int T, int B, bool prefill, int max_seqlen, const Step
     SPAN(3, row_bytes, rmsnorm(stream_, x_, w.attn_norm, xn_, nullptr, T, H, d.norm_eps));
     {
       GemmArgs g{xn_, H, w.wqkv, H, qkv_, QKV, nullptr, 0, w.bqkv, T, QKV, H, w.bqkv ? EPI_BIAS : EPI_NONE, 0};
+      if (fuse_rope) {
+        g.epi = EPI_ROPE;
+        g.rope.out = qkv_; g.rope.ldc = QKV; g.rope.cs = rope_cs_; g.rope.slots = slots;
+        g.rope.k_cache = kc; g.rope.v_cache = vc;
+        g.rope.Hq = d.heads; g.rope.Hkv = d.kv_heads; g.rope.D = D; g.rope.page_size = page_;
+      }
       SPAN(gcat, gwork(T, QKV, H), gemm_bf16_tn(stream_, g));
     }
-    SPAN(3, 2.0 * T * (QD + 2.0 * KD) * 2, rope_kv_write(stream_, qkv_, positions, slots, model_.inv_freq, kc, vc, T, d.heads, d.kv_heads, D, page_));
+    if (!fuse_rope)
+      SPAN(3, 2.0 * T * (QD + 2.0 * KD) * 2, rope_kv_write(stream_, qkv_, positions, slots, model_.inv_freq, kc, vc, T, d.heads, d.kv_heads, D, page_));
     const int Bd = prefill ? step_decode_rows_ : 0, Bpf = B - Bd, Tpf = T - Bd;  // mixed step: decode rows trail the batch
     if (prefill && Bpf > 0) {
       AttnPrefillArgs a{};

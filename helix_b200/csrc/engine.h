@@ -165,6 +165,7 @@ class Engine {
   uint8_t* ws_ = nullptr;
   size_t ws_bytes_ = 0;
   bf16 *x_ = nullptr, *xn_ = nullptr, *qkv_ = nullptr, *attn_ = nullptr, *h_ = nullptr;
+  float* rope_cs_ = nullptr;  // [t_cap][head_dim] cos | sin of the current step's positions (EPI_ROPE)
   float* logits_ = nullptr;
   float* dec_ws_ = nullptr;
   float* skinny_ws_ = nullptr;  // fp32 partial slabs of the decode-step GEMMs

@@ -94,7 +94,8 @@ template <int BN, int EPI, int CG = 1>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
-               const bf16* __restrict__ bias, int M, int N, int K, int tile_grp, int tile_group_n) {
+               const bf16* __restrict__ bias, int M, int N, int K, int tile_grp, int tile_group_n,
+               const __grid_constant__ RopeEpi rope) {
   using C = Cfg<BN, CG>;
   constexpr int TILE_M = BLOCK_M * CG;  // rows of one UMMA tile (per CTA: BLOCK_M)
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -106,6 +107,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   constexpr bool kSwiGLU = (EPI == EPI_SWIGLU);
   constexpr bool kResid = (EPI == EPI_RESID || EPI == EPI_BIAS_RESID);
   constexpr bool kBias = (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_BIAS_RESID);
+  constexpr bool kRope = (EPI == EPI_ROPE);
   constexpr int OUT_BN = kSwiGLU ? BN / 2 : BN;          // output columns per tile
   constexpr int CHUNK_COLS = kF32 ? 32 : 64;             // output columns per 128-byte staging row
   constexpr int NCHUNK = (OUT_BN + CHUNK_COLS - 1) / CHUNK_COLS;
@@ -262,6 +264,88 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const uint32_t t_tile = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
+      if constexpr (kRope) {
+        // QKV projection of a decoder: the tile is BN / D whole heads.  Group g takes heads g, g + 2, ...; a thread owns
+        // its token's row of the head and pairs column i with i + D/2 straight from TMEM: round to bf16 (what the row
+        // kernel read back), rotate by the step's cos/sin table, store to the qkv activation, and for k / v heads to the
+        // row's slot of the paged cache as well.  64-byte pieces per thread; the mainloop (K = hidden) hides them.
+        const int D = rope.D, half = D >> 1;
+        const int row_g = m0 + row;
+        const bool row_ok = row_g < M;
+        const float* cs = rope.cs + (size_t)(row_ok ? row_g : 0) * D;
+        const int slot = (row_ok && rope.slots) ? rope.slots[row_g] : -1;
+        const int page = slot >= 0 ? slot / rope.page_size : 0, off = slot >= 0 ? slot % rope.page_size : 0;
+        bf16* const orow = rope.out + (size_t)(row_ok ? row_g : 0) * rope.ldc;
+        for (int hl = grp; hl < BN / D; hl += 2) {
+          const int n_head0 = n_out0 + hl * D;
+          const int hidx = n_head0 / D;
+          const int kind = hidx < rope.Hq ? 0 : (hidx < rope.Hq + rope.Hkv ? 1 : 2);  // q / k / v
+          bf16* crow = nullptr;
+          if (kind != 0 && slot >= 0) {
+            const int kvh = hidx - rope.Hq - (kind == 2 ? rope.Hkv : 0);
+            crow = (kind == 1 ? rope.k_cache : rope.v_cache) + (((size_t)page * rope.Hkv + kvh) * rope.page_size + off) * D;
+          }
+          for (int hh = 0; hh < half / 32; ++hh) {
+            uint32_t v1[32], v2[32];
+            tmem_ld_32x32b_x32(t_tile + hl * D + hh * 32, v1);
+            tmem_ld_32x32b_x32(t_tile + hl * D + half + hh * 32, v2);
+            tmem_ld_wait();
+            float a[32], b[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { a[j] = __uint_as_float(v1[j]); b[j] = __uint_as_float(v2[j]); }
+            if (bias) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float ba[8], bb[8];
+                unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(bias + n_head0 + hh * 32) + j), ba);
+                unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(bias + n_head0 + half + hh * 32) + j), bb);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { a[8 * j + k] += ba[k]; b[8 * j + k] += bb[k]; }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              a[j] = __bfloat162float(__float2bfloat16(a[j]));
+              b[j] = __bfloat162float(__float2bfloat16(b[j]));
+            }
+            if (kind != 2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + hh * 32) + j);
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(cs + half + hh * 32) + j);
+                const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float x = a[4 * j + k], y = b[4 * j + k];
+                  a[4 * j + k] = rope_lo(x, y, cc[k], ss[k]);
+                  b[4 * j + k] = rope_hi(x, y, cc[k], ss[k]);
+                }
+              }
+            }
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 lo, hi;
+                lo.x = pack_bf16x2(a[8 * j + 0], a[8 * j + 1]); lo.y = pack_bf16x2(a[8 * j + 2], a[8 * j + 3]);
+                lo.z = pack_bf16x2(a[8 * j + 4], a[8 * j + 5]); lo.w = pack_bf16x2(a[8 * j + 6], a[8 * j + 7]);
+                hi.x = pack_bf16x2(b[8 * j + 0], b[8 * j + 1]); hi.y = pack_bf16x2(b[8 * j + 2], b[8 * j + 3]);
+                hi.z = pack_bf16x2(b[8 * j + 4], b[8 * j + 5]); hi.w = pack_bf16x2(b[8 * j + 6], b[8 * j + 7]);
+                reinterpret_cast<uint4*>(orow + n_head0 + hh * 32)[j] = lo;
+                reinterpret_cast<uint4*>(orow + n_head0 + half + hh * 32)[j] = hi;
+                if (crow) {
+                  reinterpret_cast<uint4*>(crow + hh * 32)[j] = lo;
+                  reinterpret_cast<uint4*>(crow + half + hh * 32)[j] = hi;
+                }
+              }
+            }
+          }
+        }
+        // this warp's TMEM reads of the accumulator stage are complete -> hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[as], 0); else mbar_arrive(&tmem_empty[as]); }
+        continue;
+      }
       int last_c = -1;
       for (int c = grp; c < NCHUNK; c += 2) last_c = c;
       if (last_c < 0) {  // this group has no chunk in such a narrow tile: release the accumulator right away
@@ -434,7 +518,7 @@ cudaError_t launch_cfg(cudaStream_t stream, const GemmArgs& g, int num_sms) {
   cfg.attrs = attr;
   cfg.numAttrs = (CG > 1) ? 1 : 0;
   static const int l2_hints = [] { const char* e = getenv("HB_GEMM_L2HINTS"); return e ? atoi(e) : 0; }();  // A/B knob
-  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mr, g.bias, g.M, g.N, g.K, grp, group_n | (l2_hints ? 2 : 0));
+  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mr, g.bias, g.M, g.N, g.K, grp, group_n | (l2_hints ? 2 : 0), g.rope);
 }
 
 bool use_pair() {  // HB_GEMM_2CTA=0 falls back to single-CTA tiles (A/B measurements)
@@ -457,10 +541,10 @@ cudaError_t launch_epi(cudaStream_t stream, const GemmArgs& g, int num_sms) {
       if (use_pair() && (long)((g.M + 255) / 256) * ((g.N + 255) / 256) >= num_sms / 2) return launch_cfg<256, EPI, 2>(stream, g, num_sms);
       return launch_cfg<256, EPI, 1>(stream, g, num_sms);
     case 128:
-      if constexpr (EPI != EPI_SWIGLU) return launch_cfg<128, EPI, 1>(stream, g, num_sms);
+      if constexpr (EPI != EPI_SWIGLU && EPI != EPI_ROPE) return launch_cfg<128, EPI, 1>(stream, g, num_sms);
       return cudaErrorInvalidValue;
     case 64:
-      if constexpr (EPI != EPI_SWIGLU) return launch_cfg<64, EPI, 1>(stream, g, num_sms);
+      if constexpr (EPI != EPI_SWIGLU && EPI != EPI_ROPE) return launch_cfg<64, EPI, 1>(stream, g, num_sms);
       return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
@@ -478,7 +562,7 @@ cudaError_t set_attr_epi() {
   cudaError_t e;
   if ((e = set_attr<256, EPI, 2>()) != cudaSuccess) return e;
   if ((e = set_attr<256, EPI, 1>()) != cudaSuccess) return e;
-  if constexpr (EPI != EPI_SWIGLU) {
+  if constexpr (EPI != EPI_SWIGLU && EPI != EPI_ROPE) {
     if ((e = set_attr<128, EPI, 1>()) != cudaSuccess) return e;
     return set_attr<64, EPI, 1>();
   }
@@ -494,6 +578,7 @@ cudaError_t gemm_init() {
   if ((e = set_attr_epi<EPI_RESID>()) != cudaSuccess) return e;
   if ((e = set_attr_epi<EPI_BIAS_RESID>()) != cudaSuccess) return e;
   if ((e = set_attr_epi<EPI_F32>()) != cudaSuccess) return e;
+  if ((e = set_attr_epi<EPI_ROPE>()) != cudaSuccess) return e;
   return set_attr_epi<EPI_SWIGLU>();
 }
 
@@ -528,6 +613,14 @@ cudaError_t gemm_bf16_tn(cudaStream_t stream, const GemmArgs& g) {
       return launch_epi<EPI_SWIGLU>(stream, h, sms);
     }
     case EPI_F32: return launch_epi<EPI_F32>(stream, g, sms);
+    case EPI_ROPE: {
+      const RopeEpi& r = g.rope;
+      if ((g.N % 256) || !r.out || !r.cs || (r.D != 64 && r.D != 128) || g.N != (r.Hq + 2 * r.Hkv) * r.D || (r.ldc % 8)) return cudaErrorInvalidValue;
+      if (r.slots && (!r.k_cache || !r.v_cache || r.page_size <= 0)) return cudaErrorInvalidValue;
+      GemmArgs h = g;
+      h.block_n = 256;
+      return launch_epi<EPI_ROPE>(stream, h, sms);
+    }
   }
   return cudaErrorInvalidValue;
 }

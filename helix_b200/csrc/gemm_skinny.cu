@@ -159,7 +159,7 @@ __device__ __noinline__ void finish_tile(const SkinnyEpi& epi, const uint8_t* __
         if (rot) {
           float sn, cs;
           sincosf((float)epi.positions[m] * freq, &sn, &cs);
-          const bf16 lo = __float2bfloat16(a * cs - b * sn), hi = __float2bfloat16(b * cs + a * sn);
+          const bf16 lo = __float2bfloat16(rope_lo(a, b, cs, sn)), hi = __float2bfloat16(rope_hi(a, b, cs, sn));
           if (head < epi.Hq) {
             bf16* qrow = epi.qkv_out + (size_t)m * N + (size_t)head * D;
             qrow[j] = lo;

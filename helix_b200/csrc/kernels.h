@@ -26,6 +26,19 @@ enum Epi : int {
   EPI_SWIGLU = 5,      // W rows packed per 256-row tile as [128 gate | 128 up];
                        // C[m, tile*128+j] = silu(gate_j) * up_j   (bf16, ldc counts N/2 columns)
   EPI_F32 = 6,         // C = acc                              (fp32)
+  EPI_ROPE = 7,        // fused QKV projection of a decoder: C = bf16(acc [+ bias]) with the q and k heads rotated
+                       // (RopeEpi) and the k / v rows also scattered into the paged KV cache
+};
+
+// What EPI_ROPE needs beyond the GEMM itself (the job of rope_kv_write, done on the accumulators' way out).
+struct RopeEpi {
+  bf16* out = nullptr;             // == GemmArgs::C, written with plain stores (row stride ldc elements)
+  int ldc = 0;
+  const float* cs = nullptr;       // [M][D]: cos(pos*inv_freq[i]) for i < D/2, then sin (rope_table)
+  const int32_t* slots = nullptr;  // slot_mapping as in rope_kv_write; null or < 0: no cache write for the row
+  bf16* k_cache = nullptr;
+  bf16* v_cache = nullptr;
+  int Hq = 0, Hkv = 0, D = 0, page_size = 0;
 };
 
 struct GemmArgs {
@@ -41,6 +54,7 @@ struct GemmArgs {
   int M, N, K;
   Epi epi;
   int block_n;  // 0 = choose
+  RopeEpi rope{};  // EPI_ROPE only
 };
 cudaError_t gemm_bf16_tn(cudaStream_t stream, const GemmArgs& a);
 // Debug/test-only CUDA-core GEMM (same contract, EPI_NONE/EPI_F32 only); used by tests as an on-device checker.
@@ -67,6 +81,9 @@ cudaError_t layernorm(cudaStream_t s, const bf16* x, const bf16* gamma, const bf
 cudaError_t rope_kv_write(cudaStream_t s, bf16* qkv, const int32_t* positions, const int32_t* slot_mapping,
                           const float* inv_freq, bf16* k_cache, bf16* v_cache, int T, int Hq, int Hkv, int D,
                           int page_size);
+// cs[t][0..D/2) = cos(positions[t] * inv_freq[i]), cs[t][D/2..D) = sin(...): the table EPI_ROPE reads (once per step,
+// shared by every layer).
+cudaError_t rope_table(cudaStream_t s, const int32_t* positions, const float* inv_freq, float* cs, int T, int D);
 // Greedy / Gumbel-max sampling over fp32 logits[B,V]: out[b] = argmax_v(logits[b,v]/temp[b] + g(seed[b],v)),
 // temp[b] <= 0 -> pure argmax (lowest index wins ties).
 cudaError_t sample_tokens(cudaStream_t s, const float* logits, int ldl, const float* temperature, const uint64_t* seed,

@@ -401,4 +401,14 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+__device__ __forceinline__ void unpack_bf16x8(uint4 u, float (&f)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// RoPE pair (lo, hi) = (x[i], x[i + D/2]) rotated by (c, s); explicit fma / mul so that the row kernel and the GEMM
+// epilogue round identically whatever the compiler would contract.
+__device__ __forceinline__ float rope_lo(float a, float b, float c, float s) { return __fmaf_rn(a, c, -__fmul_rn(b, s)); }
+__device__ __forceinline__ float rope_hi(float a, float b, float c, float s) { return __fmaf_rn(b, c, __fmul_rn(a, s)); }
+
 }  // namespace hb

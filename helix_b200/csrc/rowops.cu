@@ -4,6 +4,7 @@
 
 #include "kernels.h"
 #include "launch.h"
+#include "ptx.cuh"
 
 namespace hb {
 namespace {
@@ -225,6 +226,18 @@ layernorm_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma
   }
 }
 
+__global__ void rope_table_kernel(const int32_t* __restrict__ positions, const float* __restrict__ inv_freq,
+                                  float* __restrict__ cs, int T, int D) {
+  const int half = D / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * half) return;
+  const int t = i / half, k = i % half;
+  float s, c;
+  sincosf((float)positions[t] * inv_freq[k], &s, &c);
+  cs[(size_t)t * D + k] = c;
+  cs[(size_t)t * D + half + k] = s;
+}
+
 // One block per token. Pairs (i, i+D/2) of each q/k head are rotated; k,v rows go to the paged cache.
 __global__ void __launch_bounds__(256)
 rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positions,
@@ -252,8 +265,8 @@ rope_kv_write_kernel(bf16* __restrict__ qkv, const int32_t* __restrict__ positio
     __nv_bfloat162* hi = reinterpret_cast<__nv_bfloat162*>(row + h * D + half + j);
     const float2 a = __bfloat1622float2(*lo), b = __bfloat1622float2(*hi);
     const float c0 = cs[j], c1 = cs[j + 1], s0 = cs[half + j], s1 = cs[half + j + 1];
-    *lo = __floats2bfloat162_rn(a.x * c0 - b.x * s0, a.y * c1 - b.y * s1);
-    *hi = __floats2bfloat162_rn(b.x * c0 + a.x * s0, b.y * c1 + a.y * s1);
+    *lo = __floats2bfloat162_rn(rope_lo(a.x, b.x, c0, s0), rope_lo(a.y, b.y, c1, s1));
+    *hi = __floats2bfloat162_rn(rope_hi(a.x, b.x, c0, s0), rope_hi(a.y, b.y, c1, s1));
   }
   const int slot = slot_mapping ? slot_mapping[t] : -1;
   if (slot < 0) return;
@@ -591,6 +604,13 @@ cudaError_t bert_embed_ln(cudaStream_t s, const int32_t* tokens, const int32_t* 
     layernorm_kernel<true><<<T, kRowThreads, 0, s>>>(nullptr, gamma, beta, x, H, eps, tokens, positions, word, pos, type0);
   return cudaGetLastError();
 }
+cudaError_t rope_table(cudaStream_t s, const int32_t* positions, const float* inv_freq, float* cs, int T, int D) {
+  if (T <= 0) return cudaSuccess;
+  const int n = T * (D / 2);
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, s>>>(positions, inv_freq, cs, T, D);
+  return cudaGetLastError();
+}
+
 cudaError_t rope_kv_write(cudaStream_t s, bf16* qkv, const int32_t* positions, const int32_t* slot_mapping,
                           const float* inv_freq, bf16* k_cache, bf16* v_cache, int T, int Hq, int Hkv, int D,
                           int page_size) {

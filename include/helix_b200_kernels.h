@@ -34,6 +34,11 @@ int hbk_rmsnorm(const void* x, const void* w, void* out, const int32_t* row_inde
 int hbk_layernorm(const void* x, const void* gamma, const void* beta, void* out, int rows, int H, float eps);
 int hbk_rope_kv_write(void* qkv, const int32_t* positions, const int32_t* slot_mapping, const float* inv_freq,
                       void* k_cache, void* v_cache, int T, int Hq, int Hkv, int D, int page_size);
+/* QKV projection with RoPE + KV scatter in the GEMM epilogue (EPI_ROPE): qkv[T, (Hq+2Hkv)*D] = A[T,K] * W^T (+ bias), q / k heads
+   rotated, k / v rows also written to the paged cache — must equal hbk_gemm followed by hbk_rope_kv_write bit for bit */
+int hbk_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, void* qkv, const void* bias, const int32_t* positions,
+                      const int32_t* slot_mapping, const float* inv_freq, void* k_cache, void* v_cache, int T, int K,
+                      int Hq, int Hkv, int D, int page_size);
 int hbk_sample(const float* logits, int ldl, const float* temperature, const uint64_t* seed, int32_t* out, int B, int V);
 /* as hbk_sample, restricted per row to the top_k / top_p survivors (either pointer may be NULL) */
 int hbk_sample_filtered(const float* logits, int ldl, const float* temperature, const uint64_t* seed, const int32_t* top_k,

@@ -162,6 +162,35 @@ def test_rope_and_kv_scatter(L, D, Hq, Hkv):
     assert kc.float().abs().sum(dim=(1, 3)).view(-1).count_nonzero() == T - 1
 
 
+@pytest.mark.parametrize("D,Hq,Hkv,T,K,with_bias", [(128, 32, 8, 1100, 512, False), (128, 12, 2, 300, 256, True),
+                                                      (64, 32, 8, 260, 256, False), (64, 4, 2, 37, 128, True)])
+def test_qkv_gemm_rope_epilogue_equals_gemm_then_row_kernel(L, D, Hq, Hkv, T, K, with_bias):
+    """EPI_ROPE (RoPE + KV scatter on the accumulators' way out of the QKV projection) against the two-kernel path it
+    replaces: same GEMM, same bf16 rounding before the rotation, same cos/sin — the activation and both cache planes
+    must be identical bit for bit (CTA-pair and single-CTA tiles, ragged last row tile, skipped slots)."""
+    N, page, npages = (Hq + 2 * Hkv) * D, 64, 20
+    A, W = rnd(T, K, seed=31, scale=0.5), rnd(N, K, seed=32, scale=0.5)
+    bias = rnd(N, seed=33) if with_bias else None
+    pos = torch.randint(0, 5000, (T,), device="cuda", dtype=torch.int32)
+    slots = torch.randperm(npages * page, device="cuda")[:T].to(torch.int32)
+    slots[T // 2] = -1
+    inv = (1.0 / (500000.0 ** (torch.arange(0, D, 2, device="cuda").float() / D))).contiguous()
+    ref = torch.empty(T, N, device="cuda", dtype=BF)
+    ck(L, L.hbk_gemm(p(A), K, p(W), K, p(ref), N, None, 0, p(bias) if with_bias else None, T, N, K, 1 if with_bias else 0, 0))
+    kc_ref = torch.zeros(npages, Hkv, page, D, device="cuda", dtype=BF)
+    vc_ref = torch.zeros_like(kc_ref)
+    ck(L, L.hbk_rope_kv_write(p(ref), p(pos), p(slots), p(inv), p(kc_ref), p(vc_ref), T, Hq, Hkv, D, page))
+    got = torch.full((T, N), 7.0, device="cuda", dtype=BF)
+    kc, vc = torch.zeros_like(kc_ref), torch.zeros_like(kc_ref)
+    ck(L, L.hbk_gemm_qkv_rope(p(A), K, p(W), K, p(got), p(bias) if with_bias else None, p(pos), p(slots), p(inv), p(kc), p(vc),
+                              T, K, Hq, Hkv, D, page))
+    bad = (got != ref).nonzero()
+    assert bad.numel() == 0, (f"{bad.shape[0]} mismatches, first {bad[:4].tolist()}, cols%D {sorted(set((bad[:, 1] % D).tolist()))[:16]}, "
+                              f"heads {sorted(set((bad[:, 1] // D).tolist()))[:16]}, max diff {(got.float() - ref.float()).abs().max().item()}")
+    assert torch.equal(kc, kc_ref) and torch.equal(vc, vc_ref)
+    assert ref.float().abs().max() > 1.0  # not a vacuous comparison
+
+
 def test_sampling_argmax_and_gumbel(L):
     B, V = 7, 128256
     logits = torch.randn(B, V, device="cuda")
