@@ -115,20 +115,34 @@ class EmbedBatcher:
 
 class StreamDecoder:
     """Token ids -> text for streaming: the visible text must not depend on how the tokens were grouped into polls.
-    Decoding each poll's ids on its own garbles any character whose bytes / pieces straddle two polls, so the whole
-    sequence is decoded and only the new, stable suffix is released; a trailing U+FFFD (an incomplete multi-byte
-    sequence so far) is held back until the next tokens complete it or the stream ends."""
+    Decoding each poll's ids on its own garbles any character whose bytes / pieces straddle two polls; decoding the whole
+    sequence at every poll is quadratic in the length of the generation.  So (the scheme vLLM's detokenizer uses) the
+    tokens not yet shown are decoded together with the previously shown batch as left context, the context's own text is
+    cut off the front, and nothing is released while the tail is an incomplete multi-byte sequence (a trailing U+FFFD)
+    unless the stream has ended."""
 
     def __init__(self, tok, skip=()):
-        self.tok, self.skip, self.ids, self.emitted = tok, set(skip), [], 0
+        self.tok, self.skip, self.ids = tok, set(skip), []
+        self.ctx_off = 0    # first token of the left context
+        self.read_off = 0   # tokens before this index have been shown
 
     def feed(self, ids, final=False):
         self.ids += [t for t in ids if t not in self.skip]
-        text = self.tok.decode(self.ids)
-        stable = len(text) if final or not text.endswith("\ufffd") else len(text) - 1
-        out = text[self.emitted:stable]
-        self.emitted = max(self.emitted, stable)
-        return out
+        n = len(self.ids)
+        if self.read_off == n:
+            return ""
+        ctx_text = self.tok.decode(self.ids[self.ctx_off:self.read_off])
+        # an unfinished character is at most its last three tokens: release up to the latest clean cut
+        for hold in range(0, 1 if final else min(4, n - self.read_off)):
+            text = self.tok.decode(self.ids[self.ctx_off:n - hold])
+            if final or (not text.endswith("\ufffd") and len(text) > len(ctx_text)):
+                self.ctx_off, self.read_off = self.read_off, n - hold
+                return text[len(ctx_text):]
+        if n - self.read_off > 8:  # not an unfinished character but invalid bytes: nothing later will repair them
+            text = self.tok.decode(self.ids[self.ctx_off:])
+            self.ctx_off, self.read_off = self.read_off, n
+            return text[len(ctx_text):]
+        return ""
 
 
 class StopMatcher:
@@ -452,7 +466,13 @@ class OpenAIServer:
                 finally:
                     srv._leave()
 
-        self.httpd = ThreadingHTTPServer((self.host, self.port), H)
+        class Server(ThreadingHTTPServer):
+            # the slot's default concurrency is 256 streams (--max-num-seqs): with socketserver's backlog of 5 a burst of
+            # connections is reset by the kernel before accept() gets to them
+            request_queue_size = 1024
+            daemon_threads = True
+
+        self.httpd = Server((self.host, self.port), H)
         self.httpd.daemon_threads = True
         self.port = self.httpd.server_address[1]
         threading.Thread(target=self.httpd.serve_forever, daemon=True).start()

@@ -222,6 +222,56 @@ def test_stream_decoder_and_stop_matcher_properties():
     prop()
 
 
+def test_streaming_decode_of_arbitrary_bytes_matches_whole_decode():
+    """A random-init model emits invalid UTF-8 all the time: the incremental decoder must still show exactly what decoding
+    the whole sequence shows, whatever the grouping (and must not hold text back forever behind an invalid byte)."""
+    import random
+    from helix_b200.server import StreamDecoder
+    tok, rnd = ByteTokenizer(), random.Random(7)
+    for trial in range(600):
+        ids = [rnd.randrange(256) + ByteTokenizer.OFFSET for _ in range(rnd.randrange(0, 80))]
+        dec, out, i, held = StreamDecoder(tok), "", 0, 0
+        while i < len(ids):
+            k = rnd.randrange(1, 7)
+            i += k
+            piece = dec.feed(ids[i - k:i], final=i >= len(ids))
+            held = 0 if piece else held + k
+            assert held <= 16   # bounded hold-back
+            out += piece
+        assert out == tok.decode(ids)
+
+
+def test_burst_of_concurrent_streams_is_accepted(front):
+    """--max-num-seqs 256 means up to 256 streams connect at once: none may be reset by a short listen backlog."""
+    import http.client
+    import threading
+    from urllib.parse import urlparse
+    rt, base = front
+    u = urlparse(base)
+    go, res = threading.Event(), []
+
+    def one():
+        go.wait()
+        try:
+            c = http.client.HTTPConnection(u.hostname, u.port, timeout=60)
+            c.request("POST", "/v1/chat/completions", json.dumps({"model": "tiny", "stream": True, "max_tokens": 3,
+                                                                    "messages": [{"role": "user", "content": "hi"}]}),
+                      {"Content-Type": "application/json"})
+            r = c.getresponse()
+            body = r.read().decode()
+            res.append((r.status, body.rstrip().endswith("data: [DONE]")))
+        except OSError as e:
+            res.append((repr(e), False))
+
+    ths = [threading.Thread(target=one) for _ in range(256)]
+    for t in ths:
+        t.start()
+    go.set()
+    for t in ths:
+        t.join()
+    assert len(res) == 256 and all(r == (200, True) for r in res), [r for r in res if r != (200, True)][:3]
+
+
 def test_n_choices_logprobs_and_penalties_reach_the_engine(front):
     """Request fields the runner forwards untouched (openai_chat_handlers.go:100-175): n, logprobs/top_logprobs,
     presence/frequency penalties — one engine submission per choice with its own seed, OpenAI-shaped logprobs back."""
