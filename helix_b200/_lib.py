@@ -82,6 +82,7 @@ SIGNATURES = {
     "hb_replica_unique_id": (I, [P]),
     "hb_model_load_broadcast": (I, [P, C.POINTER(ModelDescC), P, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
     "hb_embed": (I, [P, P, P, C.c_int32, P]),
+    "hb_json_f32_array": (C.c_size_t, [P, C.c_size_t, P, C.c_size_t]),
     "hb_tok_load": (I, [C.c_char_p, C.POINTER(P)]),
     "hb_tok_free": (None, [P]),
     "hb_tok_vocab_size": (C.c_int32, [P]),

@@ -1,4 +1,5 @@
 // C ABI (include/helix_b200.h, include/helix_b200_kernels.h) over hb::Engine and the kernel launchers.
+#include <charconv>
 #include <string.h>
 
 #include <string>
@@ -194,6 +195,28 @@ int hbk_rope_kv_write(void* qkv, const int32_t* positions, const int32_t* slot_m
   return kret(hb::rope_kv_write(0, (hb::bf16*)qkv, positions, slot_mapping, inv_freq, (hb::bf16*)k_cache,
                                 (hb::bf16*)v_cache, T, Hq, Hkv, D, page_size));
 }
+size_t hb_json_f32_array(const float* v, size_t n, char* out, size_t cap) {
+  size_t len = 0;
+  auto put = [&](const char* p, size_t k) {
+    if (out && len + k <= cap) memcpy(out + len, p, k);
+    len += k;
+  };
+  put("[", 1);
+  char buf[32];
+  for (size_t i = 0; i < n; ++i) {
+    if (i) put(",", 1);
+    const float x = v[i];
+    if (!(x - x == 0.0f)) {  // NaN / inf have no JSON spelling
+      put("null", 4);
+      continue;
+    }
+    const auto r = std::to_chars(buf, buf + sizeof buf, x);  // shortest round-trip text
+    put(buf, (size_t)(r.ptr - buf));
+  }
+  put("]", 1);
+  return len;
+}
+
 int hbk_gemm_qkv_rope(const void* A, int lda, const void* W, int ldw, void* qkv, const void* bias, const int32_t* positions,
                       const int32_t* slot_mapping, const float* inv_freq, void* k_cache, void* v_cache, int T, int K,
                       int Hq, int Hkv, int D, int page_size) {

@@ -12,6 +12,8 @@ import time
 import uuid
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 
+import numpy as np
+
 from .engine import HBError, Sampling
 
 
@@ -50,6 +52,29 @@ class HFTokenizer:
         return self.encode(s + "<|start_header_id|>assistant<|end_header_id|>\n\n")
 
 
+_F32_JSON = []
+
+
+def native_f32_json():
+    """float32 vector -> JSON array bytes through libhelixb200.so (hb_json_f32_array), or None without the library."""
+    if not _F32_JSON:
+        try:
+            import ctypes
+            from . import _lib
+            L = _lib.lib()
+
+            def fmt(v):
+                v = np.ascontiguousarray(v, dtype=np.float32)
+                cap = 16 * v.size + 2           # a float32 never needs more than 15 characters + comma
+                buf = ctypes.create_string_buffer(cap)
+                n = L.hb_json_f32_array(v.ctypes.data, v.size, buf, cap)
+                return buf.raw[:n]
+            _F32_JSON.append(fmt)
+        except Exception:  # noqa: BLE001 — the front also runs against stand-in engines without the shared library
+            _F32_JSON.append(None)
+    return _F32_JSON[0]
+
+
 class EmbedBatcher:
     """Server-side coalescing of embedding requests (scope row F4).  The reference's RAG caller sends ONE chunk per
     request with 10 concurrent workers (api/pkg/rag/rag_pgvector.go:70-83) in batches of 50
@@ -62,6 +87,7 @@ class EmbedBatcher:
         self.pending = []   # [seqs, event, result slot]
         self.stop_flag = False
         self.batches = 0
+        self.expect = 1     # requests the next batch waits for (at most window_s): the size of the previous one
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
@@ -82,13 +108,17 @@ class EmbedBatcher:
                     self.cv.wait()
                 if self.stop_flag and not self.pending:
                     return
+                # wait for company, but not longer than it takes: the callers are a fixed pool of workers that each send
+                # their next chunk as soon as the previous answer arrives, so once as many requests are waiting as the
+                # last batch held, nobody else is about to show up
                 deadline = time.monotonic() + self.window_s
-                while sum(len(i["seqs"]) for i in self.pending) < self.max_seqs:
+                while sum(len(i["seqs"]) for i in self.pending) < self.max_seqs and len(self.pending) < self.expect:
                     left = deadline - time.monotonic()
                     if left <= 0:
                         break
                     self.cv.wait(left)
                 batch, self.pending = self.pending, []
+                self.expect = max(1, len(batch))
             flat = [s for i in batch for s in i["seqs"]]
             try:
                 vecs = self.engine.embed(flat)
@@ -214,7 +244,7 @@ class OpenAIServer:
     def models(self):
         return {"object": "list", "data": [{"id": m, "object": "model", "owned_by": "helix-b200"} for m in self.rt.list_models()]}
 
-    def embeddings(self, body):
+    def _embed_vectors(self, body):
         inp = body.get("input")
         enc = getattr(self.tok, "encode_for_embedding", self.tok.encode)  # [CLS] ... [SEP] framing where the model has one
         if isinstance(inp, str):
@@ -225,16 +255,44 @@ class OpenAIServer:
             seqs = [enc(x) if isinstance(x, str) else list(x) for x in inp]
         else:
             raise ValueError("input must be a string, a list of strings or token arrays")
-        vocab = self.rt.engine.desc.vocab
-        if any(not isinstance(t, int) or isinstance(t, bool) or t < 0 or t >= vocab for s in seqs for t in s):
-            raise ValueError(f"input holds token ids outside [0, {vocab})")
-        seqs = [list(s)[: self.rt.engine.cfg.max_ctx] for s in seqs]
+        vocab, max_ctx = self.rt.engine.desc.vocab, self.rt.engine.cfg.max_ctx
+        for k, s in enumerate(seqs):   # C-level checks: this runs per chunk at the indexer's request rate
+            if not isinstance(s, list) or (s and (set(map(type, s)) != {int} or min(s) < 0 or max(s) >= vocab)):
+                raise ValueError(f"input holds token ids outside [0, {vocab})")
+            if len(s) > max_ctx:
+                seqs[k] = s[:max_ctx]
         if self.batcher is None:
             self.batcher = EmbedBatcher(self.rt.engine)
-        vecs = self.batcher.embed(seqs)
+        return self.batcher.embed(seqs), sum(map(len, seqs))
+
+    def embeddings(self, body):
+        vecs, n_tok = self._embed_vectors(body)
         return {"object": "list", "model": body.get("model", self.rt.p.model),
-                "data": [{"object": "embedding", "index": i, "embedding": [float(x) for x in v]} for i, v in enumerate(vecs)],
-                "usage": {"prompt_tokens": sum(map(len, seqs)), "total_tokens": sum(map(len, seqs))}}
+                "data": [{"object": "embedding", "index": i, "embedding": v.tolist() if hasattr(v, "tolist") else [float(x) for x in v]}
+                         for i, v in enumerate(vecs)],
+                "usage": {"prompt_tokens": n_tok, "total_tokens": n_tok}}
+
+    def embeddings_bytes(self, body):
+        """The /v1/embeddings response as bytes.  Turning 768 floats into JSON text costs CPython ~0.35 ms per vector —
+        more than the GPU needs to compute it — so the vectors are written by the library (hb_json_f32_array: shortest
+        round-trip decimal per float32, what Go's encoding/json emits) and only the envelope is built here."""
+        vecs, n_tok = self._embed_vectors(body)
+        fmt = native_f32_json()
+        if fmt is None or not hasattr(vecs, "dtype"):
+            return json.dumps(self.embeddings_from(vecs, n_tok, body)).encode()
+        parts = [b'{"object":"list","model":', json.dumps(body.get("model", self.rt.p.model)).encode(), b',"data":[']
+        for i, v in enumerate(vecs):
+            parts.append((b"," if i else b"") + b'{"object":"embedding","index":%d,"embedding":' % i)
+            parts.append(fmt(v))
+            parts.append(b"}")
+        parts.append(b'],"usage":{"prompt_tokens":%d,"total_tokens":%d}}' % (n_tok, n_tok))
+        return b"".join(parts)
+
+    def embeddings_from(self, vecs, n_tok, body):
+        return {"object": "list", "model": body.get("model", self.rt.p.model),
+                "data": [{"object": "embedding", "index": i, "embedding": v.tolist() if hasattr(v, "tolist") else [float(x) for x in v]}
+                         for i, v in enumerate(vecs)],
+                "usage": {"prompt_tokens": n_tok, "total_tokens": n_tok}}
 
     def _parse_chat(self, body):
         """Validates the request and returns (prompt ids, [Sampling per choice]).  Raises ValueError -> HTTP 400."""
@@ -395,17 +453,23 @@ class OpenAIServer:
 
         class H(BaseHTTPRequestHandler):
             protocol_version = "HTTP/1.1"
+            # headers and body (or one SSE event after another) are separate small sends: with Nagle on, the second one
+            # waits for the client's delayed ACK of the first — 40 ms per response / per token on Linux
+            disable_nagle_algorithm = True
 
             def log_message(self, *a):
                 pass
 
-            def _json(self, code, obj):
-                data = json.dumps(obj).encode()
+            def _json(self, code, obj, raw=None):
+                data = raw if raw is not None else json.dumps(obj).encode()
                 self.send_response(code)
                 self.send_header("Content-Type", "application/json")
                 self.send_header("Content-Length", str(len(data)))
-                self.end_headers()
-                self.wfile.write(data)
+                # one send for headers + body (end_headers() would flush the header block on its own)
+                self._headers_buffer.append(b"\r\n")
+                head = b"".join(self._headers_buffer)
+                self._headers_buffer = []
+                self.wfile.write(head + data)
 
             def do_GET(self):
                 if self.path.rstrip("/") in ("/v1/models", "/models"):
@@ -427,7 +491,7 @@ class OpenAIServer:
                         raise ValueError("request body must be a JSON object")
                     path = self.path.rstrip("/")
                     if path.endswith("/embeddings"):
-                        return self._json(200, srv.embeddings(body))
+                        return self._json(200, None, raw=srv.embeddings_bytes(body))
                     if path.endswith("/chat/completions") or path.endswith("/completions"):
                         if not body.get("stream"):
                             return self._json(200, srv.chat(body))

@@ -255,6 +255,14 @@ int hb_tok_decode(hb_tokenizer* t, const int32_t* ids, int32_t n_ids, int32_t sk
 int hb_tok_chat_llama3(hb_tokenizer* t, const char* const* roles, const char* const* contents, int32_t n_msgs, int32_t* out,
                        int32_t cap, int32_t* n);
 
+/* ---- response encoding (scope row F1 / a5): the embedding route answers with every vector as JSON decimal text
+ *      (`data[i].embedding []float32`, api/pkg/runner/openai_embedding_handlers.go:110-772) and that encoding is where a
+ *      scripting-language front spends its time (0.35 ms per 768-wide vector in CPython).  Writes `[v0,v1,...]` with the
+ *      shortest text that parses back to the same float (what Go's encoding/json emits for float32); non-finite values
+ *      become null.  Returns the number of bytes the array needs (no terminator); nothing is written beyond `cap`, so
+ *      a return value > cap means "call again with a larger buffer".  Host-only: needs no GPU and no engine. ---- */
+size_t hb_json_f32_array(const float* v, size_t n, char* out, size_t cap);
+
 int hb_get_stats(hb_engine* e, hb_stats* out);
 /* event-timed spans around every launch (measurement aid; disables CUDA-graph replay while on) */
 int hb_set_profile(hb_engine* e, int32_t on);
