@@ -32,6 +32,7 @@ def client_proc(url, n_threads, prompt_len, decode, vocab, seed0, start_evt, q):
         c.request("POST", "/v1/completions", body, {"Content-Type": "application/json"})
         r = c.getresponse()
         chunks, toks, ttft = 0, 0, None
+        gaps, t_prev = [], None
         buf = b""
         while True:
             d = r.read1(65536)
@@ -43,11 +44,15 @@ def client_proc(url, n_threads, prompt_len, decode, vocab, seed0, start_evt, q):
                 if not line.startswith(b"data: ") or line == b"data: [DONE]":
                     continue
                 chunks += 1
+                now = time.monotonic()
+                if chunks > 2:
+                    gaps.append(now - t_prev)      # time between content chunks as the client sees them
+                t_prev = now
                 if ttft is None and chunks == 2:   # the first chunk is the empty role delta
-                    ttft = time.monotonic() - t0
+                    ttft = now - t0
                 if b'"usage"' in line:
                     toks = json.loads(line[6:]).get("usage", {}).get("completion_tokens", 0)
-        res.append((r.status, chunks, toks, ttft or 0.0, time.monotonic() - t0))
+        res.append((r.status, chunks, toks, ttft or 0.0, time.monotonic() - t0, gaps))
 
     start_evt.wait()
     ths = [threading.Thread(target=one, args=(i,)) for i in range(n_threads)]
@@ -92,6 +97,7 @@ def main():
         chunks = sum(r[1] for r in ok)
         gpu_ms = (s1["gpu_ms_prefill"] + s1["gpu_ms_decode"]) - (s0["gpu_ms_prefill"] + s0["gpu_ms_decode"])
         ttfts = sorted(r[3] for r in ok)
+        gaps = sorted(g for r in ok for g in r[5])
         print(json.dumps({
             "what": "completion tokens/s through the Python OpenAI front (server.py), stream:true", "model": a.model,
             "streams": a.streams, "client_processes": a.procs, "prompt_tokens": a.prompt, "decode_tokens": a.decode,
@@ -100,6 +106,8 @@ def main():
             "sse_chunks_per_s": round(chunks / wall, 1), "tokens_per_chunk": round(toks / max(chunks, 1), 2),
             "engine_busy_fraction": round(gpu_ms / 1e3 / wall, 3),
             "engine_device_tokens_per_s": round((toks + len(ok) * a.prompt) / (gpu_ms / 1e3), 1) if gpu_ms else None,
+            "chunk_gap_ms_p50": round(gaps[len(gaps) // 2] * 1e3, 2) if gaps else None,
+            "chunk_gap_ms_p99": round(gaps[int(len(gaps) * 0.99)] * 1e3, 2) if gaps else None,
             "ttft_s_p50": round(ttfts[len(ttfts) // 2], 3) if ttfts else None, "ttft_s_max": round(ttfts[-1], 3) if ttfts else None,
             "decode_steps": s1["steps_decode"] - s0["steps_decode"], "mixed_steps": s1["steps_mixed"] - s0["steps_mixed"]}))
     finally:
