@@ -330,6 +330,36 @@ def test_burst_of_concurrent_streams_is_accepted(front):
     assert len(res) == 256 and all(r == (200, True) for r in res), [r for r in res if r != (200, True)][:3]
 
 
+def test_client_disconnect_mid_stream_cancels_and_releases_the_request(front):
+    """The reference's backends stop generating when the HTTP client goes away; here the sequence holds KV pages until
+    it is cancelled, so a dropped stream must end in hb_cancel + hb_release, not in a generation nobody reads."""
+    import socket
+    import time
+    from urllib.parse import urlparse
+    rt, base = front
+    eng = rt.engine
+    eng.script = [(b % 26) + 97 + ByteTokenizer.OFFSET for b in range(200000)]   # an answer that never ends on its own
+    slow_wait = eng.wait
+    eng.wait = lambda rid, ms: (time.sleep(0.005), slow_wait(rid, ms))[1]        # ~200 polls per second
+    u = urlparse(base)
+    s = socket.create_connection((u.hostname, u.port))
+    body = json.dumps({"model": "tiny", "stream": True, "max_tokens": 100000, "messages": [{"role": "user", "content": "go"}]}).encode()
+    s.sendall(b"POST /v1/chat/completions HTTP/1.1\r\nHost: x\r\nContent-Type: application/json\r\nContent-Length: %d\r\n\r\n" % len(body) + body)
+    got = b""
+    while got.count(b"data: ") < 5:
+        got += s.recv(65536)
+    assert b"200 OK" in got and not eng.cancelled
+    s.setsockopt(socket.SOL_SOCKET, socket.SO_LINGER, b"\x01\x00\x00\x00\x00\x00\x00\x00")   # RST on close
+    s.close()
+    deadline = time.monotonic() + 5
+    while time.monotonic() < deadline and not eng.released:
+        time.sleep(0.02)
+    assert eng.cancelled == [1] and eng.released == [1]
+    pos = eng.reqs[1]["pos"]
+    time.sleep(0.1)
+    assert eng.reqs[1]["pos"] == pos          # nobody polls the cancelled request any more
+
+
 def test_n_choices_logprobs_and_penalties_reach_the_engine(front):
     """Request fields the runner forwards untouched (openai_chat_handlers.go:100-175): n, logprobs/top_logprobs,
     presence/frequency penalties — one engine submission per choice with its own seed, OpenAI-shaped logprobs back."""
