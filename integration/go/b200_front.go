@@ -30,10 +30,122 @@ type Tokenizer interface {
 }
 
 type openAIFront struct {
-	rt  *B200Runtime
-	tok Tokenizer
-	ln  net.Listener
-	srv *http.Server
+	rt    *B200Runtime
+	tok   Tokenizer
+	ln    net.Listener
+	srv   *http.Server
+	embed *embedBatcher
+}
+
+// embedBatcher coalesces concurrent embedding requests into few hb_embed calls (scope row F4).  The reference's indexer
+// keeps a fixed pool of workers that each send ONE chunk per request and the next one when the answer arrives
+// (rag/rag_pgvector.go:70-83): encoding them one by one leaves the GPU idle.  A batch takes everything that is queued,
+// then waits — embedWindow at most — until as many requests are in as the previous batch held: once the whole pool has
+// reported in, nobody else is about to show up.  Mirrors helix_b200/server.py EmbedBatcher (measured there: 10 workers,
+// 512-token chunks: 2.2k chunks/s at 4.3 ms per request; one worker alone 1.2 ms).
+type embedBatcher struct {
+	rt   *B200Runtime
+	jobs chan *embedJob
+	quit chan struct{}
+}
+
+type embedJob struct {
+	seqs [][]int32
+	done chan embedResult
+}
+
+type embedResult struct {
+	vecs [][]float32
+	err  error
+}
+
+const (
+	embedWindow  = 2 * time.Millisecond
+	embedMaxSeqs = 256
+)
+
+func newEmbedBatcher(rt *B200Runtime) *embedBatcher {
+	b := &embedBatcher{rt: rt, jobs: make(chan *embedJob, 4096), quit: make(chan struct{})}
+	go b.run()
+	return b
+}
+
+func (b *embedBatcher) Embed(seqs [][]int32) ([][]float32, error) {
+	j := &embedJob{seqs: seqs, done: make(chan embedResult, 1)}
+	select {
+	case b.jobs <- j:
+	case <-b.quit:
+		return nil, errors.New("helix-b200: runtime stopped")
+	}
+	select {
+	case r := <-j.done:
+		return r.vecs, r.err
+	case <-b.quit:
+		return nil, errors.New("helix-b200: runtime stopped")
+	}
+}
+
+func (b *embedBatcher) Close() { close(b.quit) }
+
+func (b *embedBatcher) run() {
+	expect := 1 // requests the next batch waits for: the size of the previous one
+	for {
+		var batch []*embedJob
+		select {
+		case j := <-b.jobs:
+			batch = append(batch, j)
+		case <-b.quit:
+			return
+		}
+		nseq := len(batch[0].seqs)
+		timer := time.NewTimer(embedWindow)
+	collect:
+		for nseq < embedMaxSeqs {
+			if len(batch) < expect {
+				select { // wait for company, but not past the window
+				case j := <-b.jobs:
+					batch = append(batch, j)
+					nseq += len(j.seqs)
+				case <-timer.C:
+					break collect
+				case <-b.quit:
+					timer.Stop()
+					return
+				}
+			} else {
+				select { // whatever else is already queued rides along
+				case j := <-b.jobs:
+					batch = append(batch, j)
+					nseq += len(j.seqs)
+				default:
+					break collect
+				}
+			}
+		}
+		timer.Stop()
+		expect = len(batch)
+		flat := make([][]int32, 0, nseq)
+		for _, j := range batch {
+			flat = append(flat, j.seqs...)
+		}
+		vecs, err := b.rt.Embed(flat)
+		if err != nil && len(batch) > 1 {
+			for _, j := range batch { // one bad sequence must not poison its neighbours: answer each request alone
+				v, e := b.rt.Embed(j.seqs)
+				j.done <- embedResult{vecs: v, err: e}
+			}
+			continue
+		}
+		k := 0
+		for _, j := range batch {
+			if err != nil {
+				j.done <- embedResult{err: err}
+				continue
+			}
+			j.done <- embedResult{vecs: vecs[k : k+len(j.seqs)]}
+			k += len(j.seqs)
+		}
+	}
 }
 
 func newOpenAIFront(rt *B200Runtime) (*openAIFront, error) {
@@ -41,7 +153,7 @@ func newOpenAIFront(rt *B200Runtime) (*openAIFront, error) {
 	if err != nil {
 		return nil, err
 	}
-	f := &openAIFront{rt: rt, tok: rt.p.Tokenizer, ln: ln}
+	f := &openAIFront{rt: rt, tok: rt.p.Tokenizer, ln: ln, embed: newEmbedBatcher(rt)}
 	mux := http.NewServeMux()
 	mux.HandleFunc("/v1/models", f.models)
 	mux.HandleFunc("/v1/chat/completions", f.chat)
@@ -55,7 +167,10 @@ func (f *openAIFront) URL() string { return "http://" + f.ln.Addr().String() }
 
 // Close stops accepting connections and closes the open ones; handlers notice through their request context and retire
 // their sequences (Generate cancels + releases) before B200Runtime.Stop destroys the engine.
-func (f *openAIFront) Close() { _ = f.srv.Close() }
+func (f *openAIFront) Close() {
+	_ = f.srv.Close()
+	f.embed.Close()
+}
 
 func randomID() string {
 	var b [12]byte
@@ -203,8 +318,7 @@ func (f *openAIFront) chat(w http.ResponseWriter, r *http.Request) {
 			st := &states[ci]
 			g := gp
 			g.Seed += uint64(ci)
-			var all []int32 // every generated id so far: text is decoded from the whole sequence (see emitStable)
-			emitted := 0
+			dec := &streamDecoder{tok: f.tok} // ids -> text without re-decoding the whole generation at every poll
 			pending := ""  // decoded text not yet released because it may be the beginning of a stop string
 			stopped := false
 			release := func(text string, final bool) (string, bool) { // -> text that may be shown now, stop hit?
@@ -243,7 +357,7 @@ func (f *openAIFront) chat(w http.ResponseWriter, r *http.Request) {
 					}
 				}
 				st.n += len(ids)
-				all = append(all, dropToken(ids, f.tok.EOS())...)
+				fresh := dropToken(ids, f.tok.EOS())
 				for _, lp := range lps {
 					e := openai.LogProb{Token: f.tok.Decode(lp.IDs[:1]), LogProb: float64(lp.LogProbs[0])}
 					for k := 1; k < len(lp.IDs); k++ {
@@ -253,9 +367,9 @@ func (f *openAIFront) chat(w http.ResponseWriter, r *http.Request) {
 					}
 					st.lps = append(st.lps, e)
 				}
-				// A character whose bytes / pieces straddle two polls must come out whole: decode everything, release only
-				// the new stable suffix, hold back a trailing U+FFFD.  Mirrors server.py StreamDecoder + StopMatcher.
-				text, hit := release(emitStable(f.tok.Decode(all), &emitted, false), false)
+				// A character whose bytes / pieces straddle two polls must come out whole (streamDecoder holds an unfinished
+				// one back); text that may still become a stop string is held by release().  Mirrors server.py.
+				text, hit := release(dec.feed(fresh, false), false)
 				st.text += text
 				if req.Stream && text != "" {
 					if err := sendSSE(chunk(ci, openai.ChatCompletionStreamChoiceDelta{Content: text}, "")); err != nil {
@@ -275,7 +389,7 @@ func (f *openAIFront) chat(w http.ResponseWriter, r *http.Request) {
 				return
 			}
 			if !stopped {
-				tail, _ := release(emitStable(f.tok.Decode(all), &emitted, true), true)
+				tail, _ := release(dec.feed(nil, true), true)
 				st.text += tail
 				if req.Stream && tail != "" {
 					_ = sendSSE(chunk(ci, openai.ChatCompletionStreamChoiceDelta{Content: tail}, ""))
@@ -338,9 +452,7 @@ func (f *openAIFront) embeddings(w http.ResponseWriter, r *http.Request) {
 		jsonError(w, http.StatusBadRequest, "invalid_request_error", err.Error())
 		return
 	}
-	// one hb_embed call per request (a micro-batcher in front of this coalesces the RAG caller's 1-chunk requests,
-	// helix_b200/server.py EmbedBatcher)
-	vecs, err := f.rt.Embed(seqs)
+	vecs, err := f.embed.Embed(seqs) // coalesced with the other requests in flight (embedBatcher)
 	if err != nil {
 		jsonError(w, http.StatusBadRequest, "invalid_request_error", err.Error())
 		return
@@ -357,19 +469,49 @@ func (f *openAIFront) embeddings(w http.ResponseWriter, r *http.Request) {
 	_ = json.NewEncoder(w).Encode(resp)
 }
 
-// emitStable returns the part of `decoded` not yet released; unless `final`, one trailing replacement rune stays held.
-func emitStable(decoded string, emitted *int, final bool) string {
-	r := []rune(decoded)
-	stable := len(r)
-	if !final && stable > 0 && r[stable-1] == '\uFFFD' {
-		stable--
-	}
-	if stable <= *emitted {
+// streamDecoder turns token ids into text for streaming.  Decoding each poll's ids alone garbles a character whose
+// bytes / pieces straddle two polls, decoding the whole sequence at every poll is quadratic in the length of the answer:
+// the ids not yet shown are decoded together with the previously shown batch as left context, that context's text is cut
+// off the front, and an unfinished character (a trailing U+FFFD, at most its last three tokens) is held back unless the
+// stream has ended.  Same algorithm as helix_b200/server.py StreamDecoder (fuzzed there against whole-sequence decoding).
+type streamDecoder struct {
+	tok     Tokenizer
+	ids     []int32
+	ctxOff  int // first id of the left context
+	readOff int // ids before this index have been shown
+}
+
+func (d *streamDecoder) feed(ids []int32, final bool) string {
+	d.ids = append(d.ids, ids...)
+	n := len(d.ids)
+	if d.readOff == n {
 		return ""
 	}
-	out := string(r[*emitted:stable])
-	*emitted = stable
-	return out
+	ctx := d.tok.Decode(d.ids[d.ctxOff:d.readOff])
+	cut := func(text string, upTo int) string {
+		d.ctxOff, d.readOff = d.readOff, upTo
+		if len(text) < len(ctx) {
+			return ""
+		}
+		return text[len(ctx):]
+	}
+	maxHold := n - d.readOff
+	if maxHold > 4 {
+		maxHold = 4
+	}
+	if final {
+		maxHold = 1
+	}
+	for hold := 0; hold < maxHold; hold++ {
+		text := d.tok.Decode(d.ids[d.ctxOff : n-hold])
+		if final || (!strings.HasSuffix(text, "\uFFFD") && len(text) > len(ctx)) {
+			return cut(text, n-hold)
+		}
+	}
+	if n-d.readOff > 8 { // not an unfinished character but invalid bytes: nothing later will repair them
+		return cut(d.tok.Decode(d.ids[d.ctxOff:]), n)
+	}
+	return ""
 }
 
 func writeSSE(w http.ResponseWriter, fl http.Flusher, v any) error {
