@@ -466,10 +466,13 @@ class OpenAIServer:
                 self.send_header("Content-Type", "application/json")
                 self.send_header("Content-Length", str(len(data)))
                 # one send for headers + body (end_headers() would flush the header block on its own)
-                self._headers_buffer.append(b"\r\n")
-                head = b"".join(self._headers_buffer)
-                self._headers_buffer = []
-                self.wfile.write(head + data)
+                pending = getattr(self, "_headers_buffer", None)
+                if isinstance(pending, list) and pending:
+                    self._headers_buffer = []
+                    self.wfile.write(b"".join(pending) + b"\r\n" + data)
+                else:   # a stdlib whose handler buffers differently: two sends, still correct (TCP_NODELAY is set)
+                    self.end_headers()
+                    self.wfile.write(data)
 
             def do_GET(self):
                 if self.path.rstrip("/") in ("/v1/models", "/models"):
